@@ -1,0 +1,115 @@
+"""Pins the float64 oracle (oracle/avse_oracle.py) with independent cross-checks.
+
+The reference ships no golden vectors and librosa/mediaio are
+not installable here, so the oracle is pinned against torch.stft / torch.istft,
+torchaudio's Slaney filterbank and algebraic identities instead.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avse_oracle as O
+
+SR, NFFT, HOP = 16000, 640, 160
+
+
+def _sig(n, seed=0):
+    return O.synth_speech(n, SR, seed) + O.synth_noise(n, seed)
+
+
+def test_stft_matches_torch():
+    y = _sig(48000, 1)
+    D = O.stft(y, NFFT, HOP)
+    assert D.shape == (321, 301)
+    ref = torch.stft(torch.from_numpy(y), NFFT, HOP, window=torch.hann_window(NFFT, periodic=True, dtype=torch.float64),
+                     center=True, pad_mode="reflect", return_complex=True).numpy()
+    assert np.max(np.abs(D - ref)) < 1e-11
+
+
+def test_istft_roundtrip_and_torch():
+    y = _sig(48000, 2)
+    D = O.stft(y, NFFT, HOP)
+    yr = O.istft(D, HOP)
+    assert yr.shape == (48000,)
+    assert np.max(np.abs(yr - y)) < 1e-12
+    ref = torch.istft(torch.from_numpy(D), NFFT, HOP, window=torch.hann_window(NFFT, periodic=True, dtype=torch.float64),
+                      center=True).numpy()
+    assert np.max(np.abs(yr - ref)) < 1e-12
+
+
+def test_istft_length_and_wss_edges():
+    # dp:68-70 feeds 300 of 301 frames -> hop*(T-1) = 47840 samples
+    D = O.stft(_sig(48000, 3), NFFT, HOP)[:, :300]
+    assert O.istft(D, HOP).shape == (47840,)
+    wss = O.window_sumsquare(300, NFFT, HOP)[NFFT // 2:-(NFFT // 2)]
+    assert abs(wss[0] - 1.25) < 1e-12 and abs(wss[HOP] - 1.5) < 1e-12 and abs(wss[-1] - wss[1]) < 1e-9
+    assert np.allclose(wss[HOP:-HOP], 1.5)
+
+
+def test_mel_filterbank_matches_torchaudio():
+    torchaudio = pytest.importorskip("torchaudio")
+    fb = O.mel_filterbank(SR, NFFT, 80, 0.0, 8000.0)
+    ref = torchaudio.functional.melscale_fbanks(321, 0.0, 8000.0, 80, SR, norm="slaney", mel_scale="slaney").numpy().T
+    assert fb.shape == (80, 321)
+    assert np.max(np.abs(fb - ref)) < 2e-7  # torchaudio builds it in float32
+
+
+def test_mel_filterbank_structure():
+    fb = O.mel_filterbank(SR, NFFT, 80, 0.0, 8000.0)
+    assert np.count_nonzero(fb) == 625
+    assert np.count_nonzero(fb, axis=0).max() <= 2
+    assert np.all(fb[:, 0] == 0) and np.all(fb[:, 320] == 0)
+    G = fb @ fb.T
+    off = G - np.diag(np.diag(G)) - np.diag(np.diag(G, 1), 1) - np.diag(np.diag(G, -1), -1)
+    assert np.max(np.abs(off)) == 0.0
+    P = np.linalg.pinv(fb)
+    assert np.max(np.abs(fb @ P - np.eye(80))) < 1e-10
+    assert np.max(np.abs(P - fb.T @ np.linalg.inv(G))) < 1e-10
+
+
+def test_amplitude_db_roundtrip_and_floor():
+    S = np.abs(np.random.RandomState(0).randn(80, 50)) * 10.0
+    S[3, 4] = 0.0
+    db = O.amplitude_to_db(S)
+    assert db.max() - db.min() <= 80.0 + 1e-12
+    keep = db > db.max() - 80.0
+    assert np.allclose(O.db_to_amplitude(db)[keep], S[keep], rtol=1e-12)
+
+
+def test_magphase_zero_convention():
+    D = np.array([[0.0 + 0.0j, 3.0 + 4.0j]])
+    mag, ph = O.magphase(D)
+    assert ph[0, 0] == 1.0 + 0.0j and abs(ph[0, 1] - (0.6 + 0.8j)) < 1e-15 and mag[0, 1] == 5.0
+
+
+def test_pair_shapes_and_snr():
+    n = 48000
+    s = O.AudioSignal(np.round(O.synth_speech(n, SR, 5) * 32767).astype(np.int16), SR)
+    nz = O.AudioSignal(np.round(O.synth_noise(17000, 5) * 32767).astype(np.int16), SR)  # shorter: exercises dp:125-128
+    mixed, speech, noise, mixed_sig = O.preprocess_audio_pair_signals(s, nz, 200, 15, 25.0)
+    assert mixed.shape == speech.shape == noise.shape == (15, 80, 20)
+    assert mixed_sig.get_number_of_samples() == 48000
+    # 0 dB SNR: speech and scaled noise have equal variance
+    sp = O.AudioSignal(np.round(O.synth_speech(n, SR, 5) * 32767).astype(np.int16), SR)
+    nn = O.fit_noise_to_speech(O.AudioSignal(np.round(O.synth_noise(17000, 5) * 32767).astype(np.int16), SR), sp)
+    f = O.AudioMixer.snr_factor(sp, nn, 0)
+    assert abs(np.var(nn.get_data() * f) / np.var(sp.get_data().astype(float)) - 1.0) < 1e-12
+
+
+def test_slices_reassemble():
+    a = O.AudioSignal(_sig(50000, 7), SR)
+    sl = O.preprocess_audio_signal(a, 200, 15, 25.0)
+    assert a.get_number_of_samples() == 48000  # truncated in place (dp:42)
+    full, _ = O.signal_to_spectrogram(a, NFFT, HOP)
+    assert full.shape == (80, 301)
+    assert np.array_equal(np.concatenate(list(sl), axis=1), full[:, :300])
+
+
+def test_reconstruct_roundtrip_quality():
+    a = O.AudioSignal(_sig(48000, 8), SR)
+    sl = O.preprocess_audio_signal(a, 200, 15, 25.0)
+    rec = O.reconstruct_speech_signal(a, sl, 25.0)
+    assert rec.get_number_of_samples() == 47840
+    x = a.get_data()[:47840]
+    err = rec.get_data() - x
+    assert np.sqrt(np.mean(err ** 2)) / np.sqrt(np.mean(x ** 2)) < 0.5  # mel round trip is lossy but close
