@@ -1,0 +1,43 @@
+// Shared constants and host/device qualifiers for the B200 spectral front/back end.
+//
+// The path mirrors /root/reference/data_processor.py:35-139 at the reference's hard-coded
+// geometry (dp:44-45, dp:83-89): 16 kHz / 25 fps -> n_fft = 640 (= 2^7 * 5), hop = 160,
+// 321 bins, 80 Slaney mel bands, 200 ms slices = 20 spectrogram frames.
+#pragma once
+
+#if defined(__CUDACC__)
+#define AVSE_HD __host__ __device__ __forceinline__
+#else
+#define AVSE_HD inline
+#endif
+
+namespace avse {
+
+constexpr int NFFT = 640;            // dp:44   int(16000 / 25)
+constexpr int HOP = 160;             // dp:45   int(n_fft / 4)
+constexpr int NBINS = NFFT / 2 + 1;  // 321
+constexpr int NMEL = 80;             // dp:86
+constexpr int HALF = NFFT / 2;       // reflect-pad width of librosa.stft(center=True)
+
+// FFT-640 factorisation: n = 40*n1 + n2, k = k1 + 16*k2  (DFT-16, twiddle, DFT-40 = 5 x 8 PFA)
+constexpr int N1 = 16;
+constexpr int N2 = 40;
+
+// One warp owns a group of 4 consecutive STFT frames.
+constexpr int FPG = 4;
+// Shared-memory frame buffer: 16 rows (k1) x 84 floats (40 complex + 2 pad) + 16 floats skew.
+constexpr int ROW_F = 84;
+constexpr int FRAME_F = N1 * ROW_F + 16;  // 1360 floats, == 16 (mod 32), multiple of 4
+constexpr int MEL_STAGE_F = 3 * NMEL * FPG;  // raw mel sums [sig][band][frame]
+constexpr int WARP_SMEM_F = FPG * FRAME_F + MEL_STAGE_F;  // 6400 floats = 25600 B per warp
+
+// mel tables
+constexpr int MEL_WMAX = 24;    // max bins per band supported (reference config: 23)
+constexpr int MEL_WROW = 25;    // padded row stride of the weight table (bank spread)
+constexpr int MEL_ROUNDS = NMEL / 8;
+constexpr int POST_CHUNK = 41;  // bins per lane in the pointwise post stage (8 lanes x 41 >= 321)
+
+constexpr float AMIN = 1e-5f;   // librosa.amplitude_to_db amin (dp:94)
+constexpr float TOP_DB = 80.0f; // librosa.amplitude_to_db top_db (dp:94)
+
+}  // namespace avse

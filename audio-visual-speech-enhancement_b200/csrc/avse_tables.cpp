@@ -1,0 +1,137 @@
+// See avse_tables.h.  Float64 throughout; rounded to float32 once at the end.
+#include "avse_tables.h"
+
+#include <cmath>
+#include <algorithm>
+
+namespace avse {
+
+namespace {
+
+const double kPi = 3.14159265358979323846;
+
+// librosa.hz_to_mel / mel_to_hz, htk=False (Slaney): linear below 1 kHz, log above.
+double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+}  // namespace
+
+bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
+    t.sample_rate = sample_rate;
+    t.fmin = fmin;
+    t.fmax = fmax;
+    t.error.clear();
+
+    // periodic Hann: scipy.signal.get_window('hann', n_fft, fftbins=True)
+    t.window.resize(NFFT);
+    for (int n = 0; n < NFFT; ++n) t.window[n] = (float)(0.5 - 0.5 * std::cos(2.0 * kPi * n / NFFT));
+
+    // pass-1 twiddles W_640^{n2*k1} = exp(-2 pi i n2 k1 / 640), layout [k1][n2]
+    t.tw1t.resize(N1 * N2 * 2);
+    for (int k1 = 0; k1 < N1; ++k1)
+        for (int n2 = 0; n2 < N2; ++n2) {
+            const int e = (n2 * k1) % NFFT;
+            const double a = -2.0 * kPi * e / NFFT;
+            t.tw1t[(k1 * N2 + n2) * 2 + 0] = (float)std::cos(a);
+            t.tw1t[(k1 * N2 + n2) * 2 + 1] = (float)std::sin(a);
+        }
+
+    // librosa.filters.mel(sr, n_fft, n_mels=80, fmin, fmax), htk=False, norm=1 (Slaney)
+    std::vector<double> mel_f(NMEL + 2);
+    {
+        const double m0 = hz_to_mel(fmin), m1 = hz_to_mel(fmax);
+        for (int j = 0; j < NMEL + 2; ++j) mel_f[j] = mel_to_hz(m0 + (m1 - m0) * j / (NMEL + 1));
+    }
+    t.fb.assign((size_t)NMEL * NBINS, 0.0);
+    for (int m = 0; m < NMEL; ++m) {
+        const double fd0 = mel_f[m + 1] - mel_f[m], fd1 = mel_f[m + 2] - mel_f[m + 1];
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        for (int k = 0; k < NBINS; ++k) {
+            const double fk = (double)sample_rate / 2.0 * k / (NBINS - 1);  // np.linspace(0, sr/2, 321)
+            const double lower = -(mel_f[m] - fk) / fd0;
+            const double upper = (mel_f[m + 2] - fk) / fd1;
+            t.fb[(size_t)m * NBINS + k] = std::max(0.0, std::min(lower, upper)) * enorm;
+        }
+        // A bin that sits exactly on a mel point (e.g. bin 320 = fmax) has weight 0 in exact
+        // arithmetic; libm rounding can leave ~1e-16.  Snap those to 0 so the support is exact.
+        double rmax = 0.0;
+        for (int k = 0; k < NBINS; ++k) rmax = std::max(rmax, t.fb[(size_t)m * NBINS + k]);
+        for (int k = 0; k < NBINS; ++k)
+            if (t.fb[(size_t)m * NBINS + k] < 1e-10 * rmax) t.fb[(size_t)m * NBINS + k] = 0.0;
+    }
+
+    // banded form
+    t.mel_lo.assign(NMEL, 0);
+    t.mel_width.assign(NMEL, 0);
+    t.mel_w.assign((size_t)NMEL * MEL_WROW, 0.0f);
+    t.mel_roundw.assign(MEL_ROUNDS, 0);
+    for (int m = 0; m < NMEL; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < NBINS; ++k)
+            if (t.fb[(size_t)m * NBINS + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+        if (lo < 0) { t.error = "empty mel band (unsupported sr/fmin/fmax for n_fft=640, n_mels=80)"; return false; }
+        for (int k = lo; k <= hi; ++k)
+            if (t.fb[(size_t)m * NBINS + k] == 0.0) { t.error = "mel band support not contiguous"; return false; }
+        const int w = hi - lo + 1;
+        if (w > MEL_WMAX) { t.error = "mel band wider than MEL_WMAX"; return false; }
+        if (lo < 1 || hi > NBINS - 2) { t.error = "mel band touches DC/Nyquist bin (unsupported by the packed-FFT post stage)"; return false; }
+        t.mel_lo[m] = lo;
+        t.mel_width[m] = w;
+        for (int j = 0; j < w; ++j) t.mel_w[(size_t)m * MEL_WROW + j] = (float)(0.5 * t.fb[(size_t)m * NBINS + lo + j]);
+        t.mel_roundw[m / 8] = std::max(t.mel_roundw[m / 8], w);
+    }
+
+    // column form (<= 2 non-zeros per bin) for lin = F^T y
+    t.col_band.assign((size_t)NBINS * 2, 0);
+    t.col_w.assign((size_t)NBINS * 2, 0.0f);
+    for (int k = 0; k < NBINS; ++k) {
+        int c = 0;
+        for (int m = 0; m < NMEL; ++m) {
+            const double w = t.fb[(size_t)m * NBINS + k];
+            if (w != 0.0) {
+                if (c == 2) { t.error = "filterbank column with more than 2 non-zeros"; return false; }
+                t.col_band[k * 2 + c] = m;
+                t.col_w[k * 2 + c] = (float)w;
+                ++c;
+            }
+        }
+    }
+
+    // G = F F^T must be tridiagonal; Thomas factors in float64
+    std::vector<double> diag(NMEL), sub(NMEL, 0.0), sup(NMEL, 0.0);
+    for (int a = 0; a < NMEL; ++a)
+        for (int b = 0; b < NMEL; ++b) {
+            double g = 0.0;
+            for (int k = 0; k < NBINS; ++k) g += t.fb[(size_t)a * NBINS + k] * t.fb[(size_t)b * NBINS + k];
+            if (a == b) diag[a] = g;
+            else if (b == a + 1) sup[a] = g;
+            else if (b == a - 1) sub[a] = g;
+            else if (g != 0.0) { t.error = "F F^T is not tridiagonal"; return false; }
+        }
+    t.tri_w.assign(NMEL, 0.0f);
+    t.tri_ipiv.assign(NMEL, 0.0f);
+    t.tri_sup.assign(NMEL, 0.0f);
+    std::vector<double> piv(NMEL);
+    piv[0] = diag[0];
+    for (int i = 1; i < NMEL; ++i) {
+        const double w = sub[i] / piv[i - 1];
+        piv[i] = diag[i] - w * sup[i - 1];
+        t.tri_w[i] = (float)w;
+    }
+    for (int i = 0; i < NMEL; ++i) {
+        if (!(piv[i] > 0.0)) { t.error = "F F^T not positive definite"; return false; }
+        t.tri_ipiv[i] = (float)(1.0 / piv[i]);
+        t.tri_sup[i] = (float)sup[i];
+    }
+    return true;
+}
+
+}  // namespace avse

@@ -1,0 +1,40 @@
+// Host-side (float64) construction of the constant tables the kernels read:
+// periodic Hann window, pass-1 twiddles, the Slaney mel filterbank in banded form, and the
+// structured pseudo-inverse (pinv(F) = F^T (F F^T)^-1 with F F^T tridiagonal).
+// Restates librosa.filters.mel / get_window as used at /root/reference/data_processor.py:79-89,
+// :104-112 (library semantics: SURVEY.md Appendix A.1).  Plain C++, no CUDA.
+#pragma once
+#include <vector>
+#include <string>
+#include "avse_common.h"
+
+namespace avse {
+
+struct HostTables {
+    int sample_rate = 16000;
+    double fmin = 0.0, fmax = 8000.0;
+
+    std::vector<float> window;        // [640]   periodic Hann
+    std::vector<float> tw1t;          // [16][40][2]  W_640^{n2*k1}, k1-major (re, im)
+    std::vector<double> fb;           // [80][321]  dense filterbank (float64, for tests/inverse)
+    std::vector<int> mel_lo;          // [80]  first non-zero bin of each band
+    std::vector<int> mel_width;       // [80]  number of non-zero bins
+    std::vector<float> mel_w;         // [80][MEL_WROW]  0.5 * weight (0.5 = packed-FFT unpack factor)
+    std::vector<int> mel_roundw;      // [10]  max width over bands 8r..8r+7
+
+    // inverse path
+    std::vector<float> tri_w;         // [80] Thomas forward multipliers (w[0] unused)
+    std::vector<float> tri_ipiv;      // [80] 1 / pivot
+    std::vector<float> tri_sup;       // [80] super-diagonal (sup[79] unused)
+    std::vector<int> col_band;        // [321][2] band index of the (<=2) non-zeros in column k (or 0)
+    std::vector<float> col_w;         // [321][2] their weights (0 when absent)
+
+    std::string error;                // non-empty when the configuration is unsupported
+};
+
+// Fills all tables.  Returns false (and sets t.error) when the configuration cannot be
+// represented in banded form (empty band, band wider than MEL_WMAX, column with > 2 non-zeros,
+// F F^T not tridiagonal).
+bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax);
+
+}  // namespace avse

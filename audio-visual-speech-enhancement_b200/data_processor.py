@@ -1,0 +1,272 @@
+"""Drop-in mirror of the audio half of /root/reference/data_processor.py.
+
+Same function names, positional arguments, return shapes and in-place mutation semantics as the
+reference (cited as dp:LINE), but every spectrogram / reconstruction is computed by the CUDA
+library through `engine.SpectralEngine`.  Batched entry points (`preprocess_audio_pairs`,
+`preprocess_data`) replace the reference's `multiprocess.Pool(16)` fan-out (dp:189-198): CUDA
+work is batched in the parent process, one launch over many utterances.
+
+Out of scope here: the video front end (dp:12-32) and VideoNormalizer
+(dp:201-212).  `preprocess_sample` takes the video slices from a caller-supplied callable.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .engine import SpectralEngine, geometry, fit_noise, N_FFT, HOP, N_BINS, N_MELS, SPSS
+from .mediaio_compat import AudioSignal, AudioMixer
+
+_engines = {}
+
+
+def get_engine(sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, device=None):
+    """One cached SpectralEngine per (sample_rate, fps, slice_ms, device)."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    key = (int(sample_rate), float(video_frame_rate), slice_duration_ms, dev)
+    if key not in _engines:
+        _engines[key] = SpectralEngine(sample_rate, video_frame_rate, slice_duration_ms, device="cuda:%d" % dev)
+    return _engines[key]
+
+
+def _mono_f32(audio_signal):
+    data = audio_signal.get_data(channel_index=0)  # dp:78
+    return np.ascontiguousarray(data, dtype=np.float32)
+
+
+def _to_dev(x, eng):
+    return torch.from_numpy(x).to(eng.device, non_blocking=True)
+
+
+# --------------------------------------------------------------------------------------------
+# dp:77-96
+# --------------------------------------------------------------------------------------------
+def signal_to_spectrogram(audio_signal, n_fft, hop_length, mel=True, db=True):
+    """dp:77-96.  Returns (magnitude (80|321, T) float32, phase (321, T) complex64)."""
+    if (n_fft, hop_length) != (N_FFT, HOP):
+        raise NotImplementedError("only n_fft=640 / hop_length=160 (the reference's 16 kHz / 25 fps geometry)")
+    eng = get_engine(audio_signal.get_sample_rate(), audio_signal.get_sample_rate() / float(n_fft))
+    x = _to_dev(_mono_f32(audio_signal), eng)
+    db_mel, D = eng.spectrogram(x, stft=True)
+    D = D[0].transpose(0, 1)  # (321, T)
+    mag = D.abs()
+    zeros = mag == 0
+    phase = D / (mag + zeros) + zeros  # librosa.magphase: 1+0j where D == 0 (dp:80)
+    if mel and db:
+        magnitude = db_mel[0]
+    else:
+        # non-default flag combinations are not on the reference's call paths (dp:47, dp:64 always
+        # pass mel=True, db=True); they are served from the complex STFT with torch glue.
+        magnitude = mag
+        if mel:
+            magnitude = torch.from_numpy(eng.filterbank()).to(mag.device, torch.float32) @ magnitude
+        if db:
+            magnitude = 20.0 * torch.log10(torch.clamp(magnitude, min=1e-5))
+            magnitude = torch.maximum(magnitude, magnitude.max() - 80.0)
+    return magnitude.cpu().numpy(), phase.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# dp:35-57
+# --------------------------------------------------------------------------------------------
+def preprocess_audio_signal(audio_signal, slice_duration_ms, n_video_slices, video_frame_rate):
+    """dp:35-57.  Mutates audio_signal (pad/truncate, dp:39-42) and returns (n, 80, 20) float32."""
+    samples_per_slice = int((float(slice_duration_ms) / 1000) * audio_signal.get_sample_rate())
+    signal_length = samples_per_slice * n_video_slices
+    if audio_signal.get_number_of_samples() < signal_length:
+        audio_signal.pad_with_zeros(signal_length)
+    else:
+        audio_signal.truncate(signal_length)
+    eng = get_engine(audio_signal.get_sample_rate(), video_frame_rate, slice_duration_ms)
+    x = _to_dev(_mono_f32(audio_signal), eng)
+    return eng.preprocess_signals(x, n_video_slices)[0].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# dp:60-74, dp:99-116
+# --------------------------------------------------------------------------------------------
+def reconstruct_speech_signal(mixed_signal, speech_spectrograms, video_frame_rate):
+    """dp:60-74.  speech_spectrograms: (n, 80, 20) dB slices.  Returns AudioSignal (float32 data)."""
+    eng = get_engine(mixed_signal.get_sample_rate(), video_frame_rate)
+    spec = np.asarray(speech_spectrograms, dtype=np.float32)
+    if spec.ndim != 3 or spec.shape[1:] != (N_MELS, SPSS):
+        raise ValueError("speech_spectrograms must have shape (n_slices, 80, 20)")
+    pcm = _to_dev(_mono_f32(mixed_signal), eng)
+    out = eng.reconstruct(pcm, _to_dev(np.ascontiguousarray(spec), eng))
+    return AudioSignal(out[0].cpu().numpy(), mixed_signal.get_sample_rate())
+
+
+def reconstruct_signal_from_spectrogram(magnitude, phase, sample_rate, n_fft, hop_length, mel=True, db=True):
+    """dp:99-116 with an explicit phase array (321, T).  Returns AudioSignal."""
+    if (n_fft, hop_length) != (N_FFT, HOP) or not (mel and db):
+        raise NotImplementedError("only the reference's call form: n_fft=640, hop=160, mel=True, db=True")
+    eng = get_engine(sample_rate, sample_rate / float(n_fft))
+    mag = np.ascontiguousarray(np.asarray(magnitude, dtype=np.float32))
+    ph = np.ascontiguousarray(np.asarray(phase).astype(np.complex64).T)  # frame-major (T, 321)
+    out = eng.reconstruct_with_phase(_to_dev(mag, eng).unsqueeze(0), _to_dev(ph, eng).unsqueeze(0))
+    return AudioSignal(out[0].cpu().numpy(), sample_rate)
+
+
+# --------------------------------------------------------------------------------------------
+# dp:119-139
+# --------------------------------------------------------------------------------------------
+def _fit_noise_np(noise, n_speech):
+    """dp:125-128: double until long enough, truncate == periodic tiling."""
+    n = noise.shape[0]
+    if n < n_speech:
+        noise = noise[np.arange(n_speech) % n]
+    return noise[:n_speech]
+
+
+def preprocess_audio_pair_signals(speech_signal, noise_signal, slice_duration_ms, n_video_slices, video_frame_rate, snr_db=0):
+    """dp:125-139 on in-memory AudioSignal objects.  Mutates speech_signal (pad/truncate, dp:136) like the
+    reference; returns (mixed_slices, speech_slices, noise_slices, mixed_signal)."""
+    out = preprocess_audio_pairs([speech_signal], [noise_signal], slice_duration_ms, [n_video_slices], video_frame_rate,
+                                 snr_db=[snr_db])
+    return out[0]
+
+
+def preprocess_audio_pair(speech_file_path, noise_file_path, slice_duration_ms, n_video_slices, video_frame_rate):
+    """dp:119-139 (same positional signature)."""
+    print("preprocessing pair: %s, %s" % (speech_file_path, noise_file_path))
+    speech_signal = AudioSignal.from_wav_file(speech_file_path)
+    noise_signal = AudioSignal.from_wav_file(noise_file_path)
+    return preprocess_audio_pair_signals(speech_signal, noise_signal, slice_duration_ms, n_video_slices, video_frame_rate)
+
+
+def preprocess_audio_pairs(speech_signals, noise_signals, slice_duration_ms, n_video_slices, video_frame_rate, snr_db=None):
+    """Batched dp:119-139: lists of AudioSignal -> list of (mixed, speech, noise slices, mixed AudioSignal).
+
+    Utterances are bucketed by n_video_slices (equal signal_length) and each bucket is one launch."""
+    sr = speech_signals[0].get_sample_rate()
+    eng = get_engine(sr, video_frame_rate, slice_duration_ms)
+    results = [None] * len(speech_signals)
+    buckets = {}
+    for i, nvs in enumerate(n_video_slices):
+        buckets.setdefault(int(nvs), []).append(i)
+    for nvs, idxs in buckets.items():
+        L = eng.samples_per_slice * nvs
+        sp = [_mono_f32(speech_signals[i]) for i in idxs]
+        width = max(max(len(s) for s in sp), 1)
+        S = np.zeros((len(idxs), width), dtype=np.float32)
+        N = np.zeros((len(idxs), width), dtype=np.float32)
+        lens = np.zeros(len(idxs), dtype=np.int32)
+        for r, i in enumerate(idxs):
+            S[r, :len(sp[r])] = sp[r]
+            N[r, :len(sp[r])] = _fit_noise_np(_mono_f32(noise_signals[i]), len(sp[r]))
+            lens[r] = len(sp[r])
+        snr = None
+        if snr_db is not None:
+            snr = _to_dev(np.asarray([snr_db[i] for i in idxs], dtype=np.float32), eng)
+        mixed, speech, noise, pcm = eng.preprocess_pairs(_to_dev(S, eng), _to_dev(N, eng), nvs, lengths=_to_dev(lens, eng), snr_db=snr)
+        mixed, speech, noise, pcm = mixed.cpu().numpy(), speech.cpu().numpy(), noise.cpu().numpy(), pcm.cpu().numpy()
+        for r, i in enumerate(idxs):
+            # observable mutation of the reference: speech padded/truncated in place (dp:136 -> dp:39-42)
+            if speech_signals[i].get_number_of_samples() < L:
+                speech_signals[i].pad_with_zeros(L)
+            else:
+                speech_signals[i].truncate(L)
+            results[i] = (mixed[r], speech[r], noise[r], AudioSignal(pcm[r], sr))
+    return results
+
+
+# --------------------------------------------------------------------------------------------
+# dp:142-198 sample assembly and the batch driver
+# --------------------------------------------------------------------------------------------
+Sample = namedtuple('Sample', [
+    'speaker_id',
+    'video_file_path',
+    'speech_file_path',
+    'noise_file_path',
+    'video_samples',
+    'mixed_spectrograms',
+    'speech_spectrograms',
+    'noise_spectrograms',
+    'mixed_signal',
+    'video_frame_rate'
+])
+
+
+def assemble_sample(speech_entry, noise_file_path, video_samples, video_frame_rate, pair_result):
+    """dp:164-177: n_slices = min(video, audio); truncate the four arrays."""
+    mixed_spectrograms, speech_spectrograms, noise_spectrograms, mixed_signal = pair_result
+    n_slices = min(video_samples.shape[0], mixed_spectrograms.shape[0])
+    return Sample(
+        speaker_id=speech_entry.speaker_id,
+        video_file_path=speech_entry.video_path,
+        speech_file_path=speech_entry.audio_path,
+        noise_file_path=noise_file_path,
+        video_samples=video_samples[:n_slices],
+        mixed_spectrograms=mixed_spectrograms[:n_slices],
+        speech_spectrograms=speech_spectrograms[:n_slices],
+        noise_spectrograms=noise_spectrograms[:n_slices],
+        mixed_signal=mixed_signal,
+        video_frame_rate=video_frame_rate
+    )
+
+
+def preprocess_data(speech_entries, noise_file_paths, video_preprocessor, slice_duration_ms=200):
+    """dp:189-198 with the Pool(16) fan-out replaced by one batched GPU pass.
+
+    video_preprocessor(video_path, slice_duration_ms) -> (video_samples, fps) stands in for the
+    out-of-scope preprocess_video_sample (dp:12-32).  Samples whose video or audio loading fails are
+    dropped, like try_preprocess_sample (dp:180-186)."""
+    print("preprocessing data...")
+    staged = []
+    for entry, noise_path in zip(speech_entries, noise_file_paths):
+        try:
+            video_samples, fps = video_preprocessor(entry.video_path, slice_duration_ms)
+            speech = AudioSignal.from_wav_file(entry.audio_path)
+            noise = AudioSignal.from_wav_file(noise_path)
+            staged.append((entry, noise_path, video_samples, fps, speech, noise))
+        except Exception as e:  # dp:184-186
+            print("failed to preprocess %s (%s)" % ((entry, noise_path), e))
+    samples = []
+    by_fps = {}
+    for item in staged:
+        by_fps.setdefault(float(item[3]), []).append(item)
+    for fps, items in by_fps.items():
+        try:
+            res = preprocess_audio_pairs([it[4] for it in items], [it[5] for it in items], slice_duration_ms,
+                                         [it[2].shape[0] for it in items], fps)
+        except Exception as e:
+            print("failed to preprocess batch at %s fps (%s)" % (fps, e))
+            continue
+        for it, r in zip(items, res):
+            samples.append(assemble_sample(it[0], it[1], it[2], it[3], r))
+    return samples
+
+
+def make_sample_set(samples, permutation=None):
+    """speech_enhancer.py:241-262 (next row f1): concatenate slices over samples, one shared permutation."""
+    video = np.concatenate([s.video_samples for s in samples], axis=0)
+    mixed = np.concatenate([s.mixed_spectrograms for s in samples], axis=0)
+    speech = np.concatenate([s.speech_spectrograms for s in samples], axis=0)
+    perm = np.random.permutation(video.shape[0]) if permutation is None else np.asarray(permutation)
+    return video[perm], mixed[perm], speech[perm]
+
+
+class MelConverter(object):
+    """Facade named by BASELINE.json's north_star (the reference snapshot has free functions instead,
+    SURVEY.md section 0 item 2).  Signatures are this build's design."""
+
+    def __init__(self, sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200):
+        self.engine = get_engine(sample_rate, video_frame_rate, slice_duration_ms)
+        self.sample_rate = sample_rate
+        self.video_frame_rate = video_frame_rate
+        self.slice_duration_ms = slice_duration_ms
+
+    def signal_to_mel_spectrogram(self, audio_signal):
+        return signal_to_spectrogram(audio_signal, N_FFT, HOP, mel=True, db=True)[0]
+
+    def signal_to_slices(self, audio_signal, n_video_slices):
+        return preprocess_audio_signal(audio_signal, self.slice_duration_ms, n_video_slices, self.video_frame_rate)
+
+    def mix_pair(self, speech_signal, noise_signal, n_video_slices, snr_db=0):
+        return preprocess_audio_pair_signals(speech_signal, noise_signal, self.slice_duration_ms, n_video_slices,
+                                             self.video_frame_rate, snr_db=snr_db)
+
+    def reconstruct_signal_from_mel_spectrogram(self, mixed_signal, mel_slices):
+        return reconstruct_speech_signal(mixed_signal, mel_slices, self.video_frame_rate)

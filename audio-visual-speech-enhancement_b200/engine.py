@@ -1,0 +1,249 @@
+"""Batched, device-resident host mirror of the reference's spectral path.
+
+`SpectralEngine` owns one `avse_ctx` (constant tables on one GPU) and exposes the batched
+equivalents of /root/reference/data_processor.py:35-139 on torch CUDA tensors.  All arithmetic
+runs in libavse_b200.so (hand-written CUDA, sm_100a) through the C ABI; torch only supplies
+device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import ForwardArgs, InverseArgs, check
+
+N_FFT, HOP, N_BINS, N_MELS, SPSS = 640, 160, 321, 80, 20
+LAYOUT_SLICES, LAYOUT_SPEC = 0, 1
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def geometry(sample_rate, video_frame_rate, slice_duration_ms=200):
+    """dp:36, dp:44-45, dp:49 integer geometry."""
+    samples_per_slice = int((float(slice_duration_ms) / 1000) * sample_rate)
+    n_fft = int(float(sample_rate) / video_frame_rate)
+    hop = int(n_fft / 4)
+    spss = int(samples_per_slice / hop) if hop else 0
+    return samples_per_slice, n_fft, hop, spss
+
+
+class SpectralEngine(object):
+    """One GPU's worth of the spectral front/back end."""
+
+    def __init__(self, sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, fmin=0.0, fmax=8000.0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SpectralEngine needs a CUDA device: this framework has no CPU path")
+        sps, n_fft, hop, spss = geometry(sample_rate, video_frame_rate, slice_duration_ms)
+        if (n_fft, hop) != (N_FFT, HOP):
+            raise NotImplementedError(
+                "kernels are specialised for n_fft=640/hop=160 (sample_rate/fps = 640, the reference's 16 kHz / 25 fps); got n_fft=%d" % n_fft)
+        self.sample_rate = int(sample_rate)
+        self.video_frame_rate = float(video_frame_rate)
+        self.slice_duration_ms = slice_duration_ms
+        self.samples_per_slice = sps
+        self.spss = spss
+        if spss != SPSS:
+            raise NotImplementedError("slice_duration_ms must give 20 spectrogram frames per slice (200 ms at hop 160)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._lib = _native.load()
+        h = ctypes.c_void_p()
+        check(self._lib.avse_create(self.sample_rate, float(fmin), float(fmax), self.device.index or 0, ctypes.byref(h)), "avse_create")
+        self._ctx = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                self._lib.avse_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def filterbank(self):
+        """librosa.filters.mel(sr, 640, 80, fmin, fmax) as built by the library (float64 (80, 321))."""
+        fb = np.zeros((N_MELS, N_BINS), dtype=np.float64)
+        check(self._lib.avse_get_filterbank(self._ctx, fb.ctypes.data), "avse_get_filterbank")
+        return fb
+
+    def _as_batch(self, x):
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        return x
+
+    @staticmethod
+    def n_frames(L):
+        return 1 + L // HOP
+
+    # ------------------------------------------------------------------ a3: SNR factor
+    def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None):
+        """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], max_key[B,3])."""
+        speech, noise = self._as_batch(speech), self._as_batch(noise)
+        B, L = speech.shape
+        assert noise.shape == speech.shape and noise.stride(0) == speech.stride(0)
+        factor = torch.empty(B, dtype=torch.float32, device=self.device)
+        if max_key is None:
+            max_key = torch.empty((B, 3), dtype=torch.int32, device=self.device)
+        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), speech.stride(0), _ptr(lengths), B, L,
+                                        _ptr(snr_db), _ptr(factor), _ptr(max_key), self._stream()), "avse_snr_factor")
+        return factor, max_key
+
+    # ------------------------------------------------------------------ a1/a4/a5: forward
+    def forward_raw(self, speech, noise=None, L=None, len_speech=None, len_noise=None, factor=None, layout=LAYOUT_SLICES,
+                    n_slices=None, want=("speech", "noise", "mixed"), mixed_pcm=True, max_key=None, stft=False, out=None):
+        """Launch avse_forward.  Returns dict with un-floored outputs + max_key (see include/avse_b200.h)."""
+        speech = self._as_batch(speech)
+        B = speech.shape[0]
+        if L is None:
+            L = speech.shape[1]
+        if noise is not None:
+            noise = self._as_batch(noise)
+            assert noise.stride(0) == speech.stride(0) and noise.shape[0] == B
+        T = self.n_frames(L)
+        if n_slices is None:
+            n_slices = T // SPSS
+        res = {} if out is None else out
+        ld_t = (T + 3) // 4 * 4
+        shape = (B, n_slices, N_MELS, SPSS) if layout == LAYOUT_SLICES else (B, N_MELS, ld_t)
+        for name in ("speech", "noise", "mixed"):
+            if name in want and (name == "speech" or noise is not None):
+                if name not in res:
+                    res[name] = torch.empty(shape, dtype=torch.float32, device=self.device)
+            else:
+                res.setdefault(name, None)
+        if mixed_pcm and noise is not None:
+            if "mixed_pcm" not in res:
+                res["mixed_pcm"] = torch.empty((B, L), dtype=torch.float32, device=self.device)
+        else:
+            res.setdefault("mixed_pcm", None)
+        if max_key is None:
+            max_key = torch.empty((B, 3), dtype=torch.int32, device=self.device)
+            check(self._lib.avse_reset_max(self._ctx, _ptr(max_key), 3 * B, self._stream()), "avse_reset_max")
+        res["max_key"] = max_key
+        res["stft"] = torch.empty((B, T, N_BINS), dtype=torch.complex64, device=self.device) if stft else None
+        ref = res["speech"]
+        a = ForwardArgs()
+        a.speech, a.noise, a.in_stride = _ptr(speech), _ptr(noise), speech.stride(0)
+        a.len_speech, a.len_noise, a.factor = _ptr(len_speech), _ptr(len_noise), _ptr(factor)
+        a.B, a.L = B, L
+        a.layout, a.n_slices, a.ld_t = layout, n_slices, ld_t
+        a.out_speech, a.out_noise, a.out_mixed = _ptr(res["speech"]), _ptr(res["noise"]), _ptr(res["mixed"])
+        a.out_stride = ref.stride(0) if ref is not None else 0
+        a.mixed_pcm = _ptr(res["mixed_pcm"])
+        a.pcm_stride = res["mixed_pcm"].stride(0) if res["mixed_pcm"] is not None else 0
+        a.max_key = _ptr(max_key)
+        a.stft_speech = _ptr(res["stft"])
+        check(self._lib.avse_forward(self._ctx, ctypes.byref(a), self._stream()), "avse_forward")
+        res["T"], res["ld_t"], res["n_slices"], res["layout"] = T, ld_t, n_slices, layout
+        return res
+
+    def floor_(self, data, max_key, which):
+        """amplitude_to_db's top_db floor (dp:94), in place, per utterance."""
+        B = data.shape[0]
+        n = data[0].numel()
+        check(self._lib.avse_floor_inplace(self._ctx, _ptr(data), data.stride(0), n, B, _ptr(max_key), which, self._stream()),
+              "avse_floor_inplace")
+        return data
+
+    def floor_gather(self, spec, max_key, which, n_slices):
+        """dp:49-57: SPEC [B,80,ld_t] (un-floored) -> floored slices [B,n_slices,80,20]."""
+        B, _, ld_t = spec.shape
+        out = torch.empty((B, n_slices, N_MELS, SPSS), dtype=torch.float32, device=self.device)
+        check(self._lib.avse_floor_gather(self._ctx, _ptr(spec), spec.stride(0), ld_t, _ptr(out), out.stride(0), n_slices, B,
+                                          _ptr(max_key), which, self._stream()), "avse_floor_gather")
+        return out
+
+    def max_db(self, max_key):
+        out = torch.empty(max_key.shape, dtype=torch.float32, device=self.device)
+        check(self._lib.avse_max_db(self._ctx, _ptr(max_key), max_key.numel(), _ptr(out), self._stream()), "avse_max_db")
+        return out
+
+    # ------------------------------------------------------------------ batched reference-level operations
+    def preprocess_pairs(self, speech, noise, n_video_slices, lengths=None, snr_db=None, out=None):
+        """Batched preprocess_audio_pair (dp:119-139) on device tensors.
+
+        speech, noise: [B, >=max(lengths)] float32, noise already fitted to the speech length
+        (dp:125-128, see fit_noise).  Returns (mixed_slices, speech_slices, noise_slices, mixed_pcm)
+        with shapes [B, n, 80, 20] x3 and [B, L]; n = min(n_video_slices, int(T/20)) (dp:50, dp:164).
+        """
+        speech, noise = self._as_batch(speech), self._as_batch(noise)
+        L = self.samples_per_slice * int(n_video_slices)
+        T = self.n_frames(L)
+        n = min(int(n_video_slices), T // SPSS)
+        if lengths is None and speech.shape[1] != L:
+            lengths = torch.full((speech.shape[0],), speech.shape[1], dtype=torch.int32, device=self.device)
+        fl = None
+        if lengths is not None:
+            fl = lengths
+        # dp:130 variance is over the ORIGINAL speech length (before pad/truncate to L)
+        stats_L = speech.shape[1] if lengths is None else int(speech.shape[1])
+        factor, max_key = self.snr_factor(speech[:, :stats_L], noise[:, :stats_L], lengths=fl, snr_db=snr_db)
+        res = self.forward_raw(speech, noise, L=L, len_speech=fl, len_noise=fl, factor=factor, layout=LAYOUT_SLICES,
+                               n_slices=n, max_key=max_key, out=out)
+        self.floor_(res["speech"], max_key, 0)
+        self.floor_(res["noise"], max_key, 1)
+        self.floor_(res["mixed"], max_key, 2)
+        return res["mixed"], res["speech"], res["noise"], res["mixed_pcm"]
+
+    def spectrogram(self, signals, lengths=None, stft=False):
+        """Batched signal_to_spectrogram(mel=True, db=True) (dp:77-96): floored dB [B, 80, T] (+ complex STFT)."""
+        signals = self._as_batch(signals)
+        res = self.forward_raw(signals, None, len_speech=lengths, layout=LAYOUT_SPEC, want=("speech",), mixed_pcm=False, stft=stft)
+        self.floor_spec_(res["speech"], res["max_key"], 0, res["T"])
+        out = res["speech"][:, :, :res["T"]]
+        return (out, res["stft"]) if stft else out
+
+    def floor_spec_(self, spec, max_key, which, T):
+        # pad columns (>= T) are untouched garbage; floor the whole padded rows (harmless)
+        return self.floor_(spec, max_key, which)
+
+    def preprocess_signals(self, signals, n_video_slices, lengths=None):
+        """Batched preprocess_audio_signal (dp:35-57): [B, n, 80, 20] floored dB slices."""
+        signals = self._as_batch(signals)
+        L = self.samples_per_slice * int(n_video_slices)
+        if lengths is None and signals.shape[1] < L:
+            lengths = torch.full((signals.shape[0],), signals.shape[1], dtype=torch.int32, device=self.device)
+        T = self.n_frames(L)
+        n = T // SPSS
+        res = self.forward_raw(signals, None, L=L, len_speech=lengths, layout=LAYOUT_SLICES, n_slices=n, want=("speech",), mixed_pcm=False)
+        return self.floor_(res["speech"], res["max_key"], 0)
+
+    def reconstruct(self, mixed_pcm, mel_slices, lengths=None):
+        """Batched reconstruct_speech_signal (dp:60-74): mixture PCM [B, L] + dB slices [B, n, 80, 20] -> PCM [B, 160*(min(20n, T)-1)]."""
+        if not hasattr(self._lib, "avse_inverse"):
+            raise RuntimeError("libavse_b200.so was built without avse_inverse")
+        mixed_pcm = self._as_batch(mixed_pcm)
+        mel = mel_slices if mel_slices.dtype == torch.float32 else mel_slices.to(torch.float32)
+        if mel.dim() == 3:
+            mel = mel.unsqueeze(0)
+        mel = mel.contiguous()
+        B, L = mixed_pcm.shape
+        n = mel.shape[1]
+        T_use = min(SPSS * n, self.n_frames(L))
+        out_len = HOP * (T_use - 1)
+        out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
+        a = InverseArgs()
+        a.mel_db, a.layout, a.n_slices, a.ld_t = _ptr(mel), LAYOUT_SLICES, n, 0
+        a.mel_stride = mel.stride(0)
+        a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), mixed_pcm.stride(0), _ptr(lengths)
+        a.B, a.L = B, L
+        a.out_pcm, a.out_stride = _ptr(out), out.stride(0)
+        check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
+        return out
+
+
+def fit_noise(noise, n_noise, n_speech_max, lengths=None):
+    """dp:125-128 for a batch: periodic tiling noise[i mod n_noise] up to the speech length (torch gather; host-side prep)."""
+    idx = torch.arange(n_speech_max, device=noise.device) % int(n_noise)
+    return noise[..., :n_noise].index_select(-1, idx).contiguous()

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the spectral hot path (BASELINE.json metric: audio-seconds / second).
+
+Workload (config.workload): BASELINE.json configs[1] -- GRID-shaped batch, 1,000 x 3 s 16 kHz
+utterances + white noise at 0 dB SNR per GPU: SNR factor + fused mix/STFT/mel/dB + top_db floor
+into 15 AV-aligned (80, 20) slices for mixed / speech / noise and the mixed PCM.  One "step" is
+one pass over that batch.  Multi-GPU: every rank owns its own 1,000 utterances (weak scaling,
+sharded by utterance, no data-path collective); rank 0 prints ONE JSON line.
+
+  value     whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the host-facing API: pinned host buffers, H2D + D2H in the timed region
+  roofline  dominant kernel (avse_forward_kernel): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the float64 CPU restatement of the reference path (oracle/), timed on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, FPS, SLICE_MS = 16000, 25.0, 200
+UTT_SECONDS = 3.0
+L = int(SR * UTT_SECONDS)          # 48000
+N_VIDEO_SLICES = 15                # 75 mouth-crop frames / 5
+BYTES_PER_SAMPLE_PAIR = 18         # read 4+4, write 4 (mixed PCM) + 3 * 80*4/160 (three log-mels)
+INV_BYTES_PER_FRAME = 1600         # read mel 320 + mixture PCM 640, write PCM 640
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1000, help="utterances per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0: auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-inverse", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle restatement of preprocess_audio_pair (dp:119-139), Pool over utterances (dp:194)
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(seed):
+    import numpy as np
+    from oracle import avse_oracle as O
+    s = O.AudioSignal(O.synth_speech(L, SR, seed).astype(np.float32), SR)
+    n = O.AudioSignal(O.synth_noise(L, seed).astype(np.float32), SR)
+    t0 = time.perf_counter()
+    O.preprocess_audio_pair_signals(s, n, SLICE_MS, N_VIDEO_SLICES, FPS, snr_db=0)
+    return time.perf_counter() - t0
+
+
+def _cpu_prepare(n):
+    import numpy as np
+    from oracle import avse_oracle as O
+    return [(O.synth_speech(L, SR, i).astype(np.float32), O.synth_noise(L, i).astype(np.float32)) for i in range(n)]
+
+
+def _cpu_work(pair):
+    from oracle import avse_oracle as O
+    s = O.AudioSignal(pair[0], SR)
+    n = O.AudioSignal(pair[1], SR)
+    out = O.preprocess_audio_pair_signals(s, n, SLICE_MS, N_VIDEO_SLICES, FPS, snr_db=0)
+    return out[0].shape[0]
+
+
+def cpu_throughput(n_utts, procs):
+    """audio-s/s of the oracle over n_utts 3 s pairs with `procs` worker processes (inputs prepared untimed)."""
+    import multiprocessing as mp
+    pairs = _cpu_prepare(n_utts)
+    if procs <= 1:
+        t0 = time.perf_counter()
+        for p in pairs:
+            _cpu_work(p)
+        dt = time.perf_counter() - t0
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_work, pairs[:procs])  # warm the workers (imports, FFT plans)
+            t0 = time.perf_counter()
+            pool.map(_cpu_work, pairs, chunksize=max(1, n_utts // (4 * procs)))
+            dt = time.perf_counter() - t0
+    return n_utts * UTT_SECONDS / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = min(16, cores)           # dp:194 Pool(16), bounded by the box
+    n = args.cpu_sample or max(4 * procs, 64)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_throughput(n, procs)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    total_audio = n * UTT_SECONDS * len(vals)
+    total_t = sum(dt for _, dt in vals)
+    value = total_audio / total_t
+    line = {
+        "impl": "reference", "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.batch, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": procs, "kind": "port",
+                         "sample": "%d x 3 s pairs per step, oracle/avse_oracle.py preprocess_audio_pair_signals, Pool(%d) (dp:194)" % (n, procs)},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference's librosa/mediaio are not installable here; this is the float64 numpy restatement (oracle/) of dp:119-139",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, gpus):
+    return {
+        "workload": "BASELINE configs[1]: %d x 3 s 16 kHz utterances + white noise @ 0 dB per GPU; mix + 3x log-mel (n_fft 640, hop 160, 80 mel) + top_db floor + 15 AV-aligned (80,20) slices + mixed PCM" % batch,
+        "utterances_per_gpu": batch, "seconds_per_utterance": UTT_SECONDS, "sharding": "by utterance, no collective",
+        "n_gpus": gpus,
+        "l2": "per-step working set %.0f MB (inputs %.0f MB + outputs %.0f MB) > 126 MB L2; no explicit flush" % (
+            batch * L * 18 / 1e6, batch * L * 8 / 1e6, batch * L * 10 / 1e6),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def synth_batch(torch, B, device, seed):
+    """Harmonic 'voiced' speech (f0 120 +- 30 Hz, 29 harmonics ~1/k, slow envelope, peak ~0.3) + white noise sigma 0.05."""
+    g = torch.Generator(device=device).manual_seed(1234 + seed)
+    t = torch.arange(L, device=device, dtype=torch.float32) / SR
+    f0 = 120.0 + 30.0 * (2.0 * torch.rand((B, 1), generator=g, device=device) - 1.0)
+    x = torch.zeros((B, L), device=device)
+    for k in range(1, 30):
+        ph = 2.0 * torch.pi * torch.rand((B, 1), generator=g, device=device)
+        x += torch.sin(2.0 * torch.pi * k * f0 * t + ph) / k
+    env = torch.sin(torch.pi * 1.5 * t + torch.rand((B, 1), generator=g, device=device)) ** 2
+    x = x * env + 1e-3 * torch.randn((B, L), generator=g, device=device)
+    x = 0.3 * x / x.abs().amax(dim=1, keepdim=True)
+    n = 0.05 * torch.randn((B, L), generator=g, device=device)
+    return x.contiguous(), n.contiguous()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    eng_mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+    eng = eng_mod.SpectralEngine(SR, FPS, SLICE_MS, device=device)
+    B = args.batch
+
+    speech, noise = synth_batch(torch, B, device, seed=rank)
+    T = eng.n_frames(L)
+    out = {}
+
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        factor, max_key = eng.snr_factor(speech, noise, max_key=out.get("max_key"))
+        if i is not None:
+            ev_k0[i].record()
+        res = eng.forward_raw(speech, noise, L=L, factor=factor, n_slices=N_VIDEO_SLICES, max_key=max_key, out=out)
+        if i is not None:
+            ev_k1[i].record()
+        eng.floor_(res["speech"], max_key, 0)
+        eng.floor_(res["noise"], max_key, 1)
+        eng.floor_(res["mixed"], max_key, 2)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
+    tmax = torch.tensor([ms_total, k_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, k_ms_max = float(tmax[0]), float(tmax[1])
+    ms_per_step = ms_total / args.steps
+    value = world * B * UTT_SECONDS / (ms_per_step * 1e-3)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
+    alg_bytes = B * L * BYTES_PER_SAMPLE_PAIR
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "forward_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "avse_forward_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
+                "note": "FP32-issue-bound fused FFT kernel; see DESIGN.md and profiles/"}
+
+    line = {
+        "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(B, world), "roofline": roofline,
+        "gpu_launches": 5 * args.steps, "clocks": clocks,
+    }
+
+    # ---------------- inverse path (config 4), reported beside the headline ----------------
+    if not args.no_inverse and hasattr(eng._lib, "avse_inverse"):
+        res = step()
+        mixed_pcm = res["mixed_pcm"]
+        mel = res["speech"]
+        for _ in range(3):
+            eng.reconstruct(mixed_pcm, mel)
+        barrier()
+        i0 = torch.cuda.Event(enable_timing=True)
+        i1 = torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(args.steps):
+            eng.reconstruct(mixed_pcm, mel)
+        i1.record()
+        barrier()
+        inv_ms = i0.elapsed_time(i1) / args.steps
+        tinv = torch.tensor([inv_ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tinv, op=dist.ReduceOp.MAX)
+        inv_ms = float(tinv[0])
+        t_use = min(20 * N_VIDEO_SLICES, T)
+        inv_bytes = B * t_use * INV_BYTES_PER_FRAME
+        line["inverse"] = {"workload": "BASELINE configs[3]: %d enhanced mel-spectrograms (15,80,20) + mixture PCM -> waveforms per GPU" % B,
+                           "value": world * B * UTT_SECONDS / (inv_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": inv_ms,
+                           "roofline": {"bound": "hbm", "kernel": "avse_inverse_kernel", "achieved": inv_bytes / (inv_ms * 1e-3) / 1e9,
+                                        "peak": peak, "unit": "GB/s", "frac": inv_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
+
+    # ---------------- end to end through the host-facing API ----------------
+    if not args.no_e2e:
+        h_s = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        h_n = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        h_s.copy_(speech)
+        h_n.copy_(noise)
+        shape = (B, N_VIDEO_SLICES, 80, 20)
+        h_out = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        h_pcm = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        d_s = torch.empty_like(speech)
+        d_n = torch.empty_like(noise)
+        e2e_out = {}
+
+        def e2e_step():
+            d_s.copy_(h_s, non_blocking=True)
+            d_n.copy_(h_n, non_blocking=True)
+            factor, max_key = eng.snr_factor(d_s, d_n, max_key=e2e_out.get("max_key"))
+            r = eng.forward_raw(d_s, d_n, L=L, factor=factor, n_slices=N_VIDEO_SLICES, max_key=max_key, out=e2e_out)
+            for w, k in enumerate(("speech", "noise", "mixed")):
+                eng.floor_(r[k], max_key, w)
+            h_out[0].copy_(r["mixed"], non_blocking=True)
+            h_out[1].copy_(r["speech"], non_blocking=True)
+            h_out[2].copy_(r["noise"], non_blocking=True)
+            h_pcm.copy_(r["mixed_pcm"], non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        steps_e = max(3, min(args.steps, 10))
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps_e):
+            e2e_step()
+        t1.record()
+        barrier()
+        e_ms = t0.elapsed_time(t1) / steps_e
+        te = torch.tensor([e_ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0])
+        line["e2e"] = {"value": world * B * UTT_SECONDS / (e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e_ms,
+                       "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": 3 * B * N_VIDEO_SLICES * 80 * 20 * 4 + B * L * 4,
+                       "api": "SpectralEngine.snr_factor/forward_raw/floor_ over the C ABI, pinned host buffers, copies in the timed region"}
+
+    # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        procs = min(16, cores)
+        n = args.cpu_sample or max(8 * procs, 64)
+        v, dt = cpu_throughput(n, procs)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port",
+                                "sample": "%d x 3 s pairs (%.1f s wall), oracle/avse_oracle.py float64 restatement of dp:119-139, Pool(%d)" % (n, dt, procs)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+/* avse_b200.h -- C ABI of the B200-native spectral front/back end.
+ *
+ * Drop-in boundary for ONE hot path of melspectrum007/audio-visual-speech-enhancement:
+ * the audio half of data_processor.py (mix at SNR -> STFT -> mel -> dB -> AV-aligned slices,
+ * and mel -> linear -> ISTFT at predict time).  The reference has no FFI; its boundary is the
+ * set of Python functions in /root/reference/data_processor.py.  Each entry point below names
+ * the reference function(s) (file:line) whose arithmetic it replaces; the Python mirror of
+ * those signatures lives in audio-visual-speech-enhancement_b200/data_processor.py and binds
+ * this library with ctypes.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers unless the name says host; float32 unless stated.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *    allocates nothing (the context owns only small constant tables).
+ *  - Return value: 0 ok; < 0 bad arguments (AVSE_E_*); > 0 a cudaError_t.  Nothing throws.
+ *    avse_last_error() returns a thread-local description of the last failure.
+ *  - Geometry is the reference's hard-coded one (dp:44-45, dp:83-89): n_fft 640, hop 160,
+ *    321 bins, 80 mel bands, 20 spectrogram frames per 200 ms slice.
+ */
+#ifndef AVSE_B200_H
+#define AVSE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVSE_N_FFT 640
+#define AVSE_HOP 160
+#define AVSE_N_BINS 321
+#define AVSE_N_MELS 80
+#define AVSE_SPSS 20 /* spectrogram frames per slice: int(3200 / 160), dp:49 */
+
+#define AVSE_E_ARG (-1)
+#define AVSE_E_CONFIG (-2)
+#define AVSE_E_NOCUDA (-3)
+
+#define AVSE_LAYOUT_SLICES 0 /* [B][n_slices][80][20]  (np.stack of dp:52-57) */
+#define AVSE_LAYOUT_SPEC 1   /* [B][80][ld_t]          (dp:96 magnitude, time minor) */
+
+typedef struct avse_ctx avse_ctx;
+
+/* Builds the constant tables (periodic Hann, FFT twiddles, librosa.filters.mel(sr, 640, 80,
+ * fmin, fmax) in banded form, tridiagonal factors of F F^T) in float64 on the host and uploads
+ * them to `device`.  Replaces the per-call rebuilds at dp:83-89, dp:104-112. */
+int avse_create(int sample_rate, double fmin, double fmax, int device, avse_ctx** out);
+void avse_destroy(avse_ctx* ctx);
+const char* avse_last_error(void);
+const char* avse_version(void);
+
+/* Host copy of the dense filterbank, float64 [80][321] (== librosa.filters.mel, dp:83-89). */
+int avse_get_filterbank(const avse_ctx* ctx, double* host_out);
+
+/* AudioMixer.snr_factor (dp:130): factor[u] = sqrt(var(speech_u) / var(noise_u)) * 10^(-snr_db[u]/20),
+ * population variance over the first lengths[u] samples (lengths == NULL: L for all).
+ * Accumulates in float64.  snr_db == NULL means 0 dB for every utterance (the reference).
+ * Also resets max_key[u][0..2] (the running dB maxima used by avse_forward / avse_floor_*).
+ * speech/noise: [B][stride] with stride >= L. */
+int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride,
+                    const int* lengths, int B, int L, const float* snr_db,
+                    float* factor_out, int* max_key, void* stream);
+
+typedef struct avse_forward_args {
+    /* inputs */
+    const float* speech;     /* [B][in_stride] */
+    const float* noise;      /* [B][in_stride], already fitted to the speech length (dp:125-128); NULL: single signal */
+    long long in_stride;     /* elements between consecutive utterances */
+    const int* len_speech;   /* [B] samples present (zeros beyond: pad_with_zeros dp:40); NULL: L */
+    const int* len_noise;    /* [B]; NULL: same as len_speech */
+    const float* factor;     /* [B] from avse_snr_factor; NULL: 1.0 (noise used as given) */
+    int B;
+    int L;                   /* signal_length = samples_per_slice * n_video_slices (dp:37); frames T = 1 + L/160 */
+    /* outputs: un-floored dB log-mel (amplitude_to_db before its top_db clip, dp:94) */
+    int layout;              /* AVSE_LAYOUT_SLICES or AVSE_LAYOUT_SPEC */
+    int n_slices;            /* slices kept per utterance: min(video, audio) (dp:164); layout SLICES only */
+    int ld_t;                /* leading dimension (>= T) for layout SPEC */
+    float* out_speech;       /* any of the three may be NULL */
+    float* out_noise;
+    float* out_mixed;
+    long long out_stride;    /* elements between utterances in each output */
+    float* mixed_pcm;        /* [B][pcm_stride] s + f*n padded/truncated to L (dp:133, dp:39-42); may be NULL */
+    long long pcm_stride;
+    int* max_key;            /* [B][3] running maxima (speech, noise, mixed) as ordered-int keys; required */
+    float* stft_speech;      /* optional complex64 [B][T][321] (re, im interleaved): librosa.stft of `speech` (dp:79), frame-major */
+} avse_forward_args;
+
+/* preprocess_audio_pair's arithmetic (dp:130-137) / signal_to_spectrogram (dp:77-96) for a batch:
+ * one fused kernel: framing + reflect pad + Hann + packed 640-point FFT + |.| + mel + dB. */
+int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream);
+
+/* amplitude_to_db's top_db floor (dp:94): x = max(x, max_u - 80), in place on a SLICES or SPEC
+ * output of avse_forward.  which: 0 speech, 1 noise, 2 mixed (selects max_key column). */
+int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B,
+                       const int* max_key, int which, void* stream);
+
+/* dp:49-57 segment gather with the floor applied: SPEC [B][80][ld_t] -> SLICES [B][n_slices][80][20]. */
+int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, int ld_t,
+                      float* slices, long long slices_stride, int n_slices, int B,
+                      const int* max_key, int which, void* stream);
+
+/* Sets n running-max keys to "minus infinity" (needed before avse_forward when avse_snr_factor,
+ * which also resets them, is not part of the sequence, e.g. single-signal spectrograms). */
+int avse_reset_max(avse_ctx* ctx, int* max_key, int n, void* stream);
+
+/* Decodes max_key[u][which] to float dB on the host side convention (device -> device). */
+int avse_max_db(avse_ctx* ctx, const int* max_key, int n, float* out_db, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSE_B200_H */

@@ -1,0 +1,124 @@
+"""CPU-side check of the kernel's warp-stage code (csrc/avse_fwd_stages.cuh, avse_dft.cuh, avse_tables.cpp).
+
+tests/emul/avse_emul.cpp compiles the SAME __host__ __device__ stage functions with g++ and runs a
+warp as a loop over lanes, so index maps / twiddles / tables / float32 arithmetic are validated
+against the float64 oracle and the golden vectors without a GPU.  (The emulation is test
+infrastructure; the product has no CPU path.)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import avse_oracle as O
+from tests.cases import GOLDEN_CASES, SR, make_inputs, oracle_pair, fitted_noise
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "audio-visual-speech-enhancement_b200", "csrc")
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL_DB = 1e-3      # BASELINE.json north_star: <= 1e-3 dB on log-mel
+TOL_PCM = 1e-4     # <= 1e-4 of full scale on PCM
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="session")
+def emul():
+    out_dir = os.path.join(ROOT, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libavse_emul.so")
+    srcs = [os.path.join(ROOT, "tests", "emul", "avse_emul.cpp"), os.path.join(CSRC, "avse_tables.cpp")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so] + srcs)
+    lib = ctypes.CDLL(so)
+    lib.emul_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    lib.emul_filterbank.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    lib.emul_tables_info.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+def test_fft640_codelets(emul):
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        re = rng.randn(640).astype(np.float32)
+        im = rng.randn(640).astype(np.float32)
+        ore = np.zeros(640, np.float32)
+        oim = np.zeros(640, np.float32)
+        assert emul.emul_fft640(_p(re), _p(im), _p(ore), _p(oim)) == 0
+        ref = np.fft.fft(re.astype(np.float64) + 1j * im.astype(np.float64))
+        assert np.max(np.abs((ore + 1j * oim) - ref)) < 4e-7 * np.max(np.abs(ref))
+
+
+def test_filterbank_and_tridiagonal_tables(emul):
+    fb = np.zeros((80, 321))
+    assert emul.emul_filterbank(SR, 0.0, 8000.0, _p(fb)) == 0
+    ref = O.mel_filterbank(SR, 640, 80, 0.0, 8000.0)
+    assert np.max(np.abs(fb - ref)) < 1e-14
+    lo = np.zeros(80, np.int32)
+    width = np.zeros(80, np.int32)
+    tri = np.zeros(240, np.float32)
+    assert emul.emul_tables_info(SR, 0.0, 8000.0, _p(lo), _p(width), _p(tri)) == 0
+    assert width.max() <= 24 and width.min() >= 2 and width.sum() == 625
+    # Thomas factors solve (F F^T) y = a like np.linalg.pinv (dp:112)
+    w, ipiv, sup = tri[:80].astype(np.float64), tri[80:160].astype(np.float64), tri[160:].astype(np.float64)
+    a = np.abs(np.random.RandomState(1).randn(80))
+    d = a.copy()
+    for i in range(1, 80):
+        d[i] -= w[i] * d[i - 1]
+    y = np.zeros(80)
+    y[79] = d[79] * ipiv[79]
+    for i in range(78, -1, -1):
+        y[i] = (d[i] - sup[i] * y[i + 1]) * ipiv[i]
+    lin = ref.T @ y
+    assert np.max(np.abs(lin - np.linalg.pinv(ref) @ a)) < 1e-5 * np.max(np.abs(lin))
+    # unsupported configuration is refused, not silently mis-computed
+    assert emul.emul_filterbank(SR, 0.0, 100.0, _p(fb)) == -2
+
+
+def _run_emul(emul, case):
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    L = 3200 * case["nvs"]
+    fac = O.AudioMixer.snr_factor(O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(nf.astype(np.float64), SR), case["snr"])
+    ns = min(case["nvs"], (1 + L // 160) // 20)
+    outs = [np.zeros((ns, 80, 20), np.float32) for _ in range(3)]
+    pcm = np.zeros(L, np.float32)
+    mx = np.zeros(3, np.float32)
+    rc = emul.emul_forward(_p(s), _p(nf), L, len(s), len(s), fac, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm), _p(mx),
+                           SR, 0.0, 8000.0)
+    assert rc == 0
+    floored = [np.maximum(o, m - 80.0) for o, m in zip(outs, mx)]
+    return dict(speech=floored[0], noise=floored[1], mixed=floored[2], mixed_pcm=pcm)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+def test_stage_code_matches_oracle_and_golden(emul, case):
+    got = _run_emul(emul, case)
+    ref = oracle_pair(case)
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    for k in ("mixed", "speech", "noise"):
+        assert np.max(np.abs(got[k] - ref[k])) <= TOL_DB, k
+        assert np.max(np.abs(got[k] - gold[k])) <= TOL_DB + 2e-5, k
+    scale = np.max(np.abs(ref["mixed_pcm"]))
+    assert np.max(np.abs(got["mixed_pcm"] - ref["mixed_pcm"])) <= TOL_PCM * scale
+
+
+def test_single_signal_spec_layout(emul):
+    # signal_to_spectrogram on one signal of arbitrary length (dp:77-96), SPEC layout [80][ld_t]
+    n = 5000
+    x = O.synth_speech(n, SR, 7).astype(np.float32)
+    T = 1 + n // 160
+    ld = (T + 3) // 4 * 4
+    out = np.zeros((80, ld), np.float32)
+    mx = np.zeros(3, np.float32)
+    rc = emul.emul_forward(_p(x), None, n, n, n, 0.0, 1, 0, ld, _p(out), None, None, None, _p(mx), SR, 0.0, 8000.0)
+    assert rc == 0
+    ref, _ = O.signal_to_spectrogram(O.AudioSignal(x.astype(np.float64), SR), 640, 160)
+    got = np.maximum(out[:, :T], mx[0] - 80.0)
+    assert ref.shape == got.shape
+    assert np.max(np.abs(got - ref)) <= TOL_DB

@@ -1,0 +1,181 @@
+"""GPU parity tests of the forward path: CUDA kernels (through the C ABI) vs the float64 oracle and golden vectors.
+
+Tolerances are BASELINE.json's: <= 1e-3 dB on log-mel, <= 1e-4 of full scale on PCM.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import avse_oracle as O
+from tests.cases import GOLDEN_CASES, SR, FPS, make_inputs, oracle_pair, fitted_noise
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_DB = 1e-3
+TOL_PCM = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+    return mod.SpectralEngine(SR, FPS, 200, device="cuda:0")
+
+
+@pytest.fixture(scope="module")
+def dp():
+    return importlib.import_module("audio-visual-speech-enhancement_b200.data_processor")
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _run_pair(eng, case):
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    lens = _dev(np.array([len(s)], np.int32))
+    snr = _dev(np.array([case["snr"]], np.float32))
+    mixed, speech, noise, pcm = eng.preprocess_pairs(_dev(s[None]), _dev(nf[None]), case["nvs"], lengths=lens, snr_db=snr)
+    torch.cuda.synchronize()
+    return dict(mixed=mixed[0].cpu().numpy(), speech=speech[0].cpu().numpy(), noise=noise[0].cpu().numpy(),
+                mixed_pcm=pcm[0].cpu().numpy())
+
+
+def test_library_is_loaded_and_filterbank_matches(eng):
+    fb = eng.filterbank()
+    assert np.max(np.abs(fb - O.mel_filterbank(SR, 640, 80, 0.0, 8000.0))) < 1e-14
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+def test_pair_matches_oracle_and_golden(eng, case):
+    got = _run_pair(eng, case)
+    ref = oracle_pair(case)
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    for k in ("mixed", "speech", "noise"):
+        assert got[k].shape == ref[k].shape
+        assert np.max(np.abs(got[k] - ref[k])) <= TOL_DB, (k, np.max(np.abs(got[k] - ref[k])))
+        assert np.max(np.abs(got[k] - gold[k])) <= TOL_DB + 2e-5, k
+    scale = np.max(np.abs(ref["mixed_pcm"]))
+    assert np.max(np.abs(got["mixed_pcm"] - ref["mixed_pcm"])) <= TOL_PCM * scale
+
+
+def test_snr_factor_matches_mediaio_semantics(eng):
+    rng = np.random.RandomState(3)
+    B, L = 7, 20000
+    s = (rng.randn(B, L) * 1000 + 37.0).astype(np.float32)   # DC offset: variance must be mean-removed
+    n = (rng.randn(B, L) * 30 - 5.0).astype(np.float32)
+    lens = np.array([20000, 19999, 12345, 321, 5000, 20000, 7], np.int32)
+    snr = np.array([0, -10, 10, 5, -5, 2.5, 0], np.float32)
+    f, _ = eng.snr_factor(_dev(s), _dev(n), lengths=_dev(lens), snr_db=_dev(snr))
+    f = f.cpu().numpy()
+    for u in range(B):
+        ref = np.sqrt(np.var(s[u, :lens[u]].astype(np.float64)) / np.var(n[u, :lens[u]].astype(np.float64))) * 10 ** (-snr[u] / 20.0)
+        assert abs(f[u] - ref) <= 2e-7 * ref
+
+
+def test_batch_of_mixed_lengths_and_snrs(eng):
+    # ragged batch: every utterance must match its own single-utterance oracle (per-utterance max / variance)
+    cases = [dict(name="b%d" % i, n_s=[16000, 9000, 16000, 20000, 700][i], n_n=16000, nvs=5, snr=[0.0, -10.0, 10.0, 5.0, -5.0][i],
+                  seed=200 + i, scale=[1.0, 1.0, 32767.0, 0.01, 1.0][i]) for i in range(5)]
+    W = 20000
+    S = np.zeros((5, W), np.float32)
+    N = np.zeros((5, W), np.float32)
+    lens = np.zeros(5, np.int32)
+    for i, c in enumerate(cases):
+        s, n = make_inputs(c)
+        S[i, :len(s)] = s
+        N[i, :len(s)] = fitted_noise(s, n)
+        lens[i] = len(s)
+    snr = np.array([c["snr"] for c in cases], np.float32)
+    mixed, speech, noise, pcm = eng.preprocess_pairs(_dev(S), _dev(N), 5, lengths=_dev(lens), snr_db=_dev(snr))
+    for i, c in enumerate(cases):
+        ref = oracle_pair(c)
+        for k, got in (("mixed", mixed), ("speech", speech), ("noise", noise)):
+            err = np.max(np.abs(got[i].cpu().numpy() - ref[k]))
+            assert err <= TOL_DB, (i, k, err)
+        scale = np.max(np.abs(ref["mixed_pcm"]))
+        assert np.max(np.abs(pcm[i].cpu().numpy() - ref["mixed_pcm"])) <= TOL_PCM * scale
+
+
+def test_video_alignment_truncates_slices(eng):
+    # dp:164: n_slices = min(video, audio).  The floor still uses the max over ALL frames of the signal (dp:94).
+    case = GOLDEN_CASES[3]
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    ref = oracle_pair(case)
+    res = eng.forward_raw(_dev(s[None]), _dev(nf[None]), L=48000, factor=eng.snr_factor(_dev(s[None]), _dev(nf[None]))[0],
+                          n_slices=11)
+    sp = eng.floor_(res["speech"], res["max_key"], 0)[0].cpu().numpy()
+    assert sp.shape == (11, 80, 20)
+    assert np.max(np.abs(sp - ref["speech"][:11])) <= TOL_DB
+
+
+def test_spectrogram_layout_gather_and_stft(eng):
+    x = (O.synth_speech(30000, SR, 9) + O.synth_noise(30000, 9)).astype(np.float32)
+    db, D = eng.spectrogram(_dev(x), stft=True)
+    ref_db, _ = O.signal_to_spectrogram(O.AudioSignal(x.astype(np.float64), SR), 640, 160)
+    ref_D = O.stft(x.astype(np.float64), 640, 160)
+    assert db.shape == (1, 80, 188)
+    assert np.max(np.abs(db[0].cpu().numpy() - ref_db)) <= TOL_DB
+    got_D = D[0].cpu().numpy().T
+    assert np.max(np.abs(got_D - ref_D)) <= 2e-6 * np.max(np.abs(ref_D))
+    # SPEC -> slices through the segment-gather kernel == dp:49-57
+    res = eng.forward_raw(_dev(x), None, layout=1, want=("speech",), mixed_pcm=False)
+    sl = eng.floor_gather(res["speech"], res["max_key"], 0, 9)[0].cpu().numpy()
+    a = O.AudioSignal(x.astype(np.float64), SR)
+    full, _ = O.signal_to_spectrogram(a, 640, 160)
+    want = np.stack([full[:, 20 * i:20 * (i + 1)] for i in range(9)])
+    assert np.max(np.abs(sl - want)) <= TOL_DB
+
+
+def test_linearity_and_scale_invariants_full_size(eng):
+    # size-independent properties at BASELINE config-2 scale (1000 x 3 s) without a CPU oracle pass:
+    # (1) scaling the inputs by c shifts every un-floored dB value by 20 log10(c); (2) speech-only == pair's speech
+    B, L = 1000, 48000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    s = torch.randn((B, L), generator=g, device="cuda") * 0.1
+    n = torch.randn((B, L), generator=g, device="cuda") * 0.05
+    f, mk = eng.snr_factor(s, n)
+    r1 = eng.forward_raw(s, n, factor=f, max_key=mk)
+    f2, mk2 = eng.snr_factor(s * 4.0, n * 4.0)
+    r2 = eng.forward_raw(s * 4.0, n * 4.0, factor=f2, max_key=mk2)
+    assert torch.max(torch.abs(f - f2)).item() < 1e-5
+    shift = 20.0 * np.log10(4.0)
+    for k in ("speech", "noise", "mixed"):
+        d = (r2[k] - r1[k] - shift).abs().max().item()
+        assert d <= 2e-3, (k, d)   # two independent float32 evaluations: 2 x the 1e-3 dB gate
+    assert (r2["mixed_pcm"] - 4.0 * r1["mixed_pcm"]).abs().max().item() <= 1e-5
+    # every utterance's running max equals the max of what was written plus the dropped tail frame
+    mx = eng.max_db(mk)
+    assert torch.all(mx[:, 2] >= r1["mixed"].amax(dim=(1, 2, 3)) - 1e-6)
+    # floor: idempotent and exactly max - 80
+    sp = r1["speech"].clone()
+    eng.floor_(sp, mk, 0)
+    sp2 = sp.clone()
+    eng.floor_(sp2, mk, 0)
+    assert torch.equal(sp, sp2)
+    assert torch.all(sp.amin(dim=(1, 2, 3)) >= mx[:, 0] - 80.0)
+
+
+def test_data_processor_signatures(dp):
+    case = GOLDEN_CASES[0]
+    s, n = make_inputs(case)
+    ref = oracle_pair(case)
+    sp = dp.AudioSignal((s * 1.0), SR)
+    nz = dp.AudioSignal((n * 1.0), SR)
+    mixed, speech, noise, mixed_signal = dp.preprocess_audio_pair_signals(sp, nz, 200, case["nvs"], FPS, snr_db=case["snr"])
+    assert mixed.shape == (5, 80, 20) and mixed_signal.get_number_of_samples() == 16000
+    assert np.max(np.abs(mixed - ref["mixed"])) <= TOL_DB
+    a = dp.AudioSignal(s[:15000], SR)
+    sl = dp.preprocess_audio_signal(a, 200, 5, FPS)
+    assert a.get_number_of_samples() == 16000  # padded in place (dp:40)
+    oa = O.AudioSignal(s[:15000].astype(np.float64), SR)
+    assert np.max(np.abs(sl - O.preprocess_audio_signal(oa, 200, 5, FPS))) <= TOL_DB
+    mag, phase = dp.signal_to_spectrogram(dp.AudioSignal(s, SR), 640, 160)
+    rmag, rphase = O.signal_to_spectrogram(O.AudioSignal(s.astype(np.float64), SR), 640, 160)
+    assert mag.shape == (80, 101) and phase.shape == (321, 101)
+    assert np.max(np.abs(mag - rmag)) <= TOL_DB
