@@ -23,6 +23,13 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _rs(t):
+    """Row stride in elements; a size-1 leading dimension may carry an arbitrary (even 0) stride."""
+    if t is None:
+        return 0
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t[0].numel())
+
+
 def geometry(sample_rate, video_frame_rate, slice_duration_ms=200):
     """dp:36, dp:44-45, dp:49 integer geometry."""
     samples_per_slice = int((float(slice_duration_ms) / 1000) * sample_rate)
@@ -91,11 +98,11 @@ class SpectralEngine(object):
         """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], max_key[B,3])."""
         speech, noise = self._as_batch(speech), self._as_batch(noise)
         B, L = speech.shape
-        assert noise.shape == speech.shape and noise.stride(0) == speech.stride(0)
+        assert noise.shape == speech.shape and _rs(noise) == _rs(speech)
         factor = torch.empty(B, dtype=torch.float32, device=self.device)
         if max_key is None:
             max_key = torch.empty((B, 3), dtype=torch.int32, device=self.device)
-        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), speech.stride(0), _ptr(lengths), B, L,
+        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), _rs(speech), _ptr(lengths), B, L,
                                         _ptr(snr_db), _ptr(factor), _ptr(max_key), self._stream()), "avse_snr_factor")
         return factor, max_key
 
@@ -109,7 +116,7 @@ class SpectralEngine(object):
             L = speech.shape[1]
         if noise is not None:
             noise = self._as_batch(noise)
-            assert noise.stride(0) == speech.stride(0) and noise.shape[0] == B
+            assert _rs(noise) == _rs(speech) and noise.shape[0] == B
         T = self.n_frames(L)
         if n_slices is None:
             n_slices = T // SPSS
@@ -134,14 +141,14 @@ class SpectralEngine(object):
         res["stft"] = torch.empty((B, T, N_BINS), dtype=torch.complex64, device=self.device) if stft else None
         ref = res["speech"]
         a = ForwardArgs()
-        a.speech, a.noise, a.in_stride = _ptr(speech), _ptr(noise), speech.stride(0)
+        a.speech, a.noise, a.in_stride = _ptr(speech), _ptr(noise), _rs(speech)
         a.len_speech, a.len_noise, a.factor = _ptr(len_speech), _ptr(len_noise), _ptr(factor)
         a.B, a.L = B, L
         a.layout, a.n_slices, a.ld_t = layout, n_slices, ld_t
         a.out_speech, a.out_noise, a.out_mixed = _ptr(res["speech"]), _ptr(res["noise"]), _ptr(res["mixed"])
-        a.out_stride = ref.stride(0) if ref is not None else 0
+        a.out_stride = _rs(ref)
         a.mixed_pcm = _ptr(res["mixed_pcm"])
-        a.pcm_stride = res["mixed_pcm"].stride(0) if res["mixed_pcm"] is not None else 0
+        a.pcm_stride = _rs(res["mixed_pcm"])
         a.max_key = _ptr(max_key)
         a.stft_speech = _ptr(res["stft"])
         check(self._lib.avse_forward(self._ctx, ctypes.byref(a), self._stream()), "avse_forward")
@@ -152,7 +159,7 @@ class SpectralEngine(object):
         """amplitude_to_db's top_db floor (dp:94), in place, per utterance."""
         B = data.shape[0]
         n = data[0].numel()
-        check(self._lib.avse_floor_inplace(self._ctx, _ptr(data), data.stride(0), n, B, _ptr(max_key), which, self._stream()),
+        check(self._lib.avse_floor_inplace(self._ctx, _ptr(data), _rs(data), n, B, _ptr(max_key), which, self._stream()),
               "avse_floor_inplace")
         return data
 
@@ -160,7 +167,7 @@ class SpectralEngine(object):
         """dp:49-57: SPEC [B,80,ld_t] (un-floored) -> floored slices [B,n_slices,80,20]."""
         B, _, ld_t = spec.shape
         out = torch.empty((B, n_slices, N_MELS, SPSS), dtype=torch.float32, device=self.device)
-        check(self._lib.avse_floor_gather(self._ctx, _ptr(spec), spec.stride(0), ld_t, _ptr(out), out.stride(0), n_slices, B,
+        check(self._lib.avse_floor_gather(self._ctx, _ptr(spec), _rs(spec), ld_t, _ptr(out), _rs(out), n_slices, B,
                                           _ptr(max_key), which, self._stream()), "avse_floor_gather")
         return out
 
@@ -235,10 +242,10 @@ class SpectralEngine(object):
         out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.ld_t = _ptr(mel), LAYOUT_SLICES, n, 0
-        a.mel_stride = mel.stride(0)
-        a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), mixed_pcm.stride(0), _ptr(lengths)
+        a.mel_stride = _rs(mel)
+        a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), _rs(mixed_pcm), _ptr(lengths)
         a.B, a.L = B, L
-        a.out_pcm, a.out_stride = _ptr(out), out.stride(0)
+        a.out_pcm, a.out_stride = _ptr(out), _rs(out)
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
 

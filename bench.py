@@ -77,6 +77,19 @@ def _cpu_work(pair):
     return out[0].shape[0]
 
 
+_CPU_LIMIT = None
+
+
+def _cpu_init():
+    # one BLAS/OpenMP thread per worker: the pool itself is the parallelism (dp:194), avoid oversubscription
+    global _CPU_LIMIT
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU_LIMIT = threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def cpu_throughput(n_utts, procs):
     """audio-s/s of the oracle over n_utts 3 s pairs with `procs` worker processes (inputs prepared untimed)."""
     import multiprocessing as mp
@@ -88,7 +101,7 @@ def cpu_throughput(n_utts, procs):
         dt = time.perf_counter() - t0
     else:
         ctx = mp.get_context("fork")
-        with ctx.Pool(procs) as pool:
+        with ctx.Pool(procs, initializer=_cpu_init) as pool:
             pool.map(_cpu_work, pairs[:procs])  # warm the workers (imports, FFT plans)
             t0 = time.perf_counter()
             pool.map(_cpu_work, pairs, chunksize=max(1, n_utts // (4 * procs)))
@@ -147,6 +160,34 @@ class ClockSampler(object):
         self.thread = None
 
     def start(self):
+        # NVML polled from a thread (~1 ms period): the timed region is tens of ms, too short for `nvidia-smi -lms`
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            self.nvml = None
+        if self.nvml is not None:
+            self.samples = []
+            self.running = True
+            def poll():
+                nv = self.nvml
+                while self.running:
+                    try:
+                        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                        pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                        self.samples.append((sm, mx, pw, rs))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -160,6 +201,20 @@ class ClockSampler(object):
         self.thread.start()
 
     def stop(self):
+        if getattr(self, "nvml", None) is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                    "hw_power_brake": 0x80}
+            reasons = set()
+            for _, _, _, rs in self.samples:
+                for nm, b in bits.items():
+                    if rs & b:
+                        reasons.add(nm)
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
+                    "power_w_max": max(s[2] for s in self.samples) if sm else None, "samples": len(sm), "reasons": sorted(reasons),
+                    "source": "NVML polled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
