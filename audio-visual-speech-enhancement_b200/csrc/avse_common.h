@@ -28,12 +28,13 @@ constexpr int FPG = 4;
 // Shared-memory frame buffer: 16 rows (k1) x 84 floats (40 complex + 2 pad) + 16 floats skew.
 constexpr int ROW_F = 84;
 constexpr int FRAME_F = N1 * ROW_F + 16;  // 1360 floats, == 16 (mod 32), multiple of 4
-constexpr int MEL_STAGE_F = 3 * NMEL * FPG;  // raw mel sums [sig][band][frame]
-constexpr int WARP_SMEM_F = FPG * FRAME_F + MEL_STAGE_F;  // 6400 floats = 25600 B per warp
+constexpr int MEL_STAGE_F = 3 * NMEL * FPG;  // raw mel sums [sig][band][frame], staged over frame buffer 0
+constexpr int WARP_SMEM_F = FPG * FRAME_F;   // 5440 floats = 21760 B per warp
+static_assert(MEL_STAGE_F <= FRAME_F, "mel staging must fit in one frame buffer");
 
 // mel tables
 constexpr int MEL_WMAX = 24;    // max bins per band supported (reference config: 23)
-constexpr int MEL_WROW = 25;    // padded row stride of the weight table (bank spread)
+constexpr int MEL_WROW = 28;    // padded row stride of the weight table (16-byte rows, bank spread)
 constexpr int MEL_ROUNDS = NMEL / 8;
 constexpr int POST_CHUNK = 41;  // bins per lane in the pointwise post stage (8 lanes x 41 >= 321)
 

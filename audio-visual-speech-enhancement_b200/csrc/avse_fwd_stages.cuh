@@ -4,8 +4,10 @@
 // through five warp-synchronous stages that exchange data only through that warp's private
 // shared-memory region (no block-level barrier anywhere in the frame loop):
 //
-//   pass 1  lane = (frame, n2):   strided load of speech+noise, Hann, packed z = s + i*n,
-//                                  DFT-16 over n1, twiddle W_640^{n2 k1}  -> rows [k1][n2]
+//   pass 1  lane = (frame, n2):   strided load of speech+noise (register sliding window: hop = 4
+//                                  strides, so a lane re-uses 12 of its 16 samples frame to frame),
+//                                  Hann, packed z = s + i*n, DFT-16 over n1, twiddle W_640^{n2 k1}
+//                                                                          -> rows [k1][n2]
 //   pass 2  lane = (frame, k1):   DFT-40 over n2 (5 x 8 PFA)              -> Z[k] natural order
 //   post    lane = (frame, chunk): unpack S' = Z_k + conj Z_{N-k}, N' = (Z_k - conj Z_{N-k})/i,
 //                                  M' = S' + f N', three magnitudes       -> in place
@@ -42,7 +44,9 @@ AVSE_HD float fast_sqrt(float x) {
 
 AVSE_HD float fast_log2(float x) {
 #if defined(__CUDA_ARCH__)
-    return __log2f(x);
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // x >= 1e-5: never denormal
+    return y;
 #else
     return log2f(x);
 #endif
@@ -54,14 +58,19 @@ AVSE_HD float amp_to_db(float a) {
     return K * fast_log2(a > AMIN ? a : AMIN);
 }
 
-// Constant tables, device-resident (or host arrays in the emulation).
+// Constant tables.  window / tw1t / mel_w / mel_lo are staged in shared memory by the kernel.
 struct FwdTables {
     const float* window;      // [640]
     const float* tw1t;        // [16][40][2]
-    const float* mel_w;       // [80][MEL_WROW]   (copied to shared memory by the kernel)
+    const float* mel_w;       // [80][MEL_WROW]
     const int* mel_lo;        // [80]
     const int* mel_roundw;    // [10]
 };
+
+// Mel round widths of the reference configuration (sr 16 kHz, fmin 0, fmax 8 kHz): max band width
+// over bands 8r..8r+7.  The specialised kernel unrolls the band loops with these constants; any
+// other table uses the generic (runtime-width) kernel.
+#define AVSE_STD_ROUNDW {3, 3, 3, 4, 5, 7, 10, 13, 18, 23}
 
 // One group of 4 frames of one utterance.
 struct FwdTile {
@@ -70,6 +79,7 @@ struct FwdTile {
     int L;               // signal length after pad/truncate (dp:37-42); reflect domain
     int valid_s;         // samples present in sp (zeros beyond, dp:40)
     int valid_n;         // samples present in nz
+    int vmin;            // min(valid_s, valid_n) (0 when nz == nullptr): interior test
     int T;               // STFT frames: 1 + L / hop
     int t0;              // first frame of the group (multiple of 4)
     float factor;        // SNR factor (dp:130); 0 when nz == nullptr
@@ -84,34 +94,23 @@ AVSE_HD float load_sample_edge(const float* p, int i, int L, int valid) {
     return (p != nullptr && i < valid) ? p[i] : 0.0f;
 }
 
-// ---------------------------------------------------------------------------------------
-// pass 1: one (frame f, residue n2) task
-// ---------------------------------------------------------------------------------------
-template <bool EDGE>
-AVSE_HD void pass1_task(const FwdTile& tl, int f, int n2, const float (&w)[16], const float (&twr)[16],
-                        const float (&twi)[16], float* frames) {
-    const int t_raw = tl.t0 + f;
-    const int t = t_raw < tl.T ? t_raw : tl.T - 1;
-    const int base = t * HOP - HALF + n2;
-    float xr[16], xi[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int i = base + N2 * n1;
-        float s, n;
-        if (EDGE) {
-            s = load_sample_edge(tl.sp, i, tl.L, tl.valid_s);
-            n = load_sample_edge(tl.nz, i, tl.L, tl.valid_n);
-        } else {
-            s = tl.sp[i];
-            n = tl.nz[i];
-        }
-        if (n1 >= 8 && n1 < 12) {
-            // this frame's own hop: original samples [160 t, 160 t + 160)
-            if (tl.mixed_pcm != nullptr && (!EDGE || (t_raw < tl.T && i < tl.L))) tl.mixed_pcm[i] = s + tl.factor * n;
-        }
-        xr[n1] = s * w[n1];
-        xi[n1] = n * w[n1];
-    }
+// A frame is "interior" when all 640 of its samples exist in both signals without reflection.
+AVSE_HD bool frame_interior(const FwdTile& tl, int t) {
+    return t * HOP - HALF >= 0 && t * HOP + HALF <= tl.vmin && t < tl.T;
+}
+
+// Per-lane register state of pass 1 that survives from frame to frame (and group to group).
+struct Pass1Win {
+    float rs[16], rn[16];   // raw samples x[160 t - 320 + 40 n1 + lane] of frame `t_win`
+    float ns[4], nn[4];     // prefetched new samples for frame `t_pref`
+    int t_win;              // frame held in rs/rn, or -1
+    int t_pref;             // frame whose 4 new strides are in ns/nn, or -1
+};
+
+AVSE_HD void pass1_win_reset(Pass1Win& w) { w.t_win = -1; w.t_pref = -1; }
+
+// DFT-16 + twiddle + store of one (frame f, residue n2) column.
+AVSE_HD void pass1_finish(float (&xr)[16], float (&xi)[16], int f, int n2, const vec2* s_tw, float* frames) {
     dft16(xr, xi);
     float* row = frames + f * FRAME_F + 2 * n2;
     {
@@ -120,33 +119,107 @@ AVSE_HD void pass1_task(const FwdTile& tl, int f, int n2, const float (&w)[16], 
     }
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) {
+        const vec2 tw = s_tw[k1 * N2 + n2];
         vec2 v;
-        v.x = xr[k1] * twr[k1] - xi[k1] * twi[k1];
-        v.y = xr[k1] * twi[k1] + xi[k1] * twr[k1];
+        v.x = xr[k1] * tw.x - xi[k1] * tw.y;
+        v.y = xr[k1] * tw.y + xi[k1] * tw.x;
         *reinterpret_cast<vec2*>(row + k1 * ROW_F) = v;
     }
 }
 
-AVSE_HD void load_lane_consts(const FwdTables& tb, int n2, float (&w)[16], float (&twr)[16], float (&twi)[16]) {
+// Edge / generic task: every sample through the reflect + zero-pad loader.
+AVSE_HD void pass1_task_edge(const FwdTile& tl, int f, int n2, const float* s_win, const vec2* s_tw, float* frames) {
+    const int t_raw = tl.t0 + f;
+    const int t = t_raw < tl.T ? t_raw : tl.T - 1;
+    const int base = t * HOP - HALF + n2;
+    float xr[16], xi[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) w[n1] = tb.window[N2 * n1 + n2];
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-        const vec2 v = *reinterpret_cast<const vec2*>(tb.tw1t + (k1 * N2 + n2) * 2);
-        twr[k1] = v.x;
-        twi[k1] = v.y;
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const int i = base + N2 * n1;
+        const float s = load_sample_edge(tl.sp, i, tl.L, tl.valid_s);
+        const float n = load_sample_edge(tl.nz, i, tl.L, tl.valid_n);
+        if (n1 >= 8 && n1 < 12) {
+            // this frame's own hop: original samples [160 t, 160 t + 160)
+            if (tl.mixed_pcm != nullptr && t_raw < tl.T && i < tl.L) tl.mixed_pcm[i] = s + tl.factor * n;
+        }
+        const float w = s_win[N2 * n1 + n2];
+        xr[n1] = s * w;
+        xi[n1] = n * w;
     }
+    pass1_finish(xr, xi, f, n2, s_tw, frames);
 }
 
-template <bool EDGE>
-AVSE_HD void stage_pass1(const FwdTables& tb, const FwdTile& tl, int lane, float* frames) {
-    float w[16], twr[16], twi[16];
-    load_lane_consts(tb, lane, w, twr, twi);
+// Interior task for n2 = lane with the sliding register window.
+AVSE_HD void pass1_task_window(const FwdTile& tl, int f, int lane, Pass1Win& w, const float* s_win, const vec2* s_tw, float* frames) {
+    const int t = tl.t0 + f;
+    const float* ps = tl.sp + t * HOP - HALF + lane;
+    const float* pn = tl.nz + t * HOP - HALF + lane;
+    if (w.t_win == t - 1 && w.t_pref == t) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { w.rs[j] = w.rs[j + 4]; w.rn[j] = w.rn[j + 4]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { w.rs[12 + j] = w.ns[j]; w.rn[12 + j] = w.nn[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { w.rs[j] = ps[N2 * j]; w.rn[j] = pn[N2 * j]; }
+    }
+    w.t_win = t;
+    // prefetch the 4 new strides of frame t+1 while this frame is transformed
+    if (frame_interior(tl, t + 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { w.ns[j] = ps[HOP + N2 * (12 + j)]; w.nn[j] = pn[HOP + N2 * (12 + j)]; }
+        w.t_pref = t + 1;
+    } else {
+        w.t_pref = -1;
+    }
+    if (tl.mixed_pcm != nullptr) {
+        float* pm = tl.mixed_pcm + t * HOP + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pm[N2 * j] = w.rs[8 + j] + tl.factor * w.rn[8 + j];
+    }
+    float xr[16], xi[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const float wv = s_win[N2 * n1 + lane];
+        xr[n1] = w.rs[n1] * wv;
+        xi[n1] = w.rn[n1] * wv;
+    }
+    pass1_finish(xr, xi, f, lane, s_tw, frames);
+}
+
+// Interior task for the 8 left-over residues (n2 = 32..39): plain loads, no window.
+AVSE_HD void pass1_task_plain(const FwdTile& tl, int f, int n2, const float* s_win, const vec2* s_tw, float* frames) {
+    const int t = tl.t0 + f;
+    const float* ps = tl.sp + t * HOP - HALF + n2;
+    const float* pn = tl.nz + t * HOP - HALF + n2;
+    float xr[16], xi[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) { xr[n1] = ps[N2 * n1]; xi[n1] = pn[N2 * n1]; }
+    if (tl.mixed_pcm != nullptr) {
+        float* pm = tl.mixed_pcm + t * HOP + n2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pm[N2 * j] = xr[8 + j] + tl.factor * xi[8 + j];
+    }
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const float wv = s_win[N2 * n1 + n2];
+        xr[n1] *= wv;
+        xi[n1] *= wv;
+    }
+    pass1_finish(xr, xi, f, n2, s_tw, frames);
+}
+
+AVSE_HD void stage_pass1(const FwdTile& tl, int lane, Pass1Win& w, const float* s_win, const vec2* s_tw, float* frames) {
+    // tasks 0..3: (frame f, n2 = lane); task 4: (frame lane/8, n2 = 32 + lane%8)
+    const int fb = lane >> 3, n2b = 32 + (lane & 7);
+    const bool have_noise = tl.nz != nullptr;
 #pragma unroll 1
-    for (int f = 0; f < FPG; ++f) pass1_task<EDGE>(tl, f, lane, w, twr, twi, frames);
-    const int n2b = 32 + (lane & 7);
-    load_lane_consts(tb, n2b, w, twr, twi);
-    pass1_task<EDGE>(tl, lane >> 3, n2b, w, twr, twi, frames);
+    for (int f = 0; f < FPG; ++f) {
+        if (have_noise && frame_interior(tl, tl.t0 + f)) pass1_task_window(tl, f, lane, w, s_win, s_tw, frames);
+        else { pass1_task_edge(tl, f, lane, s_win, s_tw, frames); w.t_pref = -1; }
+    }
+    if (have_noise && frame_interior(tl, tl.t0 + fb)) pass1_task_plain(tl, fb, n2b, s_win, s_tw, frames);
+    else pass1_task_edge(tl, fb, n2b, s_win, s_tw, frames);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -181,13 +254,15 @@ AVSE_HD void pass2_store(int lane, int j, float* frames, const float (&yr)[40], 
 AVSE_HD void stage_post(int lane, float factor, float* frames, vec2* stft_row) {
     // stft_row: optional [321] complex row of this lane's frame receiving X_speech (dp:79 D), or nullptr
     const int f = lane >> 3, p = lane & 7;
-    float* zb = frames + f * FRAME_F;
-#pragma unroll 4
+    float* za = frames + f * FRAME_F + 2 * POST_CHUNK * p;            // slot k      = za + 2 i
+    float* zc = frames + f * FRAME_F + 2 * (NFFT - POST_CHUNK * p);   // slot 640-k  = zc - 2 i
+    const int k0 = POST_CHUNK * p;
+#pragma unroll
     for (int i = 0; i < POST_CHUNK; ++i) {
-        const int k = POST_CHUNK * p + i;
-        if (k >= 1 && k <= NBINS - 2) {
-            const vec2 a = *reinterpret_cast<const vec2*>(zb + 2 * k);
-            const vec2 c = *reinterpret_cast<const vec2*>(zb + 2 * (NFFT - k));
+        const int k = k0 + i;
+        if ((unsigned)(k - 1) <= (unsigned)(NBINS - 3)) {
+            const vec2 a = *reinterpret_cast<const vec2*>(za + 2 * i);
+            const vec2 c = *reinterpret_cast<const vec2*>(zc - 2 * i);
             const float sr = a.x + c.x, si = a.y - c.y;     // 2 * X_speech[k]
             const float nr = a.y + c.y, ni = c.x - a.x;     // 2 * X_noise[k]
             const float mr = sr + factor * nr, mi = si + factor * ni;
@@ -196,28 +271,56 @@ AVSE_HD void stage_post(int lane, float factor, float* frames, vec2* stft_row) {
             o1.y = fast_sqrt(nr * nr + ni * ni);
             o2.x = fast_sqrt(mr * mr + mi * mi);
             o2.y = 0.0f;
-            *reinterpret_cast<vec2*>(zb + 2 * k) = o1;
-            *reinterpret_cast<vec2*>(zb + 2 * (NFFT - k)) = o2;
+            *reinterpret_cast<vec2*>(za + 2 * i) = o1;
+            *reinterpret_cast<vec2*>(zc - 2 * i) = o2;
             if (stft_row != nullptr) { vec2 d; d.x = 0.5f * sr; d.y = 0.5f * si; stft_row[k] = d; }
         } else if (stft_row != nullptr && (k == 0 || k == NBINS - 1)) {
-            vec2 d; d.x = zb[2 * k]; d.y = 0.0f;   // DC / Nyquist of the real part of the packed input
+            vec2 d; d.x = za[2 * i]; d.y = 0.0f;   // DC / Nyquist of the real part of the packed input
             stft_row[k] = d;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// mel: round r, lane = (f = lane/8, band m = 8r + lane%8)
-// mel_w / mel_lo may live in shared memory
+// mel: round r, lane = (f = lane/8, band m = 8r + lane%8); W = number of bin iterations
+// (compile-time for the specialised kernel).  Accumulates into as/an/am.
 // ---------------------------------------------------------------------------------------
-AVSE_HD void stage_mel_round(int lane, int r, int roundw, const float* mel_w, const int* mel_lo,
-                             const float* frames, float* melst) {
+template <int W>
+AVSE_HD void mel_round_fixed(int lane, int r, const float* s_melw, const int* s_mello, const float* frames,
+                             float& as, float& an, float& am) {
     const int f = lane >> 3, m = 8 * r + (lane & 7);
-    const int lo = mel_lo[m];
-    const float* wrow = mel_w + m * MEL_WROW;
+    const int lo = s_mello[m];
+    const float* wrow = s_melw + m * MEL_WROW;
     const float* zs = frames + f * FRAME_F + 2 * lo;
     const float* zm = frames + f * FRAME_F + 2 * (NFFT - lo);
-    float as = 0.0f, an = 0.0f, am = 0.0f;
+    as = 0.0f; an = 0.0f; am = 0.0f;
+    constexpr int W4 = (W + 3) / 4;
+#pragma unroll
+    for (int q = 0; q < W4; ++q) {
+        const vec4 wv = *reinterpret_cast<const vec4*>(wrow + 4 * q);
+        const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            if (j < W) {
+                const vec2 sn = *reinterpret_cast<const vec2*>(zs + 2 * j);
+                const float mm = zm[-2 * j];
+                as += ww[e] * sn.x;
+                an += ww[e] * sn.y;
+                am += ww[e] * mm;
+            }
+        }
+    }
+}
+
+AVSE_HD void mel_round_generic(int lane, int r, int roundw, const float* s_melw, const int* s_mello, const float* frames,
+                               float& as, float& an, float& am) {
+    const int f = lane >> 3, m = 8 * r + (lane & 7);
+    const int lo = s_mello[m];
+    const float* wrow = s_melw + m * MEL_WROW;
+    const float* zs = frames + f * FRAME_F + 2 * lo;
+    const float* zm = frames + f * FRAME_F + 2 * (NFFT - lo);
+    as = 0.0f; an = 0.0f; am = 0.0f;
 #pragma unroll 1
     for (int j = 0; j < roundw; ++j) {
         const float w = wrow[j];
@@ -227,18 +330,50 @@ AVSE_HD void stage_mel_round(int lane, int r, int roundw, const float* mel_w, co
         an += w * sn.y;
         am += w * mm;
     }
-    melst[(0 * NMEL + m) * FPG + f] = as;   // speech
-    melst[(1 * NMEL + m) * FPG + f] = an;   // noise (unscaled)
-    melst[(2 * NMEL + m) * FPG + f] = am;   // mixture
+}
+
+// All ten rounds; results stay in registers (acc[r][sig]) until every lane has finished reading
+// the frame buffers, then stage_mel_store writes them over frame buffer 0.
+template <bool STD>
+AVSE_HD void stage_mel(int lane, const int* roundw, const float* s_melw, const int* s_mello, const float* frames,
+                       float (&acc)[MEL_ROUNDS][3]) {
+    if (STD) {
+        mel_round_fixed<3>(lane, 0, s_melw, s_mello, frames, acc[0][0], acc[0][1], acc[0][2]);
+        mel_round_fixed<3>(lane, 1, s_melw, s_mello, frames, acc[1][0], acc[1][1], acc[1][2]);
+        mel_round_fixed<3>(lane, 2, s_melw, s_mello, frames, acc[2][0], acc[2][1], acc[2][2]);
+        mel_round_fixed<4>(lane, 3, s_melw, s_mello, frames, acc[3][0], acc[3][1], acc[3][2]);
+        mel_round_fixed<5>(lane, 4, s_melw, s_mello, frames, acc[4][0], acc[4][1], acc[4][2]);
+        mel_round_fixed<7>(lane, 5, s_melw, s_mello, frames, acc[5][0], acc[5][1], acc[5][2]);
+        mel_round_fixed<10>(lane, 6, s_melw, s_mello, frames, acc[6][0], acc[6][1], acc[6][2]);
+        mel_round_fixed<13>(lane, 7, s_melw, s_mello, frames, acc[7][0], acc[7][1], acc[7][2]);
+        mel_round_fixed<18>(lane, 8, s_melw, s_mello, frames, acc[8][0], acc[8][1], acc[8][2]);
+        mel_round_fixed<23>(lane, 9, s_melw, s_mello, frames, acc[9][0], acc[9][1], acc[9][2]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < MEL_ROUNDS; ++r)
+            mel_round_generic(lane, r, roundw[r], s_melw, s_mello, frames, acc[r][0], acc[r][1], acc[r][2]);
+    }
+}
+
+// raw mel layout in (dead) frame buffer 0: melst[(sig * 80 + band) * 4 + frame]
+AVSE_HD void stage_mel_store(int lane, const float (&acc)[MEL_ROUNDS][3], float* melst) {
+    const int f = lane >> 3;
+#pragma unroll
+    for (int r = 0; r < MEL_ROUNDS; ++r) {
+        const int m = 8 * r + (lane & 7);
+        melst[(0 * NMEL + m) * FPG + f] = acc[r][0];   // speech
+        melst[(1 * NMEL + m) * FPG + f] = acc[r][1];   // noise (unscaled)
+        melst[(2 * NMEL + m) * FPG + f] = acc[r][2];   // mixture
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// dB: signal sig (0 speech, 1 noise, 2 mixture), sub-round q in 0..2, band m = 32q + lane
-// Output layouts: slices [n_slices][80][20] (dp:49-57) or spectrogram [80][ld_t].
-// Returns the max dB over the valid frames of this task (or -inf).
+// dB: 240 (signal, band) tasks in 8 sub-rounds of 32 lanes: id = 32 q + lane, sig = id / 80
+// (0 speech, 1 noise, 2 mixture).  Output layouts: slices [n_slices][80][20] (dp:49-57) or
+// spectrogram [80][ld_t].  Folds the max dB over the valid frames into mx[sig].
 // ---------------------------------------------------------------------------------------
 struct FwdOut {
-    float* dst;       // base of this utterance's output for signal sig (nullptr: skip stores)
+    float* dst[3];    // base of this utterance's output per signal (nullptr: skip stores)
     int layout;       // 0: slices [ns][80][20], 1: spectrogram [80][ld_t]
     int n_slices;     // slices kept (dp:164: min(video, audio))
     int ld_t;         // leading dimension for layout 1
@@ -252,43 +387,49 @@ AVSE_HD float neg_inf() {
 #endif
 }
 
-AVSE_HD float stage_db(int lane, int q, float scale, const float* melst_sig, const FwdOut& out, int t0, int T) {
-    const int m = 32 * q + lane;
-    float mx = neg_inf();
-    if (m < NMEL) {
-        const vec4 v = *reinterpret_cast<const vec4*>(melst_sig + m * FPG);
-        float d[4];
-        d[0] = amp_to_db(v.x * scale);
-        d[1] = amp_to_db(v.y * scale);
-        d[2] = amp_to_db(v.z * scale);
-        d[3] = amp_to_db(v.w * scale);
+AVSE_HD void stage_db(int lane, int q, float factor, bool have_noise, const float* melst, const FwdOut& out, int t0, int T,
+                      float (&mx)[3]) {
+    const int id = 32 * q + lane;
+    if (id >= 3 * NMEL) return;
+    const int sig = id >= 2 * NMEL ? 2 : (id >= NMEL ? 1 : 0);
+    if (sig > 0 && !have_noise) return;
+    const int m = id - sig * NMEL;
+    const float scale = sig == 1 ? factor : 1.0f;
+    const vec4 v = *reinterpret_cast<const vec4*>(melst + id * FPG);
+    float d[4];
+    d[0] = amp_to_db(v.x * scale);
+    d[1] = amp_to_db(v.y * scale);
+    d[2] = amp_to_db(v.z * scale);
+    d[3] = amp_to_db(v.w * scale);
+    float lm = neg_inf();
 #pragma unroll
-        for (int f = 0; f < 4; ++f)
-            if (t0 + f < T) mx = d[f] > mx ? d[f] : mx;
-        if (out.dst != nullptr) {
-            if (out.layout == 0) {
-                const int spss = 20;
-                const int sl = t0 / spss, tt = t0 - sl * spss;    // 4 | t0 and 4 | 20: group never straddles
-                if (sl < out.n_slices) {
-                    float* p = out.dst + ((size_t)sl * NMEL + m) * spss + tt;
-                    if (t0 + 3 < T) {
-                        vec4 o; o.x = d[0]; o.y = d[1]; o.z = d[2]; o.w = d[3];
-                        *reinterpret_cast<vec4*>(p) = o;
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < 4; ++f)
-                            if (t0 + f < T) p[f] = d[f];
-                    }
-                }
+    for (int f = 0; f < 4; ++f)
+        if (t0 + f < T) lm = d[f] > lm ? d[f] : lm;
+    mx[0] = (sig == 0 && lm > mx[0]) ? lm : mx[0];
+    mx[1] = (sig == 1 && lm > mx[1]) ? lm : mx[1];
+    mx[2] = (sig == 2 && lm > mx[2]) ? lm : mx[2];
+    float* dst = sig == 0 ? out.dst[0] : (sig == 1 ? out.dst[1] : out.dst[2]);
+    if (dst == nullptr) return;
+    if (out.layout == 0) {
+        const int spss = 20;
+        const int sl = t0 / spss, tt = t0 - sl * spss;    // 4 | t0 and 4 | 20: a group never straddles slices
+        if (sl < out.n_slices) {
+            float* p = dst + ((size_t)sl * NMEL + m) * spss + tt;
+            if (t0 + 3 < T) {
+                vec4 o; o.x = d[0]; o.y = d[1]; o.z = d[2]; o.w = d[3];
+                *reinterpret_cast<vec4*>(p) = o;
             } else {
-                float* p = out.dst + (size_t)m * out.ld_t + t0;
 #pragma unroll
                 for (int f = 0; f < 4; ++f)
                     if (t0 + f < T) p[f] = d[f];
             }
         }
+    } else {
+        float* p = dst + (size_t)m * out.ld_t + t0;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            if (t0 + f < T) p[f] = d[f];
     }
-    return mx;
 }
 
 // order-preserving float <-> int key for atomicMax on floats of either sign

@@ -175,8 +175,16 @@ extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* 
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_WARPS = 4;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
-constexpr int FWD_SMEM_TABLE_F = NMEL * MEL_WROW + NMEL + 16;   // mel_w, mel_lo, roundw(+pad)
-constexpr int FWD_SMEM_BYTES = (FWD_WARPS * WARP_SMEM_F + FWD_SMEM_TABLE_F) * 4;
+// shared memory: per-warp frame buffers, then CTA-shared tables
+constexpr int FWD_SM_MELW = FWD_WARPS * WARP_SMEM_F;              // [80][MEL_WROW]
+constexpr int FWD_SM_MELLO = FWD_SM_MELW + NMEL * MEL_WROW;       // [80] int
+constexpr int FWD_SM_ROUNDW = FWD_SM_MELLO + NMEL;                // [16] int
+constexpr int FWD_SM_WIN = FWD_SM_ROUNDW + 16;                    // [640]
+constexpr int FWD_SM_TW = FWD_SM_WIN + NFFT;                      // [16][40] vec2
+constexpr int FWD_SMEM_F = FWD_SM_TW + N1 * N2 * 2;
+constexpr int FWD_SMEM_BYTES = FWD_SMEM_F * 4;
+static_assert((FWD_SM_MELW % 4) == 0 && (FWD_SM_TW % 2) == 0, "table alignment");
+static_assert(2 * (FWD_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
 
 struct FwdParams {
     avse_forward_args a;
@@ -185,17 +193,21 @@ struct FwdParams {
     int G;   // groups of 4 frames per utterance
 };
 
+template <bool STD>
 __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* s_melw = smem + FWD_WARPS * WARP_SMEM_F;
-    int* s_mello = reinterpret_cast<int*>(s_melw + NMEL * MEL_WROW);
-    int* s_roundw = s_mello + NMEL;
+    float* s_melw = smem + FWD_SM_MELW;
+    int* s_mello = reinterpret_cast<int*>(smem + FWD_SM_MELLO);
+    int* s_roundw = reinterpret_cast<int*>(smem + FWD_SM_ROUNDW);
+    float* s_win = smem + FWD_SM_WIN;
+    vec2* s_tw = reinterpret_cast<vec2*>(smem + FWD_SM_TW);
     for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) s_melw[i] = P.tb.mel_w[i];
     for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) s_mello[i] = P.tb.mel_lo[i];
     if (threadIdx.x < MEL_ROUNDS) s_roundw[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
+    for (int i = threadIdx.x; i < NFFT; i += FWD_THREADS) s_win[i] = P.tb.window[i];
+    for (int i = threadIdx.x; i < N1 * N2 * 2; i += FWD_THREADS) smem[FWD_SM_TW + i] = P.tb.tw1t[i];
     float* frames = smem + warp * WARP_SMEM_F;
-    float* melst = frames + FPG * FRAME_F;
     // keep never-written pad slots finite (they are multiplied by exact-zero weights)
     for (int i = lane; i < WARP_SMEM_F; i += 32) frames[i] = 0.0f;
     __syncthreads();
@@ -211,7 +223,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
     int cur_u = -1;
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
     FwdTile tl{};
-    FwdOut out[3];
+    FwdOut out{};
+    Pass1Win win;
+    pass1_win_reset(win);
+    const bool have_noise = A.noise != nullptr;
 
     auto flush_max = [&](int u) {
 #pragma unroll
@@ -230,33 +245,29 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         if (u != cur_u) {
             if (cur_u >= 0) flush_max(cur_u);
             cur_u = u;
+            pass1_win_reset(win);
             tl.sp = A.speech + (size_t)u * A.in_stride;
-            tl.nz = A.noise ? A.noise + (size_t)u * A.in_stride : nullptr;
+            tl.nz = have_noise ? A.noise + (size_t)u * A.in_stride : nullptr;
             tl.L = A.L;
             tl.T = P.T;
             int vs = A.len_speech ? A.len_speech[u] : A.L;
             int vn = A.len_noise ? A.len_noise[u] : vs;
             tl.valid_s = vs < A.L ? vs : A.L;
             tl.valid_n = vn < A.L ? vn : A.L;
-            tl.factor = A.noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
+            tl.vmin = have_noise ? (tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n) : 0;
+            tl.factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
             tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
-            float* dsts[3] = {A.out_speech, A.out_noise, A.out_mixed};
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                out[s].dst = dsts[s] ? dsts[s] + (size_t)u * A.out_stride : nullptr;
-                out[s].layout = A.layout;
-                out[s].n_slices = A.n_slices;
-                out[s].ld_t = A.ld_t;
-            }
+            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
+            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
+            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+            out.layout = A.layout;
+            out.n_slices = A.n_slices;
+            out.ld_t = A.ld_t;
         }
         tl.t0 = g * FPG;
 
         // ---- pass 1 ----
-        const int vmin = tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n;
-        const bool interior = (tl.nz != nullptr) && (tl.t0 * HOP - HALF >= 0) && ((tl.t0 + FPG - 1) * HOP + HALF <= vmin) &&
-                              (tl.t0 + FPG - 1 < tl.T);
-        if (interior) stage_pass1<false>(P.tb, tl, lane, frames);
-        else stage_pass1<true>(P.tb, tl, lane, frames);
+        stage_pass1(tl, lane, win, s_win, s_tw, frames);
         __syncwarp();
 
         // ---- pass 2 ----
@@ -279,26 +290,28 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         }
         __syncwarp();
 
-        // ---- mel ----
-#pragma unroll 1
-        for (int r = 0; r < MEL_ROUNDS; ++r) stage_mel_round(lane, r, s_roundw[r], s_melw, s_mello, frames, melst);
+        // ---- mel (results staged over the now-dead frame buffer 0) ----
+        {
+            float acc[MEL_ROUNDS][3];
+            stage_mel<STD>(lane, s_roundw, s_melw, s_mello, frames, acc);
+            __syncwarp();
+            stage_mel_store(lane, acc, frames);
+        }
         __syncwarp();
 
         // ---- dB + stores ----
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            if (s == 1 && tl.nz == nullptr) continue;
-            if (s == 2 && tl.nz == nullptr) continue;
-            const float scale = (s == 1) ? tl.factor : 1.0f;
-#pragma unroll 1
-            for (int q = 0; q < 3; ++q) {
-                const float v = stage_db(lane, q, scale, melst + s * NMEL * FPG, out[s], tl.t0, tl.T);
-                mx[s] = fmaxf(mx[s], v);
-            }
-        }
+        for (int q = 0; q < 8; ++q) stage_db(lane, q, tl.factor, have_noise, frames, out, tl.t0, tl.T, mx);
         __syncwarp();
     }
     if (cur_u >= 0) flush_max(cur_u);
+}
+
+static bool tables_are_std(const HostTables& h) {
+    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
+    for (int r = 0; r < MEL_ROUNDS; ++r)
+        if (h.mel_roundw[r] != std_w[r]) return false;
+    return true;
 }
 
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
@@ -330,14 +343,16 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
     if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
         configured_dev = dev;
     }
     const long long total = (long long)a.B * P.G;
     long long blocks = 2LL * ctx->num_sms;
     const long long need = (total + FWD_WARPS - 1) / FWD_WARPS;
     if (blocks > need) blocks = need;
-    avse_forward_kernel<<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    if (tables_are_std(ctx->host)) avse_forward_kernel<true><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    else avse_forward_kernel<false><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

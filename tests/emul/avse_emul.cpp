@@ -30,30 +30,41 @@ extern "C" int emul_tables_info(int sample_rate, double fmin, double fmax, int* 
     return 0;
 }
 
+// Runs the five warp stages for one group; `win` is the per-lane pass-1 register state.
+struct EmulWarp {
+    alignas(16) float frames[WARP_SMEM_F];
+    Pass1Win win[32];
+    float yr[32][40], yi[32][40];
+    float acc[32][MEL_ROUNDS][3];
+};
+
+static void emul_fft_stages(EmulWarp& w, const HostTables& h, const FwdTile& tl) {
+    const vec2* s_tw = reinterpret_cast<const vec2*>(h.tw1t.data());
+    for (int lane = 0; lane < 32; ++lane) stage_pass1(tl, lane, w.win[lane], h.window.data(), s_tw, w.frames);
+    for (int j = 0; j < 2; ++j) {
+        for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, j, w.frames, w.yr[lane], w.yi[lane]);
+        for (int lane = 0; lane < 32; ++lane) pass2_store(lane, j, w.frames, w.yr[lane], w.yi[lane]);
+    }
+}
+
 // 640-point FFT of one complex frame through pass 1 (with unit window) + pass 2: checks the
 // DFT-16 / twiddle / DFT-40 codelets and the shared-memory index maps in isolation.
 extern "C" int emul_fft640(const float* re, const float* im, float* out_re, float* out_im) {
     HostTables h;
     if (!build_tables(h, 16000, 0.0, 8000.0)) return -2;
-    std::vector<float> ones(NFFT, 1.0f);
-    FwdTables tb{ones.data(), h.tw1t.data(), h.mel_w.data(), h.mel_lo.data(), h.mel_roundw.data()};
-    alignas(16) static float frames[WARP_SMEM_F];
-    memset(frames, 0, sizeof(frames));
-    // feed the frame as "speech = re, noise = im" of a signal whose frame 2 is interior
-    const int L = 4 * NFFT;
+    for (auto& v : h.window) v = 1.0f;
+    static EmulWarp w;
+    memset(w.frames, 0, sizeof(w.frames));
+    for (int lane = 0; lane < 32; ++lane) pass1_win_reset(w.win[lane]);
+    const int L = 8 * NFFT;
     std::vector<float> s(L, 0.0f), n(L, 0.0f);
-    const int t = 4;  // frame 4 covers original samples [4*160-320, 4*160+320) = [320, 960)
+    const int t = 8;  // frame 8 covers original samples [8*160-320, 8*160+320); group t0 = 8 is interior
     for (int i = 0; i < NFFT; ++i) { s[t * HOP - HALF + i] = re[i]; n[t * HOP - HALF + i] = im[i]; }
     FwdTile tl{};
-    tl.sp = s.data(); tl.nz = n.data(); tl.L = L; tl.valid_s = L; tl.valid_n = L; tl.T = 1 + L / HOP; tl.t0 = 4;
+    tl.sp = s.data(); tl.nz = n.data(); tl.L = L; tl.valid_s = L; tl.valid_n = L; tl.vmin = L; tl.T = 1 + L / HOP; tl.t0 = 8;
     tl.factor = 0.0f; tl.mixed_pcm = nullptr;
-    for (int lane = 0; lane < 32; ++lane) stage_pass1<true>(tb, tl, lane, frames);
-    static float yr[32][40], yi[32][40];
-    for (int j = 0; j < 2; ++j) {
-        for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, j, frames, yr[lane], yi[lane]);
-        for (int lane = 0; lane < 32; ++lane) pass2_store(lane, j, frames, yr[lane], yi[lane]);
-    }
-    for (int k = 0; k < NFFT; ++k) { out_re[k] = frames[2 * k]; out_im[k] = frames[2 * k + 1]; }
+    emul_fft_stages(w, h, tl);
+    for (int k = 0; k < NFFT; ++k) { out_re[k] = w.frames[2 * k]; out_im[k] = w.frames[2 * k + 1]; }
     return 0;
 }
 
@@ -62,47 +73,39 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
                             float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
     HostTables h;
     if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
-    FwdTables tb{h.window.data(), h.tw1t.data(), h.mel_w.data(), h.mel_lo.data(), h.mel_roundw.data()};
-    alignas(16) static float smem[WARP_SMEM_F];
-    memset(smem, 0, sizeof(smem));
-    float* frames = smem;
-    float* melst = smem + FPG * FRAME_F;
+    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
+    bool is_std = true;
+    for (int r = 0; r < MEL_ROUNDS; ++r) is_std = is_std && (h.mel_roundw[r] == std_w[r]);
+    static EmulWarp w;
+    memset(w.frames, 0, sizeof(w.frames));
+    for (int lane = 0; lane < 32; ++lane) pass1_win_reset(w.win[lane]);
     const int T = 1 + L / HOP, G = (T + FPG - 1) / FPG;
+    const bool have_noise = noise != nullptr;
     FwdTile tl{};
     tl.sp = speech; tl.nz = noise; tl.L = L;
     tl.valid_s = valid_s < L ? valid_s : L;
     tl.valid_n = valid_n < L ? valid_n : L;
-    tl.T = T; tl.factor = noise ? factor : 0.0f; tl.mixed_pcm = mixed_pcm;
-    FwdOut out[3];
-    float* dsts[3] = {out_sp, out_nz, out_mix};
-    for (int s = 0; s < 3; ++s) { out[s].dst = dsts[s]; out[s].layout = layout; out[s].n_slices = n_slices; out[s].ld_t = ld_t; }
+    tl.vmin = have_noise ? (tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n) : 0;
+    tl.T = T; tl.factor = have_noise ? factor : 0.0f; tl.mixed_pcm = mixed_pcm;
+    FwdOut out{};
+    out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
+    out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
     float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    static float yr[32][40], yi[32][40];
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * FPG;
-        const int vmin = tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n;
-        const bool interior = (tl.nz != nullptr) && (tl.t0 * HOP - HALF >= 0) && ((tl.t0 + FPG - 1) * HOP + HALF <= vmin) &&
-                              (tl.t0 + FPG - 1 < tl.T);
+        emul_fft_stages(w, h, tl);
+        for (int lane = 0; lane < 32; ++lane) stage_post(lane, tl.factor, w.frames, nullptr);
         for (int lane = 0; lane < 32; ++lane) {
-            if (interior) stage_pass1<false>(tb, tl, lane, frames);
-            else stage_pass1<true>(tb, tl, lane, frames);
+            if (is_std) stage_mel<true>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
+            else stage_mel<false>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
         }
-        for (int j = 0; j < 2; ++j) {
-            for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, j, frames, yr[lane], yi[lane]);
-            for (int lane = 0; lane < 32; ++lane) pass2_store(lane, j, frames, yr[lane], yi[lane]);
-        }
-        for (int lane = 0; lane < 32; ++lane) stage_post(lane, tl.factor, frames, nullptr);
-        for (int r = 0; r < MEL_ROUNDS; ++r)
-            for (int lane = 0; lane < 32; ++lane) stage_mel_round(lane, r, tb.mel_roundw[r], tb.mel_w, tb.mel_lo, frames, melst);
-        for (int s = 0; s < 3; ++s) {
-            if (s >= 1 && noise == nullptr) continue;
-            const float scale = (s == 1) ? tl.factor : 1.0f;
-            for (int q = 0; q < 3; ++q)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const float v = stage_db(lane, q, scale, melst + s * NMEL * FPG, out[s], tl.t0, T);
-                    if (v > mx[s]) mx[s] = v;
-                }
-        }
+        for (int lane = 0; lane < 32; ++lane) stage_mel_store(lane, w.acc[lane], w.frames);
+        for (int q = 0; q < 8; ++q)
+            for (int lane = 0; lane < 32; ++lane) {
+                float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
+                stage_db(lane, q, tl.factor, have_noise, w.frames, out, tl.t0, T, lm);
+                for (int s = 0; s < 3; ++s) if (lm[s] > mx[s]) mx[s] = lm[s];
+            }
     }
     for (int s = 0; s < 3; ++s) max3[s] = key_to_float(float_to_key(mx[s]));
     return 0;
