@@ -23,20 +23,20 @@ constexpr int HALF = NFFT / 2;       // reflect-pad width of librosa.stft(center
 constexpr int N1 = 16;
 constexpr int N2 = 40;
 
-// One warp owns a group of 4 consecutive STFT frames.
-constexpr int FPG = 4;
+// One warp owns a group of 2 consecutive STFT frames (10.9 KB of shared memory per warp -> 16 warps / SM).
+constexpr int FPG = 2;
 // Shared-memory frame buffer: 16 rows (k1) x 84 floats (40 complex + 2 pad) + 16 floats skew.
 constexpr int ROW_F = 84;
 constexpr int FRAME_F = N1 * ROW_F + 16;  // 1360 floats, == 16 (mod 32), multiple of 4
 constexpr int MEL_STAGE_F = 3 * NMEL * FPG;  // raw mel sums [sig][band][frame], staged over frame buffer 0
-constexpr int WARP_SMEM_F = FPG * FRAME_F;   // 5440 floats = 21760 B per warp
+constexpr int WARP_SMEM_F = FPG * FRAME_F;   // 2720 floats = 10880 B per warp
 static_assert(MEL_STAGE_F <= FRAME_F, "mel staging must fit in one frame buffer");
 
 // mel tables
 constexpr int MEL_WMAX = 24;    // max bins per band supported (reference config: 23)
 constexpr int MEL_WROW = 28;    // padded row stride of the weight table (16-byte rows, bank spread)
-constexpr int MEL_ROUNDS = NMEL / 8;
-constexpr int POST_CHUNK = 41;  // bins per lane in the pointwise post stage (8 lanes x 41 >= 321)
+constexpr int MEL_ROUNDS = NMEL / 16;   // one round = 16 consecutive bands x 2 frames
+constexpr int POST_CHUNK = 21;  // bins per lane in the pointwise post stage (16 lanes x 21 >= 321; odd: bank spread)
 
 constexpr float AMIN = 1e-5f;   // librosa.amplitude_to_db amin (dp:94)
 constexpr float TOP_DB = 80.0f; // librosa.amplitude_to_db top_db (dp:94)

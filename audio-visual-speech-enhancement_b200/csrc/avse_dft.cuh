@@ -123,4 +123,27 @@ AVSE_HD void dft40(const float (&xr)[40], const float (&xi)[40], float (&yr)[40]
     }
 }
 
+// In-place variant: element (8a + 5b) % 40 holds input n = (8a + 5b) % 40 on entry and, on exit,
+// element (8c + 5d) % 40 holds output k = (16c + 25d) % 40.  80 live registers instead of 160.
+AVSE_HD void dft40_inplace(float (&xr)[40], float (&xi)[40]) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        float tr[5], ti[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { tr[a] = xr[(8 * a + 5 * b) % 40]; ti[a] = xi[(8 * a + 5 * b) % 40]; }
+        dft5(tr, ti);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { xr[(8 * c + 5 * b) % 40] = tr[c]; xi[(8 * c + 5 * b) % 40] = ti[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        float tr[8], ti[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { tr[b] = xr[(8 * c + 5 * b) % 40]; ti[b] = xi[(8 * c + 5 * b) % 40]; }
+        dft8(tr, ti);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { xr[(8 * c + 5 * d) % 40] = tr[d]; xi[(8 * c + 5 * d) % 40] = ti[d]; }
+    }
+}
+
 }  // namespace avse

@@ -1,18 +1,18 @@
 // Warp-stage functions of the fused forward kernel (mix at SNR -> STFT -> mel -> dB).
 //
-// One warp owns a group of FPG = 4 consecutive STFT frames of one utterance and walks them
+// One warp owns a group of FPG = 2 consecutive STFT frames of one utterance and walks them
 // through five warp-synchronous stages that exchange data only through that warp's private
 // shared-memory region (no block-level barrier anywhere in the frame loop):
 //
-//   pass 1  lane = (frame, n2):   strided load of speech+noise (register sliding window: hop = 4
-//                                  strides, so a lane re-uses 12 of its 16 samples frame to frame),
+//   pass 1  lane = (frame, n2):   strided load of speech+noise (hop = 4 strides of 40 samples, so the
+//                                  two frames of a group share one batch of 20 loads per signal),
 //                                  Hann, packed z = s + i*n, DFT-16 over n1, twiddle W_640^{n2 k1}
 //                                                                          -> rows [k1][n2]
 //   pass 2  lane = (frame, k1):   DFT-40 over n2 (5 x 8 PFA)              -> Z[k] natural order
 //   post    lane = (frame, chunk): unpack S' = Z_k + conj Z_{N-k}, N' = (Z_k - conj Z_{N-k})/i,
 //                                  M' = S' + f N', three magnitudes       -> in place
 //   mel     lane = (frame, band):  banded Slaney filterbank sums           -> raw mel [sig][band][frame]
-//   dB      lane = band:           20 log10(max(1e-5, .)), running max, 16-byte stores
+//   dB      lane = (sig, band):    20 log10(max(1e-5, .)), running max, 8-byte stores
 //
 // Reference semantics: /root/reference/data_processor.py:77-96 (signal_to_spectrogram),
 // :130-133 (SNR mix), :35-57 (slice layout); librosa/mediaio semantics per SURVEY.md App. A.
@@ -64,15 +64,15 @@ struct FwdTables {
     const float* tw1t;        // [16][40][2]
     const float* mel_w;       // [80][MEL_WROW]
     const int* mel_lo;        // [80]
-    const int* mel_roundw;    // [10]
+    const int* mel_roundw;    // [MEL_ROUNDS]
 };
 
 // Mel round widths of the reference configuration (sr 16 kHz, fmin 0, fmax 8 kHz): max band width
-// over bands 8r..8r+7.  The specialised kernel unrolls the band loops with these constants; any
+// over bands 16r..16r+15.  The specialised kernel unrolls the band loops with these constants; any
 // other table uses the generic (runtime-width) kernel.
-#define AVSE_STD_ROUNDW {3, 3, 3, 4, 5, 7, 10, 13, 18, 23}
+#define AVSE_STD_ROUNDW {3, 4, 7, 13, 23}
 
-// One group of 4 frames of one utterance.
+// One group of FPG frames of one utterance.
 struct FwdTile {
     const float* sp;     // speech samples of this utterance
     const float* nz;     // noise samples (already fitted to the speech length), may be nullptr
@@ -81,7 +81,7 @@ struct FwdTile {
     int valid_n;         // samples present in nz
     int vmin;            // min(valid_s, valid_n) (0 when nz == nullptr): interior test
     int T;               // STFT frames: 1 + L / hop
-    int t0;              // first frame of the group (multiple of 4)
+    int t0;              // first frame of the group (multiple of FPG)
     float factor;        // SNR factor (dp:130); 0 when nz == nullptr
     float* mixed_pcm;    // [L] or nullptr: s + f*n (dp:133), zero-padded / truncated to L
 };
@@ -96,164 +96,122 @@ AVSE_HD float load_sample_edge(const float* p, int i, int L, int valid) {
 
 // A frame is "interior" when all 640 of its samples exist in both signals without reflection.
 AVSE_HD bool frame_interior(const FwdTile& tl, int t) {
-    return t * HOP - HALF >= 0 && t * HOP + HALF <= tl.vmin && t < tl.T;
+    return tl.nz != nullptr && t * HOP - HALF >= 0 && t * HOP + HALF <= tl.vmin && t < tl.T;
 }
 
-// Per-lane register state of pass 1 that survives from frame to frame (and group to group).
-struct Pass1Win {
-    float rs[16], rn[16];   // raw samples x[160 t - 320 + 40 n1 + lane] of frame `t_win`
-    float ns[4], nn[4];     // prefetched new samples for frame `t_pref`
-    int t_win;              // frame held in rs/rn, or -1
-    int t_pref;             // frame whose 4 new strides are in ns/nn, or -1
-};
-
-AVSE_HD void pass1_win_reset(Pass1Win& w) { w.t_win = -1; w.t_pref = -1; }
-
-// DFT-16 + twiddle + store of one (frame f, residue n2) column.
-AVSE_HD void pass1_finish(float (&xr)[16], float (&xi)[16], int f, int n2, const vec2* s_tw, float* frames) {
-    dft16(xr, xi);
-    float* row = frames + f * FRAME_F + 2 * n2;
-    {
-        vec2 v; v.x = xr[0]; v.y = xi[0];
-        *reinterpret_cast<vec2*>(row) = v;
+// ---------------------------------------------------------------------------------------
+// pass 1.  80 (frame, n2) columns per group over 32 lanes in three rounds:
+//   round 0: (frame 0, n2 = lane)   round 1: (frame 1, n2 = lane)   round 2: lanes 0..15 take
+//   (frame lane/8, n2 = 32 + lane%8).  Rounds 0 and 1 share one batch of 20 strided loads per
+//   signal (hop = 4 strides of 40 samples, so frame 1's column is frame 0's shifted by 4).
+//   The DFT-16 / twiddle / store code exists once (rolled loop) to stay inside the I-cache.
+// ---------------------------------------------------------------------------------------
+AVSE_HD void stage_pass1(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    const bool pair_interior = frame_interior(tl, tl.t0) && frame_interior(tl, tl.t0 + 1);
+    float rs[20], rn[20];
+    if (pair_interior) {
+        const float* ps = tl.sp + tl.t0 * HOP - HALF + lane;
+        const float* pn = tl.nz + tl.t0 * HOP - HALF + lane;
+#pragma unroll
+        for (int j = 0; j < 20; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
     }
-#pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) {
-        const vec2 tw = s_tw[k1 * N2 + n2];
-        vec2 v;
-        v.x = xr[k1] * tw.x - xi[k1] * tw.y;
-        v.y = xr[k1] * tw.y + xi[k1] * tw.x;
-        *reinterpret_cast<vec2*>(row + k1 * ROW_F) = v;
-    }
-}
-
-// Edge / generic task: every sample through the reflect + zero-pad loader.
-AVSE_HD void pass1_task_edge(const FwdTile& tl, int f, int n2, const float* s_win, const vec2* s_tw, float* frames) {
-    const int t_raw = tl.t0 + f;
-    const int t = t_raw < tl.T ? t_raw : tl.T - 1;
-    const int base = t * HOP - HALF + n2;
-    float xr[16], xi[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int i = base + N2 * n1;
-        const float s = load_sample_edge(tl.sp, i, tl.L, tl.valid_s);
-        const float n = load_sample_edge(tl.nz, i, tl.L, tl.valid_n);
-        if (n1 >= 8 && n1 < 12) {
-            // this frame's own hop: original samples [160 t, 160 t + 160)
-            if (tl.mixed_pcm != nullptr && t_raw < tl.T && i < tl.L) tl.mixed_pcm[i] = s + tl.factor * n;
-        }
-        const float w = s_win[N2 * n1 + n2];
-        xr[n1] = s * w;
-        xi[n1] = n * w;
-    }
-    pass1_finish(xr, xi, f, n2, s_tw, frames);
-}
-
-// Interior task for n2 = lane with the sliding register window.
-AVSE_HD void pass1_task_window(const FwdTile& tl, int f, int lane, Pass1Win& w, const float* s_win, const vec2* s_tw, float* frames) {
-    const int t = tl.t0 + f;
-    const float* ps = tl.sp + t * HOP - HALF + lane;
-    const float* pn = tl.nz + t * HOP - HALF + lane;
-    if (w.t_win == t - 1 && w.t_pref == t) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) { w.rs[j] = w.rs[j + 4]; w.rn[j] = w.rn[j + 4]; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { w.rs[12 + j] = w.ns[j]; w.rn[12 + j] = w.nn[j]; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { w.rs[j] = ps[N2 * j]; w.rn[j] = pn[N2 * j]; }
-    }
-    w.t_win = t;
-    // prefetch the 4 new strides of frame t+1 while this frame is transformed
-    if (frame_interior(tl, t + 1)) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { w.ns[j] = ps[HOP + N2 * (12 + j)]; w.nn[j] = pn[HOP + N2 * (12 + j)]; }
-        w.t_pref = t + 1;
-    } else {
-        w.t_pref = -1;
-    }
-    if (tl.mixed_pcm != nullptr) {
-        float* pm = tl.mixed_pcm + t * HOP + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pm[N2 * j] = w.rs[8 + j] + tl.factor * w.rn[8 + j];
-    }
-    float xr[16], xi[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const float wv = s_win[N2 * n1 + lane];
-        xr[n1] = w.rs[n1] * wv;
-        xi[n1] = w.rn[n1] * wv;
-    }
-    pass1_finish(xr, xi, f, lane, s_tw, frames);
-}
-
-// Interior task for the 8 left-over residues (n2 = 32..39): plain loads, no window.
-AVSE_HD void pass1_task_plain(const FwdTile& tl, int f, int n2, const float* s_win, const vec2* s_tw, float* frames) {
-    const int t = tl.t0 + f;
-    const float* ps = tl.sp + t * HOP - HALF + n2;
-    const float* pn = tl.nz + t * HOP - HALF + n2;
-    float xr[16], xi[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) { xr[n1] = ps[N2 * n1]; xi[n1] = pn[N2 * n1]; }
-    if (tl.mixed_pcm != nullptr) {
-        float* pm = tl.mixed_pcm + t * HOP + n2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pm[N2 * j] = xr[8 + j] + tl.factor * xi[8 + j];
-    }
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const float wv = s_win[N2 * n1 + n2];
-        xr[n1] *= wv;
-        xi[n1] *= wv;
-    }
-    pass1_finish(xr, xi, f, n2, s_tw, frames);
-}
-
-AVSE_HD void stage_pass1(const FwdTile& tl, int lane, Pass1Win& w, const float* s_win, const vec2* s_tw, float* frames) {
-    // tasks 0..3: (frame f, n2 = lane); task 4: (frame lane/8, n2 = 32 + lane%8)
-    const int fb = lane >> 3, n2b = 32 + (lane & 7);
-    const bool have_noise = tl.nz != nullptr;
 #pragma unroll 1
-    for (int f = 0; f < FPG; ++f) {
-        if (have_noise && frame_interior(tl, tl.t0 + f)) pass1_task_window(tl, f, lane, w, s_win, s_tw, frames);
-        else { pass1_task_edge(tl, f, lane, s_win, s_tw, frames); w.t_pref = -1; }
+    for (int round = 0; round < 3; ++round) {
+        const int f = round < 2 ? round : (lane >> 3) & 1;
+        const int n2 = round < 2 ? lane : 32 + (lane & 7);
+        const bool active = round < 2 || lane < 16;
+        const int t_raw = tl.t0 + f;
+        const int t = t_raw < tl.T ? t_raw : tl.T - 1;
+        const int base = t * HOP - HALF + n2;
+        if (round == 1 && pair_interior) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { rs[j] = rs[j + 4]; rn[j] = rn[j + 4]; }
+        } else if (!(round == 0 && pair_interior)) {
+            if (active) {
+                if (frame_interior(tl, t_raw)) {
+                    const float* ps = tl.sp + base;
+                    const float* pn = tl.nz + base;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        rs[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
+                        rn[j] = load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n);
+                    }
+                }
+            }
+        }
+        if (active) {
+            if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
+                // this frame's own hop: original samples [160 t, 160 t + 160) = strides n1 = 8..11
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = t * HOP + N2 * j + n2;
+                    if (i < tl.L) tl.mixed_pcm[i] = rs[8 + j] + tl.factor * rn[8 + j];
+                }
+            }
+            float xr[16], xi[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const float wv = s_win[N2 * n1 + n2];
+                xr[n1] = rs[n1] * wv;
+                xi[n1] = rn[n1] * wv;
+            }
+            dft16(xr, xi);
+            float* row = frames + f * FRAME_F + 2 * n2;
+            {
+                vec2 v; v.x = xr[0]; v.y = xi[0];
+                *reinterpret_cast<vec2*>(row) = v;
+            }
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) {
+                const vec2 tw = s_tw[k1 * N2 + n2];
+                vec2 v;
+                v.x = xr[k1] * tw.x - xi[k1] * tw.y;
+                v.y = xr[k1] * tw.y + xi[k1] * tw.x;
+                *reinterpret_cast<vec2*>(row + k1 * ROW_F) = v;
+            }
+        }
     }
-    if (have_noise && frame_interior(tl, tl.t0 + fb)) pass1_task_plain(tl, fb, n2b, s_win, s_tw, frames);
-    else pass1_task_edge(tl, fb, n2b, s_win, s_tw, frames);
 }
 
 // ---------------------------------------------------------------------------------------
-// pass 2: lane = (f = 2j + lane/16, k1 = lane%16); load + DFT-40, then (after a warp sync) store
+// pass 2: lane = (f = lane/16, k1 = lane%16): load row, in-place DFT-40; after a warp sync the
+// results are stored in natural order Z[k1 + 16 k2] over the same frame buffer.
 // ---------------------------------------------------------------------------------------
-AVSE_HD void pass2_compute(int lane, int j, const float* frames, float (&yr)[40], float (&yi)[40]) {
-    const int f = 2 * j + (lane >> 4), k1 = lane & 15;
+AVSE_HD void pass2_compute(int lane, const float* frames, float (&xr)[40], float (&xi)[40]) {
+    const int f = lane >> 4, k1 = lane & 15;
     const float* row = frames + f * FRAME_F + k1 * ROW_F;
-    float xr[40], xi[40];
 #pragma unroll
     for (int q = 0; q < 20; ++q) {
         const vec4 v = *reinterpret_cast<const vec4*>(row + 4 * q);
         xr[2 * q] = v.x; xi[2 * q] = v.y; xr[2 * q + 1] = v.z; xi[2 * q + 1] = v.w;
     }
-    dft40(xr, xi, yr, yi);
+    dft40_inplace(xr, xi);
 }
 
-AVSE_HD void pass2_store(int lane, int j, float* frames, const float (&yr)[40], const float (&yi)[40]) {
-    const int f = 2 * j + (lane >> 4), k1 = lane & 15;
+AVSE_HD void pass2_store(int lane, float* frames, const float (&xr)[40], const float (&xi)[40]) {
+    const int f = lane >> 4, k1 = lane & 15;
     float* z = frames + f * FRAME_F + 2 * k1;
 #pragma unroll
-    for (int k2 = 0; k2 < 40; ++k2) {
-        vec2 v; v.x = yr[k2]; v.y = yi[k2];
-        *reinterpret_cast<vec2*>(z + 2 * N1 * k2) = v;   // Z[k1 + 16 k2]
-    }
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int idx = (8 * c + 5 * d) % 40;     // register holding output (c, d)
+            const int k2 = (16 * c + 25 * d) % 40;    // its frequency index within the DFT-40
+            vec2 v; v.x = xr[idx]; v.y = xi[idx];
+            *reinterpret_cast<vec2*>(z + 2 * N1 * k2) = v;   // Z[k1 + 16 k2]
+        }
 }
 
 // ---------------------------------------------------------------------------------------
-// post: lane = (f = lane/8, chunk p = lane%8), bins k = 41p .. 41p+40 clipped to [1, 319]
+// post: lane = (f = lane/16, chunk p = lane%16), bins k = 21p .. 21p+20 clipped to [1, 319]
 // in place: slot k <- (|S'|, |N'|), slot 640-k <- (|M'|, 0)
 // ---------------------------------------------------------------------------------------
 AVSE_HD void stage_post(int lane, float factor, float* frames, vec2* stft_row) {
     // stft_row: optional [321] complex row of this lane's frame receiving X_speech (dp:79 D), or nullptr
-    const int f = lane >> 3, p = lane & 7;
+    const int f = lane >> 4, p = lane & 15;
     float* za = frames + f * FRAME_F + 2 * POST_CHUNK * p;            // slot k      = za + 2 i
     float* zc = frames + f * FRAME_F + 2 * (NFFT - POST_CHUNK * p);   // slot 640-k  = zc - 2 i
     const int k0 = POST_CHUNK * p;
@@ -282,13 +240,13 @@ AVSE_HD void stage_post(int lane, float factor, float* frames, vec2* stft_row) {
 }
 
 // ---------------------------------------------------------------------------------------
-// mel: round r, lane = (f = lane/8, band m = 8r + lane%8); W = number of bin iterations
+// mel: round r, lane = (f = lane/16, band m = 16r + lane%16); W = number of bin iterations
 // (compile-time for the specialised kernel).  Accumulates into as/an/am.
 // ---------------------------------------------------------------------------------------
 template <int W>
 AVSE_HD void mel_round_fixed(int lane, int r, const float* s_melw, const int* s_mello, const float* frames,
                              float& as, float& an, float& am) {
-    const int f = lane >> 3, m = 8 * r + (lane & 7);
+    const int f = lane >> 4, m = 16 * r + (lane & 15);
     const int lo = s_mello[m];
     const float* wrow = s_melw + m * MEL_WROW;
     const float* zs = frames + f * FRAME_F + 2 * lo;
@@ -315,7 +273,7 @@ AVSE_HD void mel_round_fixed(int lane, int r, const float* s_melw, const int* s_
 
 AVSE_HD void mel_round_generic(int lane, int r, int roundw, const float* s_melw, const int* s_mello, const float* frames,
                                float& as, float& an, float& am) {
-    const int f = lane >> 3, m = 8 * r + (lane & 7);
+    const int f = lane >> 4, m = 16 * r + (lane & 15);
     const int lo = s_mello[m];
     const float* wrow = s_melw + m * MEL_WROW;
     const float* zs = frames + f * FRAME_F + 2 * lo;
@@ -332,22 +290,17 @@ AVSE_HD void mel_round_generic(int lane, int r, int roundw, const float* s_melw,
     }
 }
 
-// All ten rounds; results stay in registers (acc[r][sig]) until every lane has finished reading
+// All five rounds; results stay in registers (acc[r][sig]) until every lane has finished reading
 // the frame buffers, then stage_mel_store writes them over frame buffer 0.
 template <bool STD>
 AVSE_HD void stage_mel(int lane, const int* roundw, const float* s_melw, const int* s_mello, const float* frames,
                        float (&acc)[MEL_ROUNDS][3]) {
     if (STD) {
         mel_round_fixed<3>(lane, 0, s_melw, s_mello, frames, acc[0][0], acc[0][1], acc[0][2]);
-        mel_round_fixed<3>(lane, 1, s_melw, s_mello, frames, acc[1][0], acc[1][1], acc[1][2]);
-        mel_round_fixed<3>(lane, 2, s_melw, s_mello, frames, acc[2][0], acc[2][1], acc[2][2]);
-        mel_round_fixed<4>(lane, 3, s_melw, s_mello, frames, acc[3][0], acc[3][1], acc[3][2]);
-        mel_round_fixed<5>(lane, 4, s_melw, s_mello, frames, acc[4][0], acc[4][1], acc[4][2]);
-        mel_round_fixed<7>(lane, 5, s_melw, s_mello, frames, acc[5][0], acc[5][1], acc[5][2]);
-        mel_round_fixed<10>(lane, 6, s_melw, s_mello, frames, acc[6][0], acc[6][1], acc[6][2]);
-        mel_round_fixed<13>(lane, 7, s_melw, s_mello, frames, acc[7][0], acc[7][1], acc[7][2]);
-        mel_round_fixed<18>(lane, 8, s_melw, s_mello, frames, acc[8][0], acc[8][1], acc[8][2]);
-        mel_round_fixed<23>(lane, 9, s_melw, s_mello, frames, acc[9][0], acc[9][1], acc[9][2]);
+        mel_round_fixed<4>(lane, 1, s_melw, s_mello, frames, acc[1][0], acc[1][1], acc[1][2]);
+        mel_round_fixed<7>(lane, 2, s_melw, s_mello, frames, acc[2][0], acc[2][1], acc[2][2]);
+        mel_round_fixed<13>(lane, 3, s_melw, s_mello, frames, acc[3][0], acc[3][1], acc[3][2]);
+        mel_round_fixed<23>(lane, 4, s_melw, s_mello, frames, acc[4][0], acc[4][1], acc[4][2]);
     } else {
 #pragma unroll
         for (int r = 0; r < MEL_ROUNDS; ++r)
@@ -355,12 +308,12 @@ AVSE_HD void stage_mel(int lane, const int* roundw, const float* s_melw, const i
     }
 }
 
-// raw mel layout in (dead) frame buffer 0: melst[(sig * 80 + band) * 4 + frame]
+// raw mel layout in (dead) frame buffer 0: melst[(sig * 80 + band) * 2 + frame]
 AVSE_HD void stage_mel_store(int lane, const float (&acc)[MEL_ROUNDS][3], float* melst) {
-    const int f = lane >> 3;
+    const int f = lane >> 4;
 #pragma unroll
     for (int r = 0; r < MEL_ROUNDS; ++r) {
-        const int m = 8 * r + (lane & 7);
+        const int m = 16 * r + (lane & 15);
         melst[(0 * NMEL + m) * FPG + f] = acc[r][0];   // speech
         melst[(1 * NMEL + m) * FPG + f] = acc[r][1];   // noise (unscaled)
         melst[(2 * NMEL + m) * FPG + f] = acc[r][2];   // mixture
@@ -395,16 +348,11 @@ AVSE_HD void stage_db(int lane, int q, float factor, bool have_noise, const floa
     if (sig > 0 && !have_noise) return;
     const int m = id - sig * NMEL;
     const float scale = sig == 1 ? factor : 1.0f;
-    const vec4 v = *reinterpret_cast<const vec4*>(melst + id * FPG);
-    float d[4];
-    d[0] = amp_to_db(v.x * scale);
-    d[1] = amp_to_db(v.y * scale);
-    d[2] = amp_to_db(v.z * scale);
-    d[3] = amp_to_db(v.w * scale);
-    float lm = neg_inf();
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-        if (t0 + f < T) lm = d[f] > lm ? d[f] : lm;
+    const vec2 v = *reinterpret_cast<const vec2*>(melst + id * FPG);
+    const float d0 = amp_to_db(v.x * scale);
+    const float d1 = amp_to_db(v.y * scale);
+    const bool v1 = t0 + 1 < T;    // frame t0 itself is always < T
+    const float lm = (v1 && d1 > d0) ? d1 : d0;
     mx[0] = (sig == 0 && lm > mx[0]) ? lm : mx[0];
     mx[1] = (sig == 1 && lm > mx[1]) ? lm : mx[1];
     mx[2] = (sig == 2 && lm > mx[2]) ? lm : mx[2];
@@ -412,23 +360,20 @@ AVSE_HD void stage_db(int lane, int q, float factor, bool have_noise, const floa
     if (dst == nullptr) return;
     if (out.layout == 0) {
         const int spss = 20;
-        const int sl = t0 / spss, tt = t0 - sl * spss;    // 4 | t0 and 4 | 20: a group never straddles slices
+        const int sl = t0 / spss, tt = t0 - sl * spss;    // 2 | t0 and 2 | 20: a group never straddles slices
         if (sl < out.n_slices) {
             float* p = dst + ((size_t)sl * NMEL + m) * spss + tt;
-            if (t0 + 3 < T) {
-                vec4 o; o.x = d[0]; o.y = d[1]; o.z = d[2]; o.w = d[3];
-                *reinterpret_cast<vec4*>(p) = o;
+            if (v1) {
+                vec2 o; o.x = d0; o.y = d1;
+                *reinterpret_cast<vec2*>(p) = o;
             } else {
-#pragma unroll
-                for (int f = 0; f < 4; ++f)
-                    if (t0 + f < T) p[f] = d[f];
+                p[0] = d0;
             }
         }
     } else {
         float* p = dst + (size_t)m * out.ld_t + t0;
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-            if (t0 + f < T) p[f] = d[f];
+        p[0] = d0;
+        if (v1) p[1] = d1;
     }
 }
 

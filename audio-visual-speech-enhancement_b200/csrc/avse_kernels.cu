@@ -173,7 +173,7 @@ extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* 
 // ---------------------------------------------------------------------------------------------
 // fused forward kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_WARPS = 4;
+constexpr int FWD_WARPS = 8;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
 // shared memory: per-warp frame buffers, then CTA-shared tables
 constexpr int FWD_SM_MELW = FWD_WARPS * WARP_SMEM_F;              // [80][MEL_WROW]
@@ -224,8 +224,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
     FwdTile tl{};
     FwdOut out{};
-    Pass1Win win;
-    pass1_win_reset(win);
     const bool have_noise = A.noise != nullptr;
 
     auto flush_max = [&](int u) {
@@ -245,7 +243,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         if (u != cur_u) {
             if (cur_u >= 0) flush_max(cur_u);
             cur_u = u;
-            pass1_win_reset(win);
             tl.sp = A.speech + (size_t)u * A.in_stride;
             tl.nz = have_noise ? A.noise + (size_t)u * A.in_stride : nullptr;
             tl.L = A.L;
@@ -267,23 +264,22 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         tl.t0 = g * FPG;
 
         // ---- pass 1 ----
-        stage_pass1(tl, lane, win, s_win, s_tw, frames);
+        stage_pass1(tl, lane, s_win, s_tw, frames);
         __syncwarp();
 
         // ---- pass 2 ----
-#pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
+        {
             float yr[40], yi[40];
-            pass2_compute(lane, j, frames, yr, yi);
+            pass2_compute(lane, frames, yr, yi);
             __syncwarp();
-            pass2_store(lane, j, frames, yr, yi);
+            pass2_store(lane, frames, yr, yi);
         }
         __syncwarp();
 
         // ---- post ----
         {
             vec2* srow = nullptr;
-            const int tf = tl.t0 + (lane >> 3);
+            const int tf = tl.t0 + (lane >> 4);
             if (A.stft_speech != nullptr && tf < tl.T)
                 srow = reinterpret_cast<vec2*>(A.stft_speech) + ((size_t)u * P.T + tf) * NBINS;
             stage_post(lane, tl.factor, frames, srow);

@@ -86,7 +86,7 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
         t.mel_lo[m] = lo;
         t.mel_width[m] = w;
         for (int j = 0; j < w; ++j) t.mel_w[(size_t)m * MEL_WROW + j] = (float)(0.5 * t.fb[(size_t)m * NBINS + lo + j]);
-        t.mel_roundw[m / 8] = std::max(t.mel_roundw[m / 8], w);
+        t.mel_roundw[m / 16] = std::max(t.mel_roundw[m / 16], w);
     }
 
     // column form (<= 2 non-zeros per bin) for lin = F^T y

@@ -20,7 +20,7 @@ struct HostTables {
     std::vector<int> mel_lo;          // [80]  first non-zero bin of each band
     std::vector<int> mel_width;       // [80]  number of non-zero bins
     std::vector<float> mel_w;         // [80][MEL_WROW]  0.5 * weight (0.5 = packed-FFT unpack factor)
-    std::vector<int> mel_roundw;      // [10]  max width over bands 8r..8r+7
+    std::vector<int> mel_roundw;      // [5]   max width over bands 16r..16r+15
 
     // inverse path
     std::vector<float> tri_w;         // [80] Thomas forward multipliers (w[0] unused)

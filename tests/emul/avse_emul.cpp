@@ -30,21 +30,19 @@ extern "C" int emul_tables_info(int sample_rate, double fmin, double fmax, int* 
     return 0;
 }
 
-// Runs the five warp stages for one group; `win` is the per-lane pass-1 register state.
+// One emulated warp: its private shared-memory region plus the per-lane registers that live across
+// a __syncwarp() in the kernel.
 struct EmulWarp {
     alignas(16) float frames[WARP_SMEM_F];
-    Pass1Win win[32];
     float yr[32][40], yi[32][40];
     float acc[32][MEL_ROUNDS][3];
 };
 
 static void emul_fft_stages(EmulWarp& w, const HostTables& h, const FwdTile& tl) {
     const vec2* s_tw = reinterpret_cast<const vec2*>(h.tw1t.data());
-    for (int lane = 0; lane < 32; ++lane) stage_pass1(tl, lane, w.win[lane], h.window.data(), s_tw, w.frames);
-    for (int j = 0; j < 2; ++j) {
-        for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, j, w.frames, w.yr[lane], w.yi[lane]);
-        for (int lane = 0; lane < 32; ++lane) pass2_store(lane, j, w.frames, w.yr[lane], w.yi[lane]);
-    }
+    for (int lane = 0; lane < 32; ++lane) stage_pass1(tl, lane, h.window.data(), s_tw, w.frames);
+    for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, w.frames, w.yr[lane], w.yi[lane]);
+    for (int lane = 0; lane < 32; ++lane) pass2_store(lane, w.frames, w.yr[lane], w.yi[lane]);
 }
 
 // 640-point FFT of one complex frame through pass 1 (with unit window) + pass 2: checks the
@@ -55,7 +53,6 @@ extern "C" int emul_fft640(const float* re, const float* im, float* out_re, floa
     for (auto& v : h.window) v = 1.0f;
     static EmulWarp w;
     memset(w.frames, 0, sizeof(w.frames));
-    for (int lane = 0; lane < 32; ++lane) pass1_win_reset(w.win[lane]);
     const int L = 8 * NFFT;
     std::vector<float> s(L, 0.0f), n(L, 0.0f);
     const int t = 8;  // frame 8 covers original samples [8*160-320, 8*160+320); group t0 = 8 is interior
@@ -78,7 +75,6 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
     for (int r = 0; r < MEL_ROUNDS; ++r) is_std = is_std && (h.mel_roundw[r] == std_w[r]);
     static EmulWarp w;
     memset(w.frames, 0, sizeof(w.frames));
-    for (int lane = 0; lane < 32; ++lane) pass1_win_reset(w.win[lane]);
     const int T = 1 + L / HOP, G = (T + FPG - 1) / FPG;
     const bool have_noise = noise != nullptr;
     FwdTile tl{};
