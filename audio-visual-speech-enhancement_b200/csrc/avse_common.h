@@ -17,6 +17,7 @@ constexpr int NFFT = 640;            // dp:44   int(16000 / 25)
 constexpr int HOP = 160;             // dp:45   int(n_fft / 4)
 constexpr int NBINS = NFFT / 2 + 1;  // 321
 constexpr int NMEL = 80;             // dp:86
+constexpr int SPSS = 20;             // dp:49   spectrogram frames per 200 ms slice
 constexpr int HALF = NFFT / 2;       // reflect-pad width of librosa.stft(center=True)
 
 // FFT-640 factorisation: n = 40*n1 + n2, k = k1 + 16*k2  (DFT-16, twiddle, DFT-40 = 5 x 8 PFA)

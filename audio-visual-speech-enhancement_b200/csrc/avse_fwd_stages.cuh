@@ -12,7 +12,7 @@
 //   post    lane = (frame, chunk): unpack S' = Z_k + conj Z_{N-k}, N' = (Z_k - conj Z_{N-k})/i,
 //                                  M' = S' + f N', three magnitudes       -> in place
 //   mel     lane = (frame, band):  banded Slaney filterbank sums           -> raw mel [sig][band][frame]
-//   dB      lane = (sig, band):    20 log10(max(1e-5, .)), running max, 8-byte stores
+//   dB      lane = band:           20 log10(max(1e-5, .)), running max, 8-byte stores
 //
 // Reference semantics: /root/reference/data_processor.py:77-96 (signal_to_spectrogram),
 // :130-133 (SNR mix), :35-57 (slice layout); librosa/mediaio semantics per SURVEY.md App. A.
@@ -94,86 +94,114 @@ AVSE_HD float load_sample_edge(const float* p, int i, int L, int valid) {
     return (p != nullptr && i < valid) ? p[i] : 0.0f;
 }
 
-// A frame is "interior" when all 640 of its samples exist in both signals without reflection.
-AVSE_HD bool frame_interior(const FwdTile& tl, int t) {
-    return tl.nz != nullptr && t * HOP - HALF >= 0 && t * HOP + HALF <= tl.vmin && t < tl.T;
+// A group is "interior" when both of its frames exist and all their samples are present in both
+// signals without reflection or zero padding.
+AVSE_HD bool group_interior(const FwdTile& tl) {
+    return tl.nz != nullptr && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 1) * HOP + HALF <= tl.vmin && tl.t0 + 1 < tl.T;
 }
 
 // ---------------------------------------------------------------------------------------
 // pass 1.  80 (frame, n2) columns per group over 32 lanes in three rounds:
 //   round 0: (frame 0, n2 = lane)   round 1: (frame 1, n2 = lane)   round 2: lanes 0..15 take
-//   (frame lane/8, n2 = 32 + lane%8).  Rounds 0 and 1 share one batch of 20 strided loads per
-//   signal (hop = 4 strides of 40 samples, so frame 1's column is frame 0's shifted by 4).
-//   The DFT-16 / twiddle / store code exists once (rolled loop) to stay inside the I-cache.
+//   (frame lane/8, n2 = 32 + lane%8).
 // ---------------------------------------------------------------------------------------
-AVSE_HD void stage_pass1(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
-    const bool pair_interior = frame_interior(tl, tl.t0) && frame_interior(tl, tl.t0 + 1);
-    float rs[20], rn[20];
-    if (pair_interior) {
-        const float* ps = tl.sp + tl.t0 * HOP - HALF + lane;
-        const float* pn = tl.nz + tl.t0 * HOP - HALF + lane;
+// DFT-16 over n1, twiddle W_640^{n2 k1}, store column n2 of frame f as rows [k1][n2].
+AVSE_HD void pass1_column(float (&xr)[16], float (&xi)[16], int f, int n2, const vec2* s_tw, float* frames) {
+    dft16(xr, xi);
+    float* row = frames + f * FRAME_F + 2 * n2;
+    const vec2* tw = s_tw + n2;
+    {
+        vec2 v; v.x = xr[0]; v.y = xi[0];
+        *reinterpret_cast<vec2*>(row) = v;
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) {
+        const vec2 t = tw[k1 * N2];
+        vec2 v;
+        v.x = xr[k1] * t.x - xi[k1] * t.y;
+        v.y = xr[k1] * t.y + xi[k1] * t.x;
+        *reinterpret_cast<vec2*>(row + k1 * ROW_F) = v;
+    }
+}
+
+// Interior fast path: no reflection, no bounds checks, rounds unrolled with static register indices.
+// Rounds 0 and 1 share one batch of 20 strided loads per signal (frame 1's column is frame 0's
+// shifted by 4 strides) and the 16 window values of residue n2 = lane.
+AVSE_HD void stage_pass1_interior(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    const int o0 = tl.t0 * HOP - HALF + lane;
+    float xr[16], xi[16];
+    {
+        const float* ps = tl.sp + o0;
+        const float* pn = tl.nz + o0;
+        float rs[20], rn[20], wv[16];
 #pragma unroll
         for (int j = 0; j < 20; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = s_win[N2 * j + lane];
+        if (tl.mixed_pcm != nullptr) {
+            // own hops: frame 0 -> strides 8..11, frame 1 -> strides 12..15 of the shared batch
+            float* pm = tl.mixed_pcm + o0 + HALF;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pm[N2 * j] = rs[8 + j] + tl.factor * rn[8 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { xr[j] = rs[j] * wv[j]; xi[j] = rn[j] * wv[j]; }
+        pass1_column(xr, xi, 0, lane, s_tw, frames);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { xr[j] = rs[4 + j] * wv[j]; xi[j] = rn[4 + j] * wv[j]; }
+        pass1_column(xr, xi, 1, lane, s_tw, frames);
     }
+    if (lane < 16) {
+        const int f = (lane >> 3) & 1, n2 = 32 + (lane & 7);
+        const int o2 = (tl.t0 + f) * HOP - HALF + n2;
+        const float* ps = tl.sp + o2;
+        const float* pn = tl.nz + o2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { xr[j] = ps[N2 * j]; xi[j] = pn[N2 * j]; }
+        if (tl.mixed_pcm != nullptr) {
+            float* pm = tl.mixed_pcm + o2 + HALF;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pm[N2 * j] = xr[8 + j] + tl.factor * xi[8 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] *= w; xi[j] *= w; }
+        pass1_column(xr, xi, f, n2, s_tw, frames);
+    }
+}
+
+// Edge / generic path (first and last frames, short or zero-padded signals, single-signal mode):
+// every sample goes through the reflect + zero-pad loader.  Cold code, rolled.
+AVSE_HD void stage_pass1_edge(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
 #pragma unroll 1
     for (int round = 0; round < 3; ++round) {
         const int f = round < 2 ? round : (lane >> 3) & 1;
         const int n2 = round < 2 ? lane : 32 + (lane & 7);
-        const bool active = round < 2 || lane < 16;
+        if (round == 2 && lane >= 16) continue;
         const int t_raw = tl.t0 + f;
-        const int t = t_raw < tl.T ? t_raw : tl.T - 1;
+        const int t = t_raw < tl.T ? t_raw : tl.T - 1;   // frames past the end duplicate the last one (never stored)
         const int base = t * HOP - HALF + n2;
-        if (round == 1 && pair_interior) {
+        float xr[16], xi[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { rs[j] = rs[j + 4]; rn[j] = rn[j + 4]; }
-        } else if (!(round == 0 && pair_interior)) {
-            if (active) {
-                if (frame_interior(tl, t_raw)) {
-                    const float* ps = tl.sp + base;
-                    const float* pn = tl.nz + base;
+        for (int j = 0; j < 16; ++j) {
+            xr[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
+            xi[j] = load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n);
+        }
+        if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        rs[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
-                        rn[j] = load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n);
-                    }
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int i = t * HOP + N2 * j + n2;    // this frame's own hop: strides 8..11
+                if (i < tl.L) tl.mixed_pcm[i] = xr[8 + j] + tl.factor * xi[8 + j];
             }
         }
-        if (active) {
-            if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
-                // this frame's own hop: original samples [160 t, 160 t + 160) = strides n1 = 8..11
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = t * HOP + N2 * j + n2;
-                    if (i < tl.L) tl.mixed_pcm[i] = rs[8 + j] + tl.factor * rn[8 + j];
-                }
-            }
-            float xr[16], xi[16];
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const float wv = s_win[N2 * n1 + n2];
-                xr[n1] = rs[n1] * wv;
-                xi[n1] = rn[n1] * wv;
-            }
-            dft16(xr, xi);
-            float* row = frames + f * FRAME_F + 2 * n2;
-            {
-                vec2 v; v.x = xr[0]; v.y = xi[0];
-                *reinterpret_cast<vec2*>(row) = v;
-            }
-#pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) {
-                const vec2 tw = s_tw[k1 * N2 + n2];
-                vec2 v;
-                v.x = xr[k1] * tw.x - xi[k1] * tw.y;
-                v.y = xr[k1] * tw.y + xi[k1] * tw.x;
-                *reinterpret_cast<vec2*>(row + k1 * ROW_F) = v;
-            }
-        }
+        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] *= w; xi[j] *= w; }
+        pass1_column(xr, xi, f, n2, s_tw, frames);
     }
+}
+
+AVSE_HD void stage_pass1(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    if (group_interior(tl)) stage_pass1_interior(tl, lane, s_win, s_tw, frames);
+    else stage_pass1_edge(tl, lane, s_win, s_tw, frames);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -206,35 +234,42 @@ AVSE_HD void pass2_store(int lane, float* frames, const float (&xr)[40], const f
 }
 
 // ---------------------------------------------------------------------------------------
-// post: lane = (f = lane/16, chunk p = lane%16), bins k = 21p .. 21p+20 clipped to [1, 319]
-// in place: slot k <- (|S'|, |N'|), slot 640-k <- (|M'|, 0)
+// post: lane = (f = lane/16, chunk p = lane%16), bins k = 21p .. 21p+20 (p = 15: 315..319 only).
+// In place: slot k <- (|S'|, |N'|), slot 640-k <- (|M'|, 0).  Bin 0 is processed like any other
+// (its "magnitudes" are garbage but finite and carry zero mel weight).
+// STFT: also emit X_speech[k] (dp:79 D) to stft_row[0..320].
 // ---------------------------------------------------------------------------------------
+template <bool STFT>
 AVSE_HD void stage_post(int lane, float factor, float* frames, vec2* stft_row) {
-    // stft_row: optional [321] complex row of this lane's frame receiving X_speech (dp:79 D), or nullptr
     const int f = lane >> 4, p = lane & 15;
     float* za = frames + f * FRAME_F + 2 * POST_CHUNK * p;            // slot k      = za + 2 i
     float* zc = frames + f * FRAME_F + 2 * (NFFT - POST_CHUNK * p);   // slot 640-k  = zc - 2 i
-    const int k0 = POST_CHUNK * p;
+    const bool last = p == 15;
+    constexpr int LAST_N = (NBINS - 1) - 15 * POST_CHUNK;              // 5 bins in the last chunk
+    if (STFT && stft_row != nullptr && last) {
+        vec2 d; d.x = za[2 * LAST_N]; d.y = 0.0f;                      // Nyquist bin 320 (real for real input)
+        stft_row[NBINS - 1] = d;
+    }
 #pragma unroll
     for (int i = 0; i < POST_CHUNK; ++i) {
-        const int k = k0 + i;
-        if ((unsigned)(k - 1) <= (unsigned)(NBINS - 3)) {
-            const vec2 a = *reinterpret_cast<const vec2*>(za + 2 * i);
-            const vec2 c = *reinterpret_cast<const vec2*>(zc - 2 * i);
-            const float sr = a.x + c.x, si = a.y - c.y;     // 2 * X_speech[k]
-            const float nr = a.y + c.y, ni = c.x - a.x;     // 2 * X_noise[k]
-            const float mr = sr + factor * nr, mi = si + factor * ni;
-            vec2 o1, o2;
-            o1.x = fast_sqrt(sr * sr + si * si);
-            o1.y = fast_sqrt(nr * nr + ni * ni);
-            o2.x = fast_sqrt(mr * mr + mi * mi);
-            o2.y = 0.0f;
-            *reinterpret_cast<vec2*>(za + 2 * i) = o1;
-            *reinterpret_cast<vec2*>(zc - 2 * i) = o2;
-            if (stft_row != nullptr) { vec2 d; d.x = 0.5f * sr; d.y = 0.5f * si; stft_row[k] = d; }
-        } else if (stft_row != nullptr && (k == 0 || k == NBINS - 1)) {
-            vec2 d; d.x = za[2 * i]; d.y = 0.0f;   // DC / Nyquist of the real part of the packed input
-            stft_row[k] = d;
+        if (i >= LAST_N && last) continue;
+        const vec2 a = *reinterpret_cast<const vec2*>(za + 2 * i);
+        const vec2 c = *reinterpret_cast<const vec2*>(zc - 2 * i);
+        const float sr = a.x + c.x, si = a.y - c.y;     // 2 * X_speech[k]
+        const float nr = a.y + c.y, ni = c.x - a.x;     // 2 * X_noise[k]
+        const float mr = sr + factor * nr, mi = si + factor * ni;
+        vec2 o1, o2;
+        o1.x = fast_sqrt(sr * sr + si * si);
+        o1.y = fast_sqrt(nr * nr + ni * ni);
+        o2.x = fast_sqrt(mr * mr + mi * mi);
+        o2.y = 0.0f;
+        *reinterpret_cast<vec2*>(za + 2 * i) = o1;
+        *reinterpret_cast<vec2*>(zc - 2 * i) = o2;
+        if (STFT && stft_row != nullptr) {
+            vec2 d;
+            if (i == 0 && p == 0) { d.x = a.x; d.y = 0.0f; }    // DC bin (real for real input)
+            else { d.x = 0.5f * sr; d.y = 0.5f * si; }
+            stft_row[POST_CHUNK * p + i] = d;
         }
     }
 }
@@ -321,9 +356,9 @@ AVSE_HD void stage_mel_store(int lane, const float (&acc)[MEL_ROUNDS][3], float*
 }
 
 // ---------------------------------------------------------------------------------------
-// dB: 240 (signal, band) tasks in 8 sub-rounds of 32 lanes: id = 32 q + lane, sig = id / 80
-// (0 speech, 1 noise, 2 mixture).  Output layouts: slices [n_slices][80][20] (dp:49-57) or
-// spectrogram [80][ld_t].  Folds the max dB over the valid frames into mx[sig].
+// dB: lane = band m = 32 q + lane (q = 0..2), all three signals of both frames.
+// Output layouts: slices [n_slices][80][20] (dp:49-57) or spectrogram [80][ld_t].
+// Folds the max dB over the valid frames into mx[sig] (0 speech, 1 noise, 2 mixture).
 // ---------------------------------------------------------------------------------------
 struct FwdOut {
     float* dst[3];    // base of this utterance's output per signal (nullptr: skip stores)
@@ -342,38 +377,37 @@ AVSE_HD float neg_inf() {
 
 AVSE_HD void stage_db(int lane, int q, float factor, bool have_noise, const float* melst, const FwdOut& out, int t0, int T,
                       float (&mx)[3]) {
-    const int id = 32 * q + lane;
-    if (id >= 3 * NMEL) return;
-    const int sig = id >= 2 * NMEL ? 2 : (id >= NMEL ? 1 : 0);
-    if (sig > 0 && !have_noise) return;
-    const int m = id - sig * NMEL;
-    const float scale = sig == 1 ? factor : 1.0f;
-    const vec2 v = *reinterpret_cast<const vec2*>(melst + id * FPG);
-    const float d0 = amp_to_db(v.x * scale);
-    const float d1 = amp_to_db(v.y * scale);
+    const int m = 32 * q + lane;
+    if (m >= NMEL) return;
     const bool v1 = t0 + 1 < T;    // frame t0 itself is always < T
-    const float lm = (v1 && d1 > d0) ? d1 : d0;
-    mx[0] = (sig == 0 && lm > mx[0]) ? lm : mx[0];
-    mx[1] = (sig == 1 && lm > mx[1]) ? lm : mx[1];
-    mx[2] = (sig == 2 && lm > mx[2]) ? lm : mx[2];
-    float* dst = sig == 0 ? out.dst[0] : (sig == 1 ? out.dst[1] : out.dst[2]);
-    if (dst == nullptr) return;
+    int off;                       // element offset of (band m, frame t0) inside this utterance's output
+    bool store = true;
     if (out.layout == 0) {
-        const int spss = 20;
-        const int sl = t0 / spss, tt = t0 - sl * spss;    // 2 | t0 and 2 | 20: a group never straddles slices
-        if (sl < out.n_slices) {
-            float* p = dst + ((size_t)sl * NMEL + m) * spss + tt;
-            if (v1) {
+        const int sl = t0 / SPSS, tt = t0 - sl * SPSS;   // 2 | t0 and 2 | 20: a group never straddles slices
+        off = (sl * NMEL + m) * SPSS + tt;
+        store = sl < out.n_slices;
+    } else {
+        off = m * out.ld_t + t0;
+    }
+#pragma unroll
+    for (int sig = 0; sig < 3; ++sig) {
+        if (sig > 0 && !have_noise) break;
+        const vec2 v = *reinterpret_cast<const vec2*>(melst + (sig * NMEL + m) * FPG);
+        const float scale = sig == 1 ? factor : 1.0f;
+        const float d0 = amp_to_db(v.x * scale);
+        const float d1 = amp_to_db(v.y * scale);
+        const float lm = (v1 && d1 > d0) ? d1 : d0;
+        mx[sig] = lm > mx[sig] ? lm : mx[sig];
+        float* dst = out.dst[sig];
+        if (dst != nullptr && store) {
+            if (v1 && !(off & 1)) {
                 vec2 o; o.x = d0; o.y = d1;
-                *reinterpret_cast<vec2*>(p) = o;
+                *reinterpret_cast<vec2*>(dst + off) = o;    // off is even: 8-byte aligned
             } else {
-                p[0] = d0;
+                dst[off] = d0;
+                if (v1) dst[off + 1] = d1;
             }
         }
-    } else {
-        float* p = dst + (size_t)m * out.ld_t + t0;
-        p[0] = d0;
-        if (v1) p[1] = d1;
     }
 }
 

@@ -1,4 +1,4 @@
-// CUDA kernels (sm_100a) + C ABI of the spectral front/back end.  See include/avse_b200.h.
+// CUDA kernels (sm_100a) + C ABI of the forward spectral path.  See include/avse_b200.h.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -9,52 +9,38 @@
 #include "../../include/avse_b200.h"
 #include "avse_common.h"
 #include "avse_tables.h"
+#include "avse_ctx.h"
 #include "avse_fwd_stages.cuh"
 
 using namespace avse;
 
 // ---------------------------------------------------------------------------------------------
-// context
+// context / errors
 // ---------------------------------------------------------------------------------------------
-struct avse_ctx {
-    int device = 0;
-    int num_sms = 148;
-    HostTables host;
-    // device tables (one allocation)
-    void* dbase = nullptr;
-    FwdTables fwd{};
-    const float* d_tri_w = nullptr;
-    const float* d_tri_ipiv = nullptr;
-    const float* d_tri_sup = nullptr;
-    const int* d_col_band = nullptr;
-    const float* d_col_w = nullptr;
-};
-
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-static int cuda_fail(cudaError_t e, const char* where) {
+int avse_fail(int code, const std::string& msg) { g_err = msg; return code; }
+int avse_cuda_fail(cudaError_t e, const char* where) {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
     return (int)e;
 }
-#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
 
 extern "C" const char* avse_last_error(void) { return g_err.c_str(); }
-extern "C" const char* avse_version(void) { return "avse_b200 0.1 (sm_100a)"; }
+extern "C" const char* avse_version(void) { return "avse_b200 0.2 (sm_100a)"; }
 
 extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device, avse_ctx** out) {
-    if (out == nullptr) return fail(AVSE_E_ARG, "avse_create: out is NULL");
+    if (out == nullptr) return avse_fail(AVSE_E_ARG, "avse_create: out is NULL");
     *out = nullptr;
     avse_ctx* c = new (std::nothrow) avse_ctx();
-    if (c == nullptr) return fail(AVSE_E_ARG, "avse_create: out of host memory");
+    if (c == nullptr) return avse_fail(AVSE_E_ARG, "avse_create: out of host memory");
     if (!build_tables(c->host, sample_rate, fmin, fmax)) {
         std::string e = c->host.error;
         delete c;
-        return fail(AVSE_E_CONFIG, "avse_create: " + e);
+        return avse_fail(AVSE_E_CONFIG, "avse_create: " + e);
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) { delete c; return fail(AVSE_E_NOCUDA, "avse_create: no CUDA device (this library has no CPU path)"); }
-    if (device < 0 || device >= ndev) { delete c; return fail(AVSE_E_ARG, "avse_create: bad device index"); }
+    if (e != cudaSuccess || ndev == 0) { delete c; return avse_fail(AVSE_E_NOCUDA, "avse_create: no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) { delete c; return avse_fail(AVSE_E_ARG, "avse_create: bad device index"); }
     c->device = device;
     int prev = 0;
     cudaGetDevice(&prev);
@@ -76,9 +62,9 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     std::vector<char> stage(total, 0);
     for (auto& s : secs) memcpy(stage.data() + s.off, s.src, s.bytes);
     e = cudaMalloc(&c->dbase, total);
-    if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return cuda_fail(e, "cudaMalloc(tables)"); }
+    if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return avse_cuda_fail(e, "cudaMalloc(tables)"); }
     e = cudaMemcpy(c->dbase, stage.data(), total, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(c->dbase); delete c; cudaSetDevice(prev); return cuda_fail(e, "cudaMemcpy(tables)"); }
+    if (e != cudaSuccess) { cudaFree(c->dbase); delete c; cudaSetDevice(prev); return avse_cuda_fail(e, "cudaMemcpy(tables)"); }
     char* b = (char*)c->dbase;
     c->fwd.window = (const float*)(b + secs[0].off);
     c->fwd.tw1t = (const float*)(b + secs[1].off);
@@ -90,6 +76,9 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->d_tri_sup = (const float*)(b + secs[7].off);
     c->d_col_band = (const int*)(b + secs[8].off);
     c->d_col_w = (const float*)(b + secs[9].off);
+    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
+    c->std_tables = true;
+    for (int r = 0; r < MEL_ROUNDS; ++r) c->std_tables = c->std_tables && (h.mel_roundw[r] == std_w[r]);
     cudaSetDevice(prev);
     *out = c;
     return 0;
@@ -108,7 +97,7 @@ extern "C" void avse_destroy(avse_ctx* ctx) {
 }
 
 extern "C" int avse_get_filterbank(const avse_ctx* ctx, double* host_out) {
-    if (ctx == nullptr || host_out == nullptr) return fail(AVSE_E_ARG, "avse_get_filterbank: NULL argument");
+    if (ctx == nullptr || host_out == nullptr) return avse_fail(AVSE_E_ARG, "avse_get_filterbank: NULL argument");
     memcpy(host_out, ctx->host.fb.data(), sizeof(double) * NMEL * NBINS);
     return 0;
 }
@@ -163,15 +152,15 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const float* __res
 
 extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride, const int* lengths,
                                int B, int L, const float* snr_db, float* factor_out, int* max_key, void* stream) {
-    if (!ctx || !speech || !noise || !factor_out) return fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
-    if (B <= 0 || L <= 0 || stride < L) return fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
+    if (!ctx || !speech || !noise || !factor_out) return avse_fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
+    if (B <= 0 || L <= 0 || stride < L) return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
     avse_snr_factor_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused forward kernel
+// fused forward kernel: persistent warps, each owning a contiguous range of (utterance, group) tiles
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_WARPS = 8;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
@@ -189,79 +178,79 @@ static_assert(2 * (FWD_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit")
 struct FwdParams {
     avse_forward_args a;
     FwdTables tb;
-    int T;   // frames per utterance
-    int G;   // groups of 4 frames per utterance
+    int T;            // frames per utterance
+    int G;            // groups of FPG frames per utterance
+    int total_tiles;  // B * G
+    int per_warp;     // tiles per warp (contiguous range)
 };
 
 template <bool STD>
 __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* s_melw = smem + FWD_SM_MELW;
-    int* s_mello = reinterpret_cast<int*>(smem + FWD_SM_MELLO);
-    int* s_roundw = reinterpret_cast<int*>(smem + FWD_SM_ROUNDW);
-    float* s_win = smem + FWD_SM_WIN;
-    vec2* s_tw = reinterpret_cast<vec2*>(smem + FWD_SM_TW);
-    for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) s_melw[i] = P.tb.mel_w[i];
-    for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) s_mello[i] = P.tb.mel_lo[i];
-    if (threadIdx.x < MEL_ROUNDS) s_roundw[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
-    for (int i = threadIdx.x; i < NFFT; i += FWD_THREADS) s_win[i] = P.tb.window[i];
+    for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) smem[FWD_SM_MELW + i] = P.tb.mel_w[i];
+    for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_MELLO)[i] = P.tb.mel_lo[i];
+    if (threadIdx.x < MEL_ROUNDS) reinterpret_cast<int*>(smem + FWD_SM_ROUNDW)[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
+    for (int i = threadIdx.x; i < NFFT; i += FWD_THREADS) smem[FWD_SM_WIN + i] = P.tb.window[i];
     for (int i = threadIdx.x; i < N1 * N2 * 2; i += FWD_THREADS) smem[FWD_SM_TW + i] = P.tb.tw1t[i];
     float* frames = smem + warp * WARP_SMEM_F;
     // keep never-written pad slots finite (they are multiplied by exact-zero weights)
     for (int i = lane; i < WARP_SMEM_F; i += 32) frames[i] = 0.0f;
     __syncthreads();
 
+    const float* s_melw = smem + FWD_SM_MELW;
+    const int* s_mello = reinterpret_cast<const int*>(smem + FWD_SM_MELLO);
+    const int* s_roundw = reinterpret_cast<const int*>(smem + FWD_SM_ROUNDW);
+    const float* s_win = smem + FWD_SM_WIN;
+    const vec2* s_tw = reinterpret_cast<const vec2*>(smem + FWD_SM_TW);
+
     const avse_forward_args& A = P.a;
-    const long long total = (long long)A.B * P.G;
-    const long long nwarps = (long long)gridDim.x * FWD_WARPS;
-    const long long per = (total + nwarps - 1) / nwarps;
-    const long long gw = (long long)blockIdx.x * FWD_WARPS + warp;
-    long long tile = gw * per;
-    const long long tile_end = (tile + per < total) ? tile + per : total;
-
-    int cur_u = -1;
-    float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
-    FwdTile tl{};
-    FwdOut out{};
     const bool have_noise = A.noise != nullptr;
+    const int gw = blockIdx.x * FWD_WARPS + warp;
+    int tile = gw * P.per_warp;
+    int n_tiles = P.total_tiles - tile;
+    n_tiles = n_tiles < P.per_warp ? n_tiles : P.per_warp;
+    if (n_tiles <= 0) return;
+    int u = tile / P.G;
+    int g = tile - u * P.G;
 
-    auto flush_max = [&](int u) {
+    float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
+    float factor = 0.0f;
+    int vs = 0, vn = 0;
+    bool fresh = true;
+
+    auto flush_max = [&](int uu) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             float v = mx[s];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) atomicMax(A.max_key + 3 * u + s, float_to_key(v));
+            if (lane == 0) atomicMax(A.max_key + 3 * uu + s, float_to_key(v));
             mx[s] = neg_inf();
         }
     };
 
-    for (; tile < tile_end; ++tile) {
-        const int u = (int)(tile / P.G);
-        const int g = (int)(tile - (long long)u * P.G);
-        if (u != cur_u) {
-            if (cur_u >= 0) flush_max(cur_u);
-            cur_u = u;
-            tl.sp = A.speech + (size_t)u * A.in_stride;
-            tl.nz = have_noise ? A.noise + (size_t)u * A.in_stride : nullptr;
-            tl.L = A.L;
-            tl.T = P.T;
-            int vs = A.len_speech ? A.len_speech[u] : A.L;
-            int vn = A.len_noise ? A.len_noise[u] : vs;
-            tl.valid_s = vs < A.L ? vs : A.L;
-            tl.valid_n = vn < A.L ? vn : A.L;
-            tl.vmin = have_noise ? (tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n) : 0;
-            tl.factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
-            tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
-            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
-            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
-            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
-            out.layout = A.layout;
-            out.n_slices = A.n_slices;
-            out.ld_t = A.ld_t;
+#pragma unroll 1
+    for (int it = 0; it < n_tiles; ++it) {
+        if (fresh) {
+            fresh = false;
+            vs = A.len_speech ? A.len_speech[u] : A.L;
+            vn = A.len_noise ? A.len_noise[u] : vs;
+            vs = vs < A.L ? vs : A.L;
+            vn = vn < A.L ? vn : A.L;
+            factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
         }
+        FwdTile tl;
+        tl.sp = A.speech + (size_t)u * A.in_stride;
+        tl.nz = have_noise ? A.noise + (size_t)u * A.in_stride : nullptr;
+        tl.L = A.L;
+        tl.valid_s = vs;
+        tl.valid_n = vn;
+        tl.vmin = have_noise ? (vs < vn ? vs : vn) : 0;
+        tl.T = P.T;
         tl.t0 = g * FPG;
+        tl.factor = factor;
+        tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
 
         // ---- pass 1 ----
         stage_pass1(tl, lane, s_win, s_tw, frames);
@@ -279,10 +268,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         // ---- post ----
         {
             vec2* srow = nullptr;
-            const int tf = tl.t0 + (lane >> 4);
-            if (A.stft_speech != nullptr && tf < tl.T)
+            const int tf = g * FPG + (lane >> 4);
+            if (A.stft_speech != nullptr && tf < P.T)
                 srow = reinterpret_cast<vec2*>(A.stft_speech) + ((size_t)u * P.T + tf) * NBINS;
-            stage_post(lane, tl.factor, frames, srow);
+            if (A.stft_speech != nullptr) stage_post<true>(lane, factor, frames, srow);
+            else stage_post<false>(lane, factor, frames, nullptr);
         }
         __syncwarp();
 
@@ -296,58 +286,71 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         __syncwarp();
 
         // ---- dB + stores ----
+        {
+            FwdOut out;
+            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
+            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
+            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+            out.layout = A.layout;
+            out.n_slices = A.n_slices;
+            out.ld_t = A.ld_t;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) stage_db(lane, q, tl.factor, have_noise, frames, out, tl.t0, tl.T, mx);
+            for (int q = 0; q < 3; ++q) stage_db(lane, q, factor, have_noise, frames, out, g * FPG, P.T, mx);
+        }
         __syncwarp();
-    }
-    if (cur_u >= 0) flush_max(cur_u);
-}
 
-static bool tables_are_std(const HostTables& h) {
-    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
-    for (int r = 0; r < MEL_ROUNDS; ++r)
-        if (h.mel_roundw[r] != std_w[r]) return false;
-    return true;
+        if (++g == P.G) {
+            flush_max(u);
+            g = 0;
+            ++u;
+            fresh = true;
+        }
+    }
+    if (!fresh) flush_max(u);
 }
 
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
-    if (!ctx || !args) return fail(AVSE_E_ARG, "avse_forward: NULL argument");
+    if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_forward: NULL argument");
     const avse_forward_args& a = *args;
-    if (!a.speech || !a.max_key) return fail(AVSE_E_ARG, "avse_forward: speech and max_key are required");
-    if (a.B <= 0 || a.L <= HALF) return fail(AVSE_E_ARG, "avse_forward: need B > 0 and L > 320 (reflect padding)");
-    if (!a.len_speech && a.in_stride < a.L) return fail(AVSE_E_ARG, "avse_forward: in_stride < L needs len_speech");
-    if (a.layout != AVSE_LAYOUT_SLICES && a.layout != AVSE_LAYOUT_SPEC) return fail(AVSE_E_ARG, "avse_forward: bad layout");
+    if (!a.speech || !a.max_key) return avse_fail(AVSE_E_ARG, "avse_forward: speech and max_key are required");
+    if (a.B <= 0 || a.L <= HALF) return avse_fail(AVSE_E_ARG, "avse_forward: need B > 0 and L > 320 (reflect padding)");
+    if (!a.len_speech && a.in_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_forward: in_stride < L needs len_speech");
+    if (a.layout != AVSE_LAYOUT_SLICES && a.layout != AVSE_LAYOUT_SPEC) return avse_fail(AVSE_E_ARG, "avse_forward: bad layout");
     FwdParams P;
     P.a = a;
     P.tb = ctx->fwd;
     P.T = 1 + a.L / HOP;
     P.G = (P.T + FPG - 1) / FPG;
     if (a.layout == AVSE_LAYOUT_SLICES) {
-        if (a.n_slices < 0 || (long long)a.n_slices * AVSE_SPSS > P.T) return fail(AVSE_E_ARG, "avse_forward: n_slices exceeds int(T/20) (dp:50)");
-        if (a.out_stride < (long long)a.n_slices * NMEL * AVSE_SPSS) return fail(AVSE_E_ARG, "avse_forward: out_stride too small");
+        if (a.n_slices < 0 || (long long)a.n_slices * AVSE_SPSS > P.T) return avse_fail(AVSE_E_ARG, "avse_forward: n_slices exceeds int(T/20) (dp:50)");
+        if (a.out_stride < (long long)a.n_slices * NMEL * AVSE_SPSS) return avse_fail(AVSE_E_ARG, "avse_forward: out_stride too small");
     } else {
-        if (a.ld_t < P.T) return fail(AVSE_E_ARG, "avse_forward: ld_t < T");
-        if (a.out_stride < (long long)NMEL * a.ld_t) return fail(AVSE_E_ARG, "avse_forward: out_stride too small");
+        if (a.ld_t < P.T) return avse_fail(AVSE_E_ARG, "avse_forward: ld_t < T");
+        if (a.out_stride < (long long)NMEL * a.ld_t) return avse_fail(AVSE_E_ARG, "avse_forward: out_stride too small");
     }
-    if (a.mixed_pcm && a.pcm_stride < a.L) return fail(AVSE_E_ARG, "avse_forward: pcm_stride < L");
+    if (a.mixed_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_forward: pcm_stride < L");
     float* outs[3] = {a.out_speech, a.out_noise, a.out_mixed};
     for (int s = 0; s < 3; ++s)
-        if (outs[s] && (((size_t)outs[s] & 15) || (a.out_stride & 3))) return fail(AVSE_E_ARG, "avse_forward: outputs must be 16-byte aligned with out_stride % 4 == 0");
+        if (outs[s] && (((size_t)outs[s] & 15) || (a.out_stride & 3))) return avse_fail(AVSE_E_ARG, "avse_forward: outputs must be 16-byte aligned with out_stride % 4 == 0");
+    const long long total = (long long)a.B * P.G;
+    if (total > 0x7fffffffLL) return avse_fail(AVSE_E_ARG, "avse_forward: B * groups exceeds 2^31; split the batch");
 
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (dev != ctx->device) return fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
+    if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
     if (configured_dev != dev) {
         CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
         configured_dev = dev;
     }
-    const long long total = (long long)a.B * P.G;
     long long blocks = 2LL * ctx->num_sms;
     const long long need = (total + FWD_WARPS - 1) / FWD_WARPS;
     if (blocks > need) blocks = need;
-    if (tables_are_std(ctx->host)) avse_forward_kernel<true><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    const long long nwarps = blocks * FWD_WARPS;
+    P.total_tiles = (int)total;
+    P.per_warp = (int)((total + nwarps - 1) / nwarps);
+    if (ctx->std_tables) avse_forward_kernel<true><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     else avse_forward_kernel<false><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -373,9 +376,9 @@ __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restri
 
 extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B, const int* max_key,
                                   int which, void* stream) {
-    if (!ctx || !data || !max_key) return fail(AVSE_E_ARG, "avse_floor_inplace: NULL argument");
-    if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt || which < 0 || which > 2) return fail(AVSE_E_ARG, "avse_floor_inplace: bad sizes");
-    if (((size_t)data & 15) || (stride & 3)) return fail(AVSE_E_ARG, "avse_floor_inplace: data must be 16-byte aligned with stride % 4 == 0");
+    if (!ctx || !data || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: NULL argument");
+    if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: bad sizes");
+    if (((size_t)data & 15) || (stride & 3)) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: data must be 16-byte aligned with stride % 4 == 0");
     long long bx = (n_per_utt / 4 + 255) / 256;
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
@@ -403,8 +406,8 @@ __global__ void __launch_bounds__(256) avse_floor_gather_kernel(const float* __r
 
 extern "C" int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, int ld_t, float* slices,
                                  long long slices_stride, int n_slices, int B, const int* max_key, int which, void* stream) {
-    if (!ctx || !spec || !slices || !max_key) return fail(AVSE_E_ARG, "avse_floor_gather: NULL argument");
-    if (B <= 0 || n_slices <= 0 || ld_t < n_slices * AVSE_SPSS || which < 0 || which > 2) return fail(AVSE_E_ARG, "avse_floor_gather: bad sizes");
+    if (!ctx || !spec || !slices || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_gather: NULL argument");
+    if (B <= 0 || n_slices <= 0 || ld_t < n_slices * AVSE_SPSS || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_gather: bad sizes");
     const int n = n_slices * NMEL * AVSE_SPSS;
     int bx = (n + 255) / 256;
     if (bx > 64) bx = 64;
@@ -420,7 +423,7 @@ __global__ void avse_reset_max_kernel(int* __restrict__ max_key, int n) {
 }
 
 extern "C" int avse_reset_max(avse_ctx* ctx, int* max_key, int n, void* stream) {
-    if (!ctx || !max_key || n <= 0) return fail(AVSE_E_ARG, "avse_reset_max: bad argument");
+    if (!ctx || !max_key || n <= 0) return avse_fail(AVSE_E_ARG, "avse_reset_max: bad argument");
     avse_reset_max_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_key, n);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -432,7 +435,7 @@ __global__ void avse_max_db_kernel(const int* __restrict__ max_key, int n, float
 }
 
 extern "C" int avse_max_db(avse_ctx* ctx, const int* max_key, int n, float* out_db, void* stream) {
-    if (!ctx || !max_key || !out_db || n <= 0) return fail(AVSE_E_ARG, "avse_max_db: bad argument");
+    if (!ctx || !max_key || !out_db || n <= 0) return avse_fail(AVSE_E_ARG, "avse_max_db: bad argument");
     avse_max_db_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_key, n, out_db);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -90,13 +90,13 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * FPG;
         emul_fft_stages(w, h, tl);
-        for (int lane = 0; lane < 32; ++lane) stage_post(lane, tl.factor, w.frames, nullptr);
+        for (int lane = 0; lane < 32; ++lane) stage_post<false>(lane, tl.factor, w.frames, nullptr);
         for (int lane = 0; lane < 32; ++lane) {
             if (is_std) stage_mel<true>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
             else stage_mel<false>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
         }
         for (int lane = 0; lane < 32; ++lane) stage_mel_store(lane, w.acc[lane], w.frames);
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < 3; ++q)
             for (int lane = 0; lane < 32; ++lane) {
                 float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
                 stage_db(lane, q, tl.factor, have_noise, w.frames, out, tl.t0, T, lm);
