@@ -48,11 +48,14 @@ def load(build=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build:
-        build_library()
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("AVSE_B200_LIB")  # tuning experiments: a variant build of the same sources
+    if not path:
+        if build:
+            build_library()
+        path = LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError("libavse_b200.so is missing; run `python -m __graft_entry__` / build() first (no CPU fallback exists)")
-    lib = _c.CDLL(LIB_PATH)
+    lib = _c.CDLL(path)
     vp, ll, i32, f64 = _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_double
     lib.avse_create.argtypes = [i32, f64, f64, i32, _c.POINTER(vp)]
     lib.avse_create.restype = i32

@@ -52,6 +52,16 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(out_path, defines, verbose=False):
+    """Tuning helper: compile the same sources with extra -D macros into another .so (see AVSE_B200_LIB)."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D%s" % d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return res.stderr
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -28,7 +28,13 @@ constexpr int N2 = 40;
 constexpr int FPG = 2;
 // Shared-memory frame buffer: 16 rows (k1) x 84 floats (40 complex + 2 pad) + 16 floats skew.
 constexpr int ROW_F = 84;
-constexpr int FRAME_F = N1 * ROW_F + 16;  // 1360 floats, == 16 (mod 32), multiple of 4
+// Layout of one frame region (floats): [0, 1344) rows / natural-order Z (Z uses [0, 1282)),
+// [1344, 1360) never written (kept zero: "null" partial sums), [1360, 1456) chunk-end partial sums
+// of the fused post+mel scan (16 chunks x 6 floats).
+constexpr int FRAME_ZERO_F = N1 * ROW_F;        // 1344
+constexpr int FRAME_FLUSH_F = N1 * ROW_F + 16;  // 1360
+constexpr int FRAME_F = FRAME_FLUSH_F + 96;     // 1456 floats, == 16 (mod 32), multiple of 4
+constexpr int SCAN_BINS = 336;                  // 16 chunks x POST_CHUNK bins (bins >= 320 unused)
 constexpr int MEL_STAGE_F = 3 * NMEL * FPG;  // raw mel sums [sig][band][frame], staged over frame buffer 0
 constexpr int WARP_SMEM_F = FPG * FRAME_F;   // 2720 floats = 10880 B per warp
 static_assert(MEL_STAGE_F <= FRAME_F, "mel staging must fit in one frame buffer");

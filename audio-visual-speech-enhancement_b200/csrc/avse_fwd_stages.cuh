@@ -65,6 +65,8 @@ struct FwdTables {
     const float* mel_w;       // [80][MEL_WROW]
     const int* mel_lo;        // [80]
     const int* mel_roundw;    // [MEL_ROUNDS]
+    const float* scan_w;      // [SCAN_BINS][2]  fused post+mel scan weights (avse_tables.h)
+    const int* scan_loc;      // [80][4]
 };
 
 // Mel round widths of the reference configuration (sr 16 kHz, fmin 0, fmax 8 kHz): max band width
@@ -199,8 +201,38 @@ AVSE_HD void stage_pass1_edge(const FwdTile& tl, int lane, const float* s_win, c
     }
 }
 
+// Interior path, rolled: one copy of the column code, every round loads its own 16 strides per
+// signal (the 12 shared with the previous round come from L1/L2).  Smaller code and fewer live
+// registers than the unrolled variant at the price of 24 more loads per group.
+AVSE_HD void stage_pass1_interior_rolled(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+#pragma unroll 1
+    for (int round = 0; round < 3; ++round) {
+        if (round == 2 && lane >= 16) break;
+        const int f = round < 2 ? round : (lane >> 3) & 1;
+        const int n2 = round < 2 ? lane : 32 + (lane & 7);
+        const int o = (tl.t0 + f) * HOP - HALF + n2;
+        const float* ps = tl.sp + o;
+        const float* pn = tl.nz + o;
+        float xr[16], xi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { xr[j] = ps[N2 * j]; xi[j] = pn[N2 * j]; }
+        if (tl.mixed_pcm != nullptr) {
+            float* pm = tl.mixed_pcm + o + HALF;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pm[N2 * j] = xr[8 + j] + tl.factor * xi[8 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] *= w; xi[j] *= w; }
+        pass1_column(xr, xi, f, n2, s_tw, frames);
+    }
+}
+
 AVSE_HD void stage_pass1(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+#if defined(AVSE_PASS1_ROLLED)
+    if (group_interior(tl)) stage_pass1_interior_rolled(tl, lane, s_win, s_tw, frames);
+#else
     if (group_interior(tl)) stage_pass1_interior(tl, lane, s_win, s_tw, frames);
+#endif
     else stage_pass1_edge(tl, lane, s_win, s_tw, frames);
 }
 
@@ -403,6 +435,120 @@ AVSE_HD void stage_db(int lane, int q, float factor, bool have_noise, const floa
             if (v1 && !(off & 1)) {
                 vec2 o; o.x = d0; o.y = d1;
                 *reinterpret_cast<vec2*>(dst + off) = o;    // off is even: 8-byte aligned
+            } else {
+                dst[off] = d0;
+                if (v1) dst[off + 1] = d1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused post + mel "scan" (used when HostTables::scan_ok): lane = (chunk p = lane/2, frame f = lane%2)
+// walks its 21 bins in order, unpacks the three magnitudes in registers and accumulates them straight
+// into two running band sums: A = band seg-1 (falling edge), B = band seg (rising edge).  When the
+// segment index advances (sign bit of the table's wA), A is complete for this lane: it is written over
+// the bin's own, already consumed, slots and the accumulators rotate.  The two sums left at the end of
+// the chunk go to the frame's flush area.  The magnitudes never touch shared memory, and the banded
+// gather of the generic path (the dominant source of bank conflicts) disappears.
+// s_scan: [SCAN_BINS] (wA | emit flag, wB).
+// ---------------------------------------------------------------------------------------
+template <bool STFT>
+AVSE_HD void stage_post_scan(int lane, float factor, const vec2* s_scan, float* frames, vec2* stft_row) {
+    const int f = lane & 1, p = lane >> 1;
+    float* fr = frames + f * FRAME_F;
+    float* za = fr + 2 * POST_CHUNK * p;            // slot k      = za + 2 i
+    float* zc = fr + 2 * (NFFT - POST_CHUNK * p);   // slot 640-k  = zc - 2 i
+    const vec2* tab = s_scan + POST_CHUNK * p;
+    const bool last = p == 15;
+    constexpr int LAST_N = (NBINS - 1) - 15 * POST_CHUNK;              // 5 bins in the last chunk
+    if (STFT && stft_row != nullptr && last) {
+        vec2 d; d.x = za[2 * LAST_N]; d.y = 0.0f;                      // Nyquist bin 320 (real for real input)
+        stft_row[NBINS - 1] = d;
+    }
+    float As = 0.0f, An = 0.0f, Am = 0.0f, Bs = 0.0f, Bn = 0.0f, Bm = 0.0f;
+#pragma unroll
+    for (int i = 0; i < POST_CHUNK; ++i) {
+        if (i >= LAST_N && last) continue;
+        const vec2 a = *reinterpret_cast<const vec2*>(za + 2 * i);
+        const vec2 c = *reinterpret_cast<const vec2*>(zc - 2 * i);
+        const vec2 w = tab[i];
+#if defined(__CUDA_ARCH__)
+        const bool emit = __float_as_int(w.x) < 0;
+#else
+        const bool emit = std::signbit(w.x);
+#endif
+        if (emit) {
+            vec2 o1, o2;
+            o1.x = As; o1.y = An; o2.x = Am; o2.y = 0.0f;
+            *reinterpret_cast<vec2*>(za + 2 * i) = o1;
+            *reinterpret_cast<vec2*>(zc - 2 * i) = o2;
+        }
+        const float sr = a.x + c.x, si = a.y - c.y;     // 2 * X_speech[k]
+        const float nr = a.y + c.y, ni = c.x - a.x;     // 2 * X_noise[k]
+        const float mr = sr + factor * nr, mi = si + factor * ni;
+        const float ms = fast_sqrt(sr * sr + si * si);
+        const float mn = fast_sqrt(nr * nr + ni * ni);
+        const float mm = fast_sqrt(mr * mr + mi * mi);
+        const float wa = fabsf(w.x), wb = w.y;
+        const float a_s = emit ? Bs : As, a_n = emit ? Bn : An, a_m = emit ? Bm : Am;
+        const float b_s = emit ? 0.0f : Bs, b_n = emit ? 0.0f : Bn, b_m = emit ? 0.0f : Bm;
+        As = a_s + wa * ms; An = a_n + wa * mn; Am = a_m + wa * mm;
+        Bs = b_s + wb * ms; Bn = b_n + wb * mn; Bm = b_m + wb * mm;
+        if (STFT && stft_row != nullptr) {
+            vec2 d;
+            if (i == 0 && p == 0) { d.x = a.x; d.y = 0.0f; }    // DC bin (real for real input)
+            else { d.x = 0.5f * sr; d.y = 0.5f * si; }
+            stft_row[POST_CHUNK * p + i] = d;
+        }
+    }
+    float* fl = fr + FRAME_FLUSH_F + 6 * p;
+    { vec2 o; o.x = As; o.y = An; *reinterpret_cast<vec2*>(fl + 0) = o; }
+    { vec2 o; o.x = Bs; o.y = Bn; *reinterpret_cast<vec2*>(fl + 2) = o; }
+    { vec2 o; o.x = Am; o.y = Bm; *reinterpret_cast<vec2*>(fl + 4) = o; }
+}
+
+struct alignas(16) ivec4 { int x, y, z, w; };
+
+// dB stage of the scan path: lane = band m = 32 q + lane; each band's mel sum is the sum of its two
+// partial-sum locations (s_loc[m] = frame-relative offsets SN0, M0, SN1, M1; absent parts point at zeros).
+AVSE_HD void stage_db_scan(int lane, int q, float factor, bool have_noise, const ivec4* s_loc, const float* frames,
+                           const FwdOut& out, int t0, int T, float (&mx)[3]) {
+    const int m = 32 * q + lane;
+    if (m >= NMEL) return;
+    const ivec4 loc = s_loc[m];
+    float mel[3][2];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const float* fr = frames + f * FRAME_F;
+        const vec2 sn0 = *reinterpret_cast<const vec2*>(fr + loc.x);
+        const vec2 sn1 = *reinterpret_cast<const vec2*>(fr + loc.z);
+        mel[0][f] = sn0.x + sn1.x;
+        mel[1][f] = (sn0.y + sn1.y) * factor;
+        mel[2][f] = fr[loc.y] + fr[loc.w];
+    }
+    const bool v1 = t0 + 1 < T;    // frame t0 itself is always < T
+    int off;
+    bool store = true;
+    if (out.layout == 0) {
+        const int sl = t0 / SPSS, tt = t0 - sl * SPSS;   // 2 | t0 and 2 | 20: a group never straddles slices
+        off = (sl * NMEL + m) * SPSS + tt;
+        store = sl < out.n_slices;
+    } else {
+        off = m * out.ld_t + t0;
+    }
+#pragma unroll
+    for (int sig = 0; sig < 3; ++sig) {
+        if (sig > 0 && !have_noise) break;
+        const float d0 = amp_to_db(mel[sig][0]);
+        const float d1 = amp_to_db(mel[sig][1]);
+        const float lm = (v1 && d1 > d0) ? d1 : d0;
+        mx[sig] = lm > mx[sig] ? lm : mx[sig];
+        float* dst = out.dst[sig];
+        if (dst != nullptr && store) {
+            if (v1 && !(off & 1)) {
+                vec2 o; o.x = d0; o.y = d1;
+                *reinterpret_cast<vec2*>(dst + off) = o;
             } else {
                 dst[off] = d0;
                 if (v1) dst[off + 1] = d1;

@@ -56,6 +56,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
         {h.mel_roundw.data(), h.mel_roundw.size() * 4, 0}, {h.tri_w.data(), h.tri_w.size() * 4, 0},
         {h.tri_ipiv.data(), h.tri_ipiv.size() * 4, 0}, {h.tri_sup.data(), h.tri_sup.size() * 4, 0},
         {h.col_band.data(), h.col_band.size() * 4, 0}, {h.col_w.data(), h.col_w.size() * 4, 0},
+        {h.scan_w.data(), h.scan_w.size() * 4, 0},     {h.scan_loc.data(), h.scan_loc.size() * 4, 0},
     };
     size_t total = 0;
     for (auto& s : secs) { s.off = total; total += (s.bytes + 255) / 256 * 256; }
@@ -76,9 +77,9 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->d_tri_sup = (const float*)(b + secs[7].off);
     c->d_col_band = (const int*)(b + secs[8].off);
     c->d_col_w = (const float*)(b + secs[9].off);
-    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
-    c->std_tables = true;
-    for (int r = 0; r < MEL_ROUNDS; ++r) c->std_tables = c->std_tables && (h.mel_roundw[r] == std_w[r]);
+    c->fwd.scan_w = (const float*)(b + secs[10].off);
+    c->fwd.scan_loc = (const int*)(b + secs[11].off);
+    c->std_tables = h.scan_ok;   // fused post+mel scan kernel; otherwise the generic band-gather kernel
     cudaSetDevice(prev);
     *out = c;
     return 0;
@@ -162,18 +163,31 @@ extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* 
 // ---------------------------------------------------------------------------------------------
 // fused forward kernel: persistent warps, each owning a contiguous range of (utterance, group) tiles
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_WARPS = 8;
+#ifndef AVSE_FWD_WARPS
+#define AVSE_FWD_WARPS 8       // warps per CTA
+#endif
+#ifndef AVSE_FWD_CTAS
+#define AVSE_FWD_CTAS 2        // resident CTAs per SM (sets the register cap through __launch_bounds__)
+#endif
+constexpr int FWD_WARPS = AVSE_FWD_WARPS;
+constexpr int FWD_CTAS = AVSE_FWD_CTAS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
-// shared memory: per-warp frame buffers, then CTA-shared tables
-constexpr int FWD_SM_MELW = FWD_WARPS * WARP_SMEM_F;              // [80][MEL_WROW]
-constexpr int FWD_SM_MELLO = FWD_SM_MELW + NMEL * MEL_WROW;       // [80] int
-constexpr int FWD_SM_ROUNDW = FWD_SM_MELLO + NMEL;                // [16] int
-constexpr int FWD_SM_WIN = FWD_SM_ROUNDW + 16;                    // [640]
+// shared memory: per-warp frame buffers, then CTA-shared tables: window, twiddles, then either the
+// scan tables (SCAN kernel) or the banded weight tables (generic kernel)
+constexpr int FWD_SM_WIN = FWD_WARPS * WARP_SMEM_F;               // [640]
 constexpr int FWD_SM_TW = FWD_SM_WIN + NFFT;                      // [16][40] vec2
-constexpr int FWD_SMEM_F = FWD_SM_TW + N1 * N2 * 2;
+constexpr int FWD_SM_MODE = FWD_SM_TW + N1 * N2 * 2;
+constexpr int FWD_SM_SCANW = FWD_SM_MODE;                         // SCAN: [SCAN_BINS] vec2
+constexpr int FWD_SM_SCANLOC = FWD_SM_SCANW + SCAN_BINS * 2;      // SCAN: [80] ivec4
+constexpr int FWD_SM_MELW = FWD_SM_MODE;                          // generic: [80][MEL_WROW]
+constexpr int FWD_SM_MELLO = FWD_SM_MELW + NMEL * MEL_WROW;       // generic: [80] int
+constexpr int FWD_SM_ROUNDW = FWD_SM_MELLO + NMEL;                // generic: [16] int
+constexpr int FWD_SMEM_F_SCAN = FWD_SM_SCANLOC + NMEL * 4;
+constexpr int FWD_SMEM_F_GEN = FWD_SM_ROUNDW + 16;
+constexpr int FWD_SMEM_F = FWD_SMEM_F_GEN > FWD_SMEM_F_SCAN ? FWD_SMEM_F_GEN : FWD_SMEM_F_SCAN;
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_F * 4;
-static_assert((FWD_SM_MELW % 4) == 0 && (FWD_SM_TW % 2) == 0, "table alignment");
-static_assert(2 * (FWD_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
+static_assert((FWD_SM_MODE % 4) == 0 && (FWD_SM_TW % 2) == 0 && (FWD_SM_SCANLOC % 4) == 0, "table alignment");
+static_assert(FWD_CTAS * (FWD_SMEM_BYTES + 1024) <= 233472, "the resident CTAs must fit in shared memory");
 
 struct FwdParams {
     avse_forward_args a;
@@ -184,13 +198,19 @@ struct FwdParams {
     int per_warp;     // tiles per warp (contiguous range)
 };
 
-template <bool STD>
-__global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __grid_constant__ FwdParams P) {
+// SCAN = true: fused post+mel scan (tables with scan_ok); false: generic banded gather.
+template <bool SCAN>
+__global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) smem[FWD_SM_MELW + i] = P.tb.mel_w[i];
-    for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_MELLO)[i] = P.tb.mel_lo[i];
-    if (threadIdx.x < MEL_ROUNDS) reinterpret_cast<int*>(smem + FWD_SM_ROUNDW)[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
+    if (SCAN) {
+        for (int i = threadIdx.x; i < SCAN_BINS * 2; i += FWD_THREADS) smem[FWD_SM_SCANW + i] = P.tb.scan_w[i];
+        for (int i = threadIdx.x; i < NMEL * 4; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_SCANLOC)[i] = P.tb.scan_loc[i];
+    } else {
+        for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) smem[FWD_SM_MELW + i] = P.tb.mel_w[i];
+        for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_MELLO)[i] = P.tb.mel_lo[i];
+        if (threadIdx.x < MEL_ROUNDS) reinterpret_cast<int*>(smem + FWD_SM_ROUNDW)[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
+    }
     for (int i = threadIdx.x; i < NFFT; i += FWD_THREADS) smem[FWD_SM_WIN + i] = P.tb.window[i];
     for (int i = threadIdx.x; i < N1 * N2 * 2; i += FWD_THREADS) smem[FWD_SM_TW + i] = P.tb.tw1t[i];
     float* frames = smem + warp * WARP_SMEM_F;
@@ -265,25 +285,31 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
         }
         __syncwarp();
 
-        // ---- post ----
+        // ---- post (+ mel) ----
         {
             vec2* srow = nullptr;
-            const int tf = g * FPG + (lane >> 4);
+            const int tf = g * FPG + (SCAN ? (lane & 1) : (lane >> 4));
             if (A.stft_speech != nullptr && tf < P.T)
                 srow = reinterpret_cast<vec2*>(A.stft_speech) + ((size_t)u * P.T + tf) * NBINS;
-            if (A.stft_speech != nullptr) stage_post<true>(lane, factor, frames, srow);
-            else stage_post<false>(lane, factor, frames, nullptr);
+            if (SCAN) {
+                const vec2* s_scan = reinterpret_cast<const vec2*>(smem + FWD_SM_SCANW);
+                if (A.stft_speech != nullptr) stage_post_scan<true>(lane, factor, s_scan, frames, srow);
+                else stage_post_scan<false>(lane, factor, s_scan, frames, nullptr);
+            } else {
+                if (A.stft_speech != nullptr) stage_post<true>(lane, factor, frames, srow);
+                else stage_post<false>(lane, factor, frames, nullptr);
+            }
         }
         __syncwarp();
 
-        // ---- mel (results staged over the now-dead frame buffer 0) ----
-        {
+        if (!SCAN) {
+            // ---- generic mel (results staged over the now-dead frame buffer 0) ----
             float acc[MEL_ROUNDS][3];
-            stage_mel<STD>(lane, s_roundw, s_melw, s_mello, frames, acc);
+            stage_mel<false>(lane, s_roundw, s_melw, s_mello, frames, acc);
             __syncwarp();
             stage_mel_store(lane, acc, frames);
+            __syncwarp();
         }
-        __syncwarp();
 
         // ---- dB + stores ----
         {
@@ -294,8 +320,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) avse_forward_kernel(const __gr
             out.layout = A.layout;
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
+            if (SCAN) {
+                const ivec4* s_loc = reinterpret_cast<const ivec4*>(smem + FWD_SM_SCANLOC);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) stage_db(lane, q, factor, have_noise, frames, out, g * FPG, P.T, mx);
+                for (int q = 0; q < 3; ++q) stage_db_scan(lane, q, factor, have_noise, s_loc, frames, out, g * FPG, P.T, mx);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) stage_db(lane, q, factor, have_noise, frames, out, g * FPG, P.T, mx);
+            }
         }
         __syncwarp();
 
@@ -344,7 +376,7 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
         CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
         configured_dev = dev;
     }
-    long long blocks = 2LL * ctx->num_sms;
+    long long blocks = (long long)FWD_CTAS * ctx->num_sms;
     const long long need = (total + FWD_WARPS - 1) / FWD_WARPS;
     if (blocks > need) blocks = need;
     const long long nwarps = blocks * FWD_WARPS;

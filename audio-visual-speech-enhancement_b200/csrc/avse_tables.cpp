@@ -131,6 +131,59 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
         t.tri_ipiv[i] = (float)(1.0 / piv[i]);
         t.tri_sup[i] = (float)sup[i];
     }
+
+    // ---- fused post+mel scan tables ----
+    // Segment j = [mel_f[j], mel_f[j+1]); a bin in segment j feeds band j-1 (falling edge, accumulator A)
+    // and band j (rising edge, accumulator B).  Lane chunk p scans bins 21p..21p+20 (p = 15: 315..319) and
+    // emits A whenever the segment index advances; the two accumulators left at the chunk end are flushed.
+    // Every band must end up with at most two partial sums ("locations") or the scan is not usable.
+    t.scan_ok = true;
+    t.scan_w.assign((size_t)SCAN_BINS * 2, 0.0f);
+    t.scan_loc.assign((size_t)NMEL * 4, 0);
+    std::vector<int> seg(NBINS, 0);
+    for (int k = 0; k < NBINS; ++k) {
+        const double fk = (double)sample_rate / 2.0 * k / (NBINS - 1);
+        int j = 0;
+        while (j < NMEL + 1 && mel_f[j + 1] <= fk) ++j;   // largest j with mel_f[j] <= fk (clamped to 80.. for fk >= fmax)
+        seg[k] = j;
+    }
+    for (int k = 0; k < NBINS - 1 && t.scan_ok; ++k) {
+        const int j = seg[k];
+        for (int m = 0; m < NMEL; ++m)
+            if (t.fb[(size_t)m * NBINS + k] != 0.0 && m != j - 1 && m != j) t.scan_ok = false;   // not a 2-tap triangular bank
+        const double wa = (j >= 1 && j - 1 < NMEL) ? t.fb[(size_t)(j - 1) * NBINS + k] : 0.0;
+        const double wb = (j < NMEL) ? t.fb[(size_t)j * NBINS + k] : 0.0;
+        t.scan_w[k * 2 + 0] = (float)(0.5 * wa);
+        t.scan_w[k * 2 + 1] = (float)(0.5 * wb);
+    }
+    std::vector<int> nloc(NMEL, 0);
+    auto add_loc = [&](int band, int off_sn, int off_m) {
+        if (band < 0 || band >= NMEL) return;
+        if (nloc[band] >= 2) { t.scan_ok = false; return; }
+        t.scan_loc[band * 4 + 2 * nloc[band] + 0] = off_sn;
+        t.scan_loc[band * 4 + 2 * nloc[band] + 1] = off_m;
+        ++nloc[band];
+    };
+    for (int p = 0; p < 16 && t.scan_ok; ++p) {
+        const int k0 = POST_CHUNK * p;
+        const int k1 = std::min(k0 + POST_CHUNK - 1, NBINS - 2);   // last bin of the chunk (<= 319)
+        for (int k = k0 + 1; k <= k1; ++k) {
+            if (seg[k] == seg[k - 1]) continue;
+            if (seg[k] != seg[k - 1] + 1) { t.scan_ok = false; break; }   // empty segment
+            // emission before bin k: A (band seg[k-1]-1) is written over bin k's own (already read) slots
+            t.scan_w[k * 2 + 0] = -t.scan_w[k * 2 + 0];
+            if (t.scan_w[k * 2 + 0] == 0.0f) t.scan_w[k * 2 + 0] = -0.0f;
+            add_loc(seg[k - 1] - 1, 2 * k, 2 * (NFFT - k));
+        }
+        // chunk-end flush: A -> band seg[k1]-1, B -> band seg[k1]
+        const int fl = FRAME_FLUSH_F + 6 * p;
+        add_loc(seg[k1] - 1, fl + 0, fl + 4);
+        add_loc(seg[k1], fl + 2, fl + 5);
+    }
+    for (int m = 0; m < NMEL && t.scan_ok; ++m) {
+        if (nloc[m] == 0) { t.scan_ok = false; break; }
+        for (int c = nloc[m]; c < 2; ++c) { t.scan_loc[m * 4 + 2 * c] = FRAME_ZERO_F; t.scan_loc[m * 4 + 2 * c + 1] = FRAME_ZERO_F + 2; }
+    }
     return true;
 }
 

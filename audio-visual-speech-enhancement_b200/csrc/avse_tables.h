@@ -22,6 +22,11 @@ struct HostTables {
     std::vector<float> mel_w;         // [80][MEL_WROW]  0.5 * weight (0.5 = packed-FFT unpack factor)
     std::vector<int> mel_roundw;      // [5]   max width over bands 16r..16r+15
 
+    // fused post+mel "scan" (see avse_fwd_stages.cuh stage_post_scan): valid when scan_ok
+    bool scan_ok = false;
+    std::vector<float> scan_w;        // [SCAN_BINS][2]  (wA | emit flag in the sign bit, wB), 0.5 * weights
+    std::vector<int> scan_loc;        // [80][4]  frame-relative float offsets (SN0, M0, SN1, M1) of each band's <= 2 partial sums
+
     // inverse path
     std::vector<float> tri_w;         // [80] Thomas forward multipliers (w[0] unused)
     std::vector<float> tri_ipiv;      // [80] 1 / pivot

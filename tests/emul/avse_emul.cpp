@@ -65,14 +65,13 @@ extern "C" int emul_fft640(const float* re, const float* im, float* out_re, floa
     return 0;
 }
 
-extern "C" int emul_forward(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
-                            int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
-                            float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
+// mode: 0 = what the library would pick (scan when the tables allow it), 1 = force the generic path
+extern "C" int emul_forward_mode(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
+                                 int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                                 float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax, int mode) {
     HostTables h;
     if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
-    const int std_w[MEL_ROUNDS] = AVSE_STD_ROUNDW;
-    bool is_std = true;
-    for (int r = 0; r < MEL_ROUNDS; ++r) is_std = is_std && (h.mel_roundw[r] == std_w[r]);
+    const bool scan = h.scan_ok && mode == 0;
     static EmulWarp w;
     memset(w.frames, 0, sizeof(w.frames));
     const int T = 1 + L / HOP, G = (T + FPG - 1) / FPG;
@@ -87,22 +86,36 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
     out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
     out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
     float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const vec2* s_scan = reinterpret_cast<const vec2*>(h.scan_w.data());
+    std::vector<ivec4> loc(NMEL);
+    for (int m = 0; m < NMEL; ++m) { loc[m].x = h.scan_loc[4 * m]; loc[m].y = h.scan_loc[4 * m + 1]; loc[m].z = h.scan_loc[4 * m + 2]; loc[m].w = h.scan_loc[4 * m + 3]; }
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * FPG;
         emul_fft_stages(w, h, tl);
-        for (int lane = 0; lane < 32; ++lane) stage_post<false>(lane, tl.factor, w.frames, nullptr);
-        for (int lane = 0; lane < 32; ++lane) {
-            if (is_std) stage_mel<true>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
-            else stage_mel<false>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
+        if (scan) {
+            for (int lane = 0; lane < 32; ++lane) stage_post_scan<false>(lane, tl.factor, s_scan, w.frames, nullptr);
+        } else {
+            for (int lane = 0; lane < 32; ++lane) stage_post<false>(lane, tl.factor, w.frames, nullptr);
+            for (int lane = 0; lane < 32; ++lane)
+                stage_mel<false>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
+            for (int lane = 0; lane < 32; ++lane) stage_mel_store(lane, w.acc[lane], w.frames);
         }
-        for (int lane = 0; lane < 32; ++lane) stage_mel_store(lane, w.acc[lane], w.frames);
         for (int q = 0; q < 3; ++q)
             for (int lane = 0; lane < 32; ++lane) {
                 float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
-                stage_db(lane, q, tl.factor, have_noise, w.frames, out, tl.t0, T, lm);
+                if (scan) stage_db_scan(lane, q, tl.factor, have_noise, loc.data(), w.frames, out, tl.t0, T, lm);
+                else stage_db(lane, q, tl.factor, have_noise, w.frames, out, tl.t0, T, lm);
                 for (int s = 0; s < 3; ++s) if (lm[s] > mx[s]) mx[s] = lm[s];
             }
     }
     for (int s = 0; s < 3; ++s) max3[s] = key_to_float(float_to_key(mx[s]));
-    return 0;
+    return scan ? 1 : 0;
+}
+
+extern "C" int emul_forward(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
+                            int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                            float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
+    const int rc = emul_forward_mode(speech, noise, L, valid_s, valid_n, factor, layout, n_slices, ld_t, out_sp, out_nz, out_mix,
+                                     mixed_pcm, max3, sample_rate, fmin, fmax, 0);
+    return rc < 0 ? rc : 0;
 }

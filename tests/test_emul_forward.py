@@ -122,3 +122,41 @@ def test_single_signal_spec_layout(emul):
     got = np.maximum(out[:, :T], mx[0] - 80.0)
     assert ref.shape == got.shape
     assert np.max(np.abs(got - ref)) <= TOL_DB
+
+
+def _run_mode(emul, s, nf, L, fac, ns, mode, fmin=0.0, fmax=8000.0):
+    emul.emul_forward_mode.argtypes = emul.emul_forward.argtypes + [ctypes.c_int]
+    outs = [np.zeros((ns, 80, 20), np.float32) for _ in range(3)]
+    pcm = np.zeros(L, np.float32)
+    mx = np.zeros(3, np.float32)
+    rc = emul.emul_forward_mode(_p(s), _p(nf), L, len(s), len(s), fac, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm), _p(mx),
+                                SR, fmin, fmax, mode)
+    assert rc >= 0
+    return rc, [np.maximum(o, m - 80.0) for o, m in zip(outs, mx)]
+
+
+def test_scan_and_generic_paths_agree_with_oracle(emul):
+    """The fused post+mel scan (default for the reference filterbank) and the generic banded gather must both
+    match the oracle; a non-reference filterbank (fmin 50, fmax 7000) exercises whichever path its tables allow."""
+    case = GOLDEN_CASES[0]
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    L = 3200 * case["nvs"]
+    fac = O.AudioMixer.snr_factor(O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(nf.astype(np.float64), SR), case["snr"])
+    ref = oracle_pair(case)
+    used_scan, got = _run_mode(emul, s, nf, L, fac, 5, 0)
+    assert used_scan == 1
+    used_scan, got_gen = _run_mode(emul, s, nf, L, fac, 5, 1)
+    assert used_scan == 0
+    for g in (got, got_gen):
+        for k, o in zip(("speech", "noise", "mixed"), g):
+            assert np.max(np.abs(o - ref[k])) <= TOL_DB, k
+    # other filterbank: oracle with the same fmin/fmax
+    fb = O.mel_filterbank(SR, 640, 80, 50.0, 7000.0)
+    mix = s.astype(np.float64) + fac * nf.astype(np.float64)
+    D = O.stft(mix[:L], 640, 160)
+    want = O.amplitude_to_db(fb @ np.abs(D))
+    for mode in (0, 1):
+        _, g = _run_mode(emul, s, nf, L, fac, 5, mode, 50.0, 7000.0)
+        got_full = np.concatenate(list(g[2]), axis=1)
+        assert np.max(np.abs(got_full - want[:, :100])) <= TOL_DB, mode
