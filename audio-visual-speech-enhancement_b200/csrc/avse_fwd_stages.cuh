@@ -27,6 +27,18 @@
 #include <cmath>
 #endif
 
+// Tuning switches (measured on B200, profiles/README.md): the rolled pass 1 with twiddles loaded ahead
+// of the DFT and the post scan unrolled by 7 gave the best kernel time (0.69 ms vs 0.78 ms per 1000 x 3 s).
+#if !defined(AVSE_PASS1_UNROLLED) && !defined(AVSE_PASS1_ROLLED)
+#define AVSE_PASS1_ROLLED 1
+#endif
+#if !defined(AVSE_NO_TW_PRELOAD) && !defined(AVSE_TW_PRELOAD)
+#define AVSE_TW_PRELOAD 1
+#endif
+#if !defined(AVSE_POST_UNROLL)
+#define AVSE_POST_UNROLL 7
+#endif
+
 namespace avse {
 
 struct alignas(8) vec2 { float x, y; };
@@ -109,6 +121,26 @@ AVSE_HD bool group_interior(const FwdTile& tl) {
 // ---------------------------------------------------------------------------------------
 // DFT-16 over n1, twiddle W_640^{n2 k1}, store column n2 of frame f as rows [k1][n2].
 AVSE_HD void pass1_column(float (&xr)[16], float (&xi)[16], int f, int n2, const vec2* s_tw, float* frames) {
+#if defined(AVSE_TW_PRELOAD)
+    // issue the 15 twiddle loads before the DFT so their latency hides behind its arithmetic
+    vec2 twv[16];
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) twv[k1] = s_tw[k1 * N2 + n2];
+    dft16(xr, xi);
+    float* rowp = frames + f * FRAME_F + 2 * n2;
+    {
+        vec2 v; v.x = xr[0]; v.y = xi[0];
+        *reinterpret_cast<vec2*>(rowp) = v;
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) {
+        vec2 v;
+        v.x = xr[k1] * twv[k1].x - xi[k1] * twv[k1].y;
+        v.y = xr[k1] * twv[k1].y + xi[k1] * twv[k1].x;
+        *reinterpret_cast<vec2*>(rowp + k1 * ROW_F) = v;
+    }
+    return;
+#endif
     dft16(xr, xi);
     float* row = frames + f * FRAME_F + 2 * n2;
     const vec2* tw = s_tw + n2;
@@ -467,7 +499,13 @@ AVSE_HD void stage_post_scan(int lane, float factor, const vec2* s_scan, float* 
         stft_row[NBINS - 1] = d;
     }
     float As = 0.0f, An = 0.0f, Am = 0.0f, Bs = 0.0f, Bn = 0.0f, Bm = 0.0f;
+#if defined(AVSE_POST_UNROLL)
+#define AVSE_STR_(x) #x
+#define AVSE_UNROLL_N_(n) _Pragma(AVSE_STR_(unroll n))
+    AVSE_UNROLL_N_(AVSE_POST_UNROLL)
+#else
 #pragma unroll
+#endif
     for (int i = 0; i < POST_CHUNK; ++i) {
         if (i >= LAST_N && last) continue;
         const vec2 a = *reinterpret_cast<const vec2*>(za + 2 * i);
