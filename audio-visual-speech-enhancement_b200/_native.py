@@ -29,17 +29,20 @@ class ForwardArgs(_c.Structure):
 
 class InverseArgs(_c.Structure):
     _fields_ = [
-        ("mel_db", _c.c_void_p), ("layout", _c.c_int), ("n_slices", _c.c_int), ("ld_t", _c.c_int),
+        ("mel_db", _c.c_void_p), ("layout", _c.c_int), ("n_slices", _c.c_int), ("n_frames", _c.c_int), ("ld_t", _c.c_int),
         ("mel_stride", _c.c_longlong),
         ("mixed_pcm", _c.c_void_p), ("pcm_stride", _c.c_longlong), ("len_pcm", _c.c_void_p),
         ("B", _c.c_int), ("L", _c.c_int),
         ("out_pcm", _c.c_void_p), ("out_stride", _c.c_longlong),
+        ("work", _c.c_void_p), ("work_stride", _c.c_longlong),
+        ("phase", _c.c_void_p), ("phase_stride", _c.c_longlong), ("phase_frames", _c.c_int),
     ]
 
 
 EXPORTS = [
     "avse_create", "avse_destroy", "avse_last_error", "avse_version", "avse_get_filterbank",
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
+    "avse_inverse", "avse_inverse_work_elems",
 ]
 
 
@@ -77,9 +80,10 @@ def load(build=True):
     lib.avse_reset_max.restype = i32
     lib.avse_max_db.argtypes = [vp, vp, i32, vp, vp]
     lib.avse_max_db.restype = i32
-    if hasattr(lib, "avse_inverse"):
-        lib.avse_inverse.argtypes = [vp, _c.POINTER(InverseArgs), vp]
-        lib.avse_inverse.restype = i32
+    lib.avse_inverse.argtypes = [vp, _c.POINTER(InverseArgs), vp]
+    lib.avse_inverse.restype = i32
+    lib.avse_inverse_work_elems.argtypes = [i32, _c.POINTER(ll)]
+    lib.avse_inverse_work_elems.restype = i32
     _lib = lib
     return lib
 

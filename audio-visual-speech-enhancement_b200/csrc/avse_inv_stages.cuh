@@ -1,0 +1,340 @@
+// Warp-stage functions of the inverse kernel: dB log-mel + mixture PCM -> enhanced PCM
+// (reconstruct_speech_signal, /root/reference/data_processor.py:60-74 and :99-116).
+//
+// Per frame the reference computes  lin = pinv(F) 10^(dB/20),  Y = lin * phase(STFT(mixture)),
+// y = istft(Y)  (irfft, Hann, overlap-add, / window sum-square, centre trim).  Here:
+//   * pinv(F) = F^T (F F^T)^-1 with F F^T tridiagonal: a Thomas solve per frame (separate tiny kernel,
+//     avse_mel_to_coef_kernel) gives c = (F F^T)^-1 a; lin[k] = sum of <= 2 taps of F^T c.
+//   * Two real frames ride one complex 640-point FFT in both directions: the mixture frames (t, t+1)
+//     are packed as re/im for the phase, and V = conj(Y_t + i Y_{t+1}) (Hermitian-extended) is sent
+//     through the same forward-FFT codelets, giving 640 (y_t - i y_{t+1}).
+//   * One warp streams through consecutive groups of 4 frames of one utterance chunk and keeps the
+//     overlap-add in registers: lane l owns output samples == l (mod 40) (the 8 residues 32..39 live
+//     in a small shared side buffer), so no atomics and no inter-warp exchange are needed.
+//
+// Stage order per group (warp-synchronous, private shared memory):
+//   pass 1 (mixture -> rows) | pass 2 (-> Z) | post (phase * lin -> V, in place) |
+//   pass A (DFT-40 over n2', twiddle -> rows) | pass B (DFT-16 over n1', window, overlap-add) | emit 4 hops
+#pragma once
+#include "avse_common.h"
+#include "avse_dft.cuh"
+#include "avse_fwd_stages.cuh"
+
+namespace avse {
+
+constexpr int INV_FPG = 4;                 // real frames per group (2 packed complex FFTs)
+constexpr int INV_Y_F = NMEL * INV_FPG;    // coefficient buffer [80][4]
+constexpr int INV_SIDE_ROWS = 28;          // overlap-add rows (40 samples each) alive per group
+constexpr int INV_SIDE_F = INV_SIDE_ROWS * 8;
+constexpr int INV_WARP_SMEM_F = 2 * FRAME_F + INV_Y_F + INV_SIDE_F;   // 2912 + 320 + 224 = 3456 floats
+constexpr float INV_SCALE = 1.0f / NFFT;   // irfft normalisation
+
+struct InvTile {
+    const float* pcm;   // mixture samples of this utterance
+    int L;              // signal length (reflect domain of librosa.stft)
+    int valid;          // samples present (zeros beyond)
+    int T;              // STFT frames of the mixture: 1 + L / hop
+    int T_use;          // frames reconstructed: min(20 * n_slices, T)  (dp:68)
+    int t0;             // first frame of the group (multiple of 4)
+};
+
+AVSE_HD bool inv_group_interior(const InvTile& tl) {
+    return tl.t0 * HOP - HALF >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.valid && tl.t0 + 3 < tl.T;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 1: complex FFT f packs mixture frames tA = t0 + 2f (real part) and tA + 1 (imaginary part);
+// the second is the first shifted by 4 strides of 40 samples, so one batch of 20 loads serves both.
+// ---------------------------------------------------------------------------------------
+// An all-zero windowed frame (zero padding dp:40, digital silence) has D == 0 exactly in the reference and
+// therefore phase 1 + 0j (librosa.magphase).  Packed with a non-zero partner frame its unpacked spectrum
+// would be rounding noise with a random phase, so pass 1 records per packed frame whether any windowed
+// sample is non-zero (all writers store the same value: no race) and the post stage forces 1 + 0j otherwise.
+// Flags live in the frame region's otherwise unused floats [FRAME_ZERO_F, FRAME_ZERO_F + 2).
+AVSE_HD void inv_mark_nonzero(const float (&xr)[16], const float (&xi)[16], float* frame_base) {
+    bool nr = false, ni = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { nr = nr || (xr[j] != 0.0f); ni = ni || (xi[j] != 0.0f); }
+    if (nr) frame_base[FRAME_ZERO_F] = 1.0f;
+    if (ni) frame_base[FRAME_ZERO_F + 1] = 1.0f;
+}
+
+AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    const bool interior = inv_group_interior(tl);
+#pragma unroll 1
+    for (int round = 0; round < 3; ++round) {
+        if (round == 2 && lane >= 16) break;
+        const int f = round < 2 ? round : (lane >> 3) & 1;
+        const int n2 = round < 2 ? lane : 32 + (lane & 7);
+        const int tA = tl.t0 + 2 * f;
+        float raw[20];
+        if (interior) {
+            const float* p = tl.pcm + tA * HOP - HALF + n2;
+#pragma unroll
+            for (int j = 0; j < 20; ++j) raw[j] = p[N2 * j];
+        } else {
+            // frames beyond the last one are clamped (their coefficients are zero, so they contribute nothing)
+            const int ta = tA < tl.T ? tA : tl.T - 1;
+            const int tb = tA + 1 < tl.T ? tA + 1 : tl.T - 1;
+            const int ba = ta * HOP - HALF + n2, bb = tb * HOP - HALF + n2;
+            // reflection breaks the shift relation: load both frames explicitly
+            float xa[16], xb[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                xa[j] = load_sample_edge(tl.pcm, ba + N2 * j, tl.L, tl.valid);
+                xb[j] = load_sample_edge(tl.pcm, bb + N2 * j, tl.L, tl.valid);
+            }
+            float xr[16], xi[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] = xa[j] * w; xi[j] = xb[j] * w; }
+            inv_mark_nonzero(xr, xi, frames + f * FRAME_F);
+            pass1_column(xr, xi, f, n2, s_tw, frames);
+            continue;
+        }
+        float xr[16], xi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] = raw[j] * w; xi[j] = raw[j + 4] * w; }
+        inv_mark_nonzero(xr, xi, frames + f * FRAME_F);
+        pass1_column(xr, xi, f, n2, s_tw, frames);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// post: lane = (chunk p = lane/2, complex FFT f = lane%2).  For each bin k of the chunk:
+//   X_A = (Z_k + conj Z_{N-k})/2, X_B = (Z_k - conj Z_{N-k})/(2i)        (frames tA, tA+1)
+//   phase = X/|X| (1 + 0j where X == 0, librosa.magphase dp:80)
+//   lin_t[k] = w0 c_t[b0] + w1 c_t[b1]                                    (F^T c, dp:112)
+//   Y = lin * phase;  V_k = conj(Y_A + i Y_B), V_{N-k} = conj(conj(Y_A) + i conj(Y_B))   (in place)
+// s_col: [SCAN_BINS] (b0, b1, w0, w1) as ivec4 bit patterns; ybuf: [80][4] coefficients of the group.
+// ---------------------------------------------------------------------------------------
+AVSE_HD float inv_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+AVSE_HD float bits_to_float(int b) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(b);
+#else
+    union { float f; int i; } u; u.i = b; return u.f;
+#endif
+}
+
+// EXT: the phase is read from a caller-supplied array (reconstruct_signal_from_spectrogram, dp:99) instead of
+// the recomputed mixture STFT; phA / phB point at the [321] complex rows of frames tA and tA + 1 (or nullptr).
+template <bool EXT>
+AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, float* frames, const vec2* phA, const vec2* phB) {
+    const int f = lane & 1, p = lane >> 1;
+    float* fr = frames + f * FRAME_F;
+    float* za = fr + 2 * POST_CHUNK * p;
+    float* zc = fr + 2 * (NFFT - POST_CHUNK * p);
+    const ivec4* tab = s_col + POST_CHUNK * p;
+    const float* yb = ybuf + 2 * f;     // (c_tA, c_tA+1) of band b at yb[4 b .. 4 b + 1]
+    const bool last = p == 15;
+    const bool liveA = EXT || fr[FRAME_ZERO_F] != 0.0f;       // see inv_mark_nonzero
+    const bool liveB = EXT || fr[FRAME_ZERO_F + 1] != 0.0f;
+    constexpr int LAST_N = (NBINS - 1) - 15 * POST_CHUNK;
+#pragma unroll 3
+    for (int i = 0; i < POST_CHUNK; ++i) {
+        if (i >= LAST_N && last) {
+            if (i == LAST_N) { vec2 z; z.x = 0.0f; z.y = 0.0f; *reinterpret_cast<vec2*>(za + 2 * i) = z; }   // Nyquist bin: lin = 0
+            continue;
+        }
+        vec2 a, c;
+        if (!EXT) {
+            a = *reinterpret_cast<const vec2*>(za + 2 * i);
+            c = *reinterpret_cast<const vec2*>(zc - 2 * i);
+        }
+        const ivec4 t = tab[i];
+        const vec2 y0 = *reinterpret_cast<const vec2*>(yb + 4 * t.x);
+        const vec2 y1 = *reinterpret_cast<const vec2*>(yb + 4 * t.y);
+        const float w0 = bits_to_float(t.z), w1 = bits_to_float(t.w);
+        const float linA = w0 * y0.x + w1 * y1.x;
+        const float linB = w0 * y0.y + w1 * y1.y;
+        float par, pai, pbr, pbi;
+        if (EXT) {
+            const int k = POST_CHUNK * p + i;
+            const vec2 qa = phA != nullptr ? phA[k] : vec2{1.0f, 0.0f};
+            const vec2 qb = phB != nullptr ? phB[k] : vec2{1.0f, 0.0f};
+            par = qa.x; pai = qa.y; pbr = qb.x; pbi = qb.y;
+        } else {
+            const float ar = a.x + c.x, ai = a.y - c.y;     // 2 X_A
+            const float br = a.y + c.y, bi = c.x - a.x;     // 2 X_B
+            const float na = ar * ar + ai * ai, nb = br * br + bi * bi;
+            const float ia = inv_rsqrt(na), ib = inv_rsqrt(nb);
+            const bool okA = na > 0.0f && liveA, okB = nb > 0.0f && liveB;
+            par = okA ? ar * ia : 1.0f; pai = okA ? ai * ia : 0.0f;
+            pbr = okB ? br * ib : 1.0f; pbi = okB ? bi * ib : 0.0f;
+        }
+        const float yar = linA * par, yai = linA * pai;
+        const float ybr = linB * pbr, ybi = linB * pbi;
+        vec2 v1, v2;
+        v1.x = yar - ybi; v1.y = -(yai + ybr);          // conj(Y_A + i Y_B)
+        v2.x = yar + ybi; v2.y = yai - ybr;             // conj(conj(Y_A) + i conj(Y_B))
+        *reinterpret_cast<vec2*>(za + 2 * i) = v1;
+        *reinterpret_cast<vec2*>(zc - 2 * i) = v2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass A: lane = (f = lane/16, n1' = lane%16): gather V[n1' + 16 n2'], DFT-40 over n2', multiply by
+// W_640^{n1' k2'}; after a warp sync the 40 results are written as row n1' = [k2'].
+// s_twT: [40][16] vec2, W_640^{n1' k2'} with n1' minor (conflict-free for lane = n1').
+// ---------------------------------------------------------------------------------------
+AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames, float (&xr)[40], float (&xi)[40]) {
+    const int f = lane >> 4, n1 = lane & 15;
+    const float* z = frames + f * FRAME_F + 2 * n1;
+#pragma unroll
+    for (int n2 = 0; n2 < 40; ++n2) {
+        const vec2 v = *reinterpret_cast<const vec2*>(z + 2 * N1 * n2);
+        xr[n2] = v.x; xi[n2] = v.y;
+    }
+    dft40_inplace(xr, xi);
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int idx = (8 * c + 5 * d) % 40, k2 = (16 * c + 25 * d) % 40;
+            if (k2 == 0) continue;
+            const vec2 t = s_twT[k2 * N1 + n1];
+            const float r = xr[idx] * t.x - xi[idx] * t.y;
+            const float im = xr[idx] * t.y + xi[idx] * t.x;
+            xr[idx] = r; xi[idx] = im;
+        }
+}
+
+AVSE_HD void inv_passA_store(int lane, float* frames, const float (&xr)[40], const float (&xi)[40]) {
+    const int f = lane >> 4, n1 = lane & 15;
+    float* row = frames + f * FRAME_F + n1 * ROW_F;
+    if (n1 == 0) { frames[f * FRAME_F + FRAME_ZERO_F] = 0.0f; frames[f * FRAME_F + FRAME_ZERO_F + 1] = 0.0f; }   // re-arm inv_mark_nonzero
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int idx = (8 * c + 5 * d) % 40, k2 = (16 * c + 25 * d) % 40;
+            vec2 v; v.x = xr[idx]; v.y = xi[idx];
+            *reinterpret_cast<vec2*>(row + 2 * k2) = v;
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass B: column k2' of complex FFT f: DFT-16 over n1' gives 640 (y_A - i y_B) at n = 40 k1' + k2'.
+// Window (x 1/640) and overlap-add.  Rounds 0/1 (k2' = lane): acc[J], J = j + 8 f, row J = samples
+// 160 t0 + 40 J + lane.  Round 2 (k2' = 32 + lane%8, f = lane/8, lanes 0..15): shared side buffer
+// side[J][r], two ordered phases (f = 0 then f = 1) so the adds never race.
+// ---------------------------------------------------------------------------------------
+AVSE_HD void inv_passB_column(int f, int k2, const float* s_win, const float* frames, float (&c)[20]) {
+    const float* col = frames + f * FRAME_F + 2 * k2;
+    float xr[16], xi[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const vec2 v = *reinterpret_cast<const vec2*>(col + n1 * ROW_F);
+        xr[n1] = v.x; xi[n1] = v.y;
+    }
+    dft16(xr, xi);
+#pragma unroll
+    for (int j = 0; j < 20; ++j) c[j] = 0.0f;
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const float w = s_win[N2 * k1 + k2] * INV_SCALE;
+        c[k1] += xr[k1] * w;           // frame tA sample 40 k1 + k2
+        c[k1 + 4] -= xi[k1] * w;       // frame tA + 1, one hop (4 rows) later
+    }
+}
+
+AVSE_HD void inv_stage_passB_main(int lane, const float* s_win, const float* frames, float (&acc)[INV_SIDE_ROWS]) {
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        float c[20];
+        inv_passB_column(f, lane, s_win, frames, c);
+#pragma unroll
+        for (int j = 0; j < 20; ++j) acc[j + 8 * f] += c[j];
+    }
+}
+
+// side-buffer phase ph (0 or 1): lanes with f == ph add their column into side[J][r]
+AVSE_HD void inv_stage_passB_side(int lane, int ph, const float* s_win, const float* frames, float* side) {
+    if (lane >= 16) return;
+    const int f = lane >> 3, r = lane & 7;
+    if (f != ph) return;
+    float c[20];
+    inv_passB_column(f, 32 + r, s_win, frames, c);
+#pragma unroll
+    for (int j = 0; j < 20; ++j) side[(j + 8 * f) * 8 + r] += c[j];
+}
+
+// librosa.istft window sum-square at padded position P for T_use frames (Appendix A.1): sum over the
+// (<= 4) frames t = P/160 - q that exist.  Interior value is exactly 1.5 for the periodic Hann at hop N/4.
+AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win) {
+    const int h = P / HOP, r = P - h * HOP;
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int t = h - q;
+        const float w = s_win[r + HOP * q];
+        if (t >= 0 && t < T_use) s += w * w;
+    }
+    return s > 1.17549435e-38f ? 1.0f / s : 1.0f;   // "> tiny(float32)" guard of librosa.istft
+}
+
+// Emit the 4 finished hops of the group (rows J = 0..15) and rotate the overlap-add state.
+// out: trimmed PCM of this utterance (index o = P - 320), out_len = 160 (T_use - 1).
+AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win, float* out,
+                                 float (&acc)[INV_SIDE_ROWS]) {
+    if (write) {
+        const bool interior = t0 >= 3 && t0 + 3 < T_use;   // every row has its 4 frames
+#pragma unroll
+        for (int J = 0; J < 16; ++J) {
+            const int P = t0 * HOP + N2 * J + lane;
+            const int o = P - HALF;
+            if (o >= 0 && o < out_len) {
+                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win);
+                out[o] = acc[J] * rw;
+            }
+        }
+    }
+#pragma unroll
+    for (int J = 0; J < 12; ++J) acc[J] = acc[J + 16];
+#pragma unroll
+    for (int J = 12; J < INV_SIDE_ROWS; ++J) acc[J] = 0.0f;
+}
+
+// side buffer: lane = (row J = lane/2, half = lane%2): 4 samples each, then rotate rows.
+AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool write, const float* s_win, float* out,
+                                 const float* side, float (&keep)[4], float (&carry)[4]) {
+    // reads only: caller performs the rotation after a warp sync (see inv_stage_rotate_side)
+    const int J = lane >> 1, hf = lane & 1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        keep[e] = side[J * 8 + 4 * hf + e];
+        carry[e] = (J + 16 < INV_SIDE_ROWS) ? side[(J + 16) * 8 + 4 * hf + e] : 0.0f;
+    }
+    if (write) {
+        const bool interior = t0 >= 3 && t0 + 3 < T_use;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int P = t0 * HOP + N2 * J + 32 + 4 * hf + e;
+            const int o = P - HALF;
+            if (o >= 0 && o < out_len) {
+                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win);
+                out[o] = keep[e] * rw;
+            }
+        }
+    }
+}
+
+AVSE_HD void inv_stage_rotate_side(int lane, float* side, const float (&carry)[4]) {
+    const int J = lane >> 1, hf = lane & 1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        side[J * 8 + 4 * hf + e] = carry[e];                 // rows 0..15 <- rows 16..31 (rows >= 28 are zero)
+        if (J + 16 < INV_SIDE_ROWS) side[(J + 16) * 8 + 4 * hf + e] = 0.0f;
+    }
+}
+
+}  // namespace avse

@@ -1,0 +1,258 @@
+// Inverse path (predict time): dB log-mel + mixture PCM -> PCM.  See include/avse_b200.h, avse_inv_stages.cuh.
+#include <cuda_runtime.h>
+#include <string>
+
+#include "../../include/avse_b200.h"
+#include "avse_common.h"
+#include "avse_ctx.h"
+#include "avse_inv_stages.cuh"
+
+using namespace avse;
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1: c = (F F^T)^-1 10^(dB/20) per frame (Thomas, one thread per frame), coefficient layout
+// work[u][band][t_pad] (time minor, zero for t >= T_use so that padded groups contribute nothing).
+// Replaces np.linalg.pinv + np.dot of dp:112 together with db_to_amplitude (dp:101).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) avse_mel_to_coef_kernel(const float* __restrict__ mel_db, int layout, int ld_t,
+                                                               long long mel_stride, int T_use, int T_pad,
+                                                               const float* __restrict__ tri_w, const float* __restrict__ tri_ipiv,
+                                                               const float* __restrict__ tri_sup, float* __restrict__ work,
+                                                               long long work_stride) {
+    const int u = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T_pad) return;
+    float* dst = work + (size_t)u * work_stride + t;
+    if (t >= T_use) {
+#pragma unroll 8
+        for (int m = 0; m < NMEL; ++m) dst[(size_t)m * T_pad] = 0.0f;
+        return;
+    }
+    const float* src = mel_db + (size_t)u * mel_stride;
+    size_t base, mstride;
+    if (layout == AVSE_LAYOUT_SLICES) {
+        const int s = t / SPSS, tt = t - s * SPSS;
+        base = (size_t)s * NMEL * SPSS + tt;
+        mstride = SPSS;
+    } else {
+        base = t;
+        mstride = ld_t;
+    }
+    constexpr float K = 0.16609640474436813f;   // log2(10) / 20 :  10^(dB/20) = 2^(K dB)   (librosa.db_to_amplitude)
+    float d[NMEL];
+#pragma unroll
+    for (int m = 0; m < NMEL; ++m) d[m] = exp2f(K * src[base + (size_t)m * mstride]);
+#pragma unroll
+    for (int m = 1; m < NMEL; ++m) d[m] -= __ldg(tri_w + m) * d[m - 1];
+    d[NMEL - 1] *= __ldg(tri_ipiv + NMEL - 1);
+#pragma unroll
+    for (int m = NMEL - 2; m >= 0; --m) d[m] = (d[m] - __ldg(tri_sup + m) * d[m + 1]) * __ldg(tri_ipiv + m);
+#pragma unroll
+    for (int m = 0; m < NMEL; ++m) dst[(size_t)m * T_pad] = d[m];
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2: phase of the mixture, lin * phase, packed inverse FFT, overlap-add in registers
+// ---------------------------------------------------------------------------------------------
+constexpr int INV_WARPS = 6;
+constexpr int INV_THREADS = INV_WARPS * 32;
+constexpr int INV_SM_WIN = INV_WARPS * INV_WARP_SMEM_F;      // [640]
+constexpr int INV_SM_TW = INV_SM_WIN + NFFT;                 // [16][40] vec2   W^{n2 k1}, n2 minor
+constexpr int INV_SM_TWT = INV_SM_TW + N1 * N2 * 2;          // [40][16] vec2   W^{n1' k2'}, n1' minor
+constexpr int INV_SM_COL = INV_SM_TWT + N1 * N2 * 2;         // [SCAN_BINS] ivec4
+constexpr int INV_SMEM_F = INV_SM_COL + SCAN_BINS * 4;
+constexpr int INV_SMEM_BYTES = INV_SMEM_F * 4;
+static_assert((INV_SM_COL % 4) == 0 && (INV_SM_TW % 2) == 0, "table alignment");
+static_assert(2 * (INV_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
+
+struct InvParams {
+    avse_inverse_args a;
+    const float* window;
+    const float* tw1t;
+    const int* col_band;
+    const float* col_w;
+    int T;            // mixture STFT frames
+    int T_use;        // frames reconstructed
+    int T_pad;        // coefficient row length (multiple of 4, >= 4 (G + 1))
+    int G;            // groups of 4 frames
+    int chunks;       // chunks per utterance
+    int cg;           // groups per chunk
+    int out_len;      // 160 (T_use - 1)
+};
+
+__global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __grid_constant__ InvParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NFFT; i += INV_THREADS) smem[INV_SM_WIN + i] = P.window[i];
+    for (int i = threadIdx.x; i < N1 * N2; i += INV_THREADS) {
+        const int k1 = i / N2, n2 = i - k1 * N2;
+        const float re = P.tw1t[2 * i], im = P.tw1t[2 * i + 1];
+        smem[INV_SM_TW + 2 * i] = re; smem[INV_SM_TW + 2 * i + 1] = im;
+        smem[INV_SM_TWT + 2 * (n2 * N1 + k1)] = re; smem[INV_SM_TWT + 2 * (n2 * N1 + k1) + 1] = im;   // symmetric in (n2, k1)
+    }
+    for (int i = threadIdx.x; i < SCAN_BINS; i += INV_THREADS) {
+        int* e = reinterpret_cast<int*>(smem + INV_SM_COL) + 4 * i;
+        if (i < NBINS) {
+            e[0] = P.col_band[2 * i]; e[1] = P.col_band[2 * i + 1];
+            e[2] = __float_as_int(P.col_w[2 * i]); e[3] = __float_as_int(P.col_w[2 * i + 1]);
+        } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
+    }
+    float* frames = smem + warp * INV_WARP_SMEM_F;
+    float* ybuf = frames + 2 * FRAME_F;
+    float* side = ybuf + INV_Y_F;
+    for (int i = lane; i < INV_WARP_SMEM_F; i += 32) frames[i] = 0.0f;
+    __syncthreads();
+
+    const float* s_win = smem + INV_SM_WIN;
+    const vec2* s_tw = reinterpret_cast<const vec2*>(smem + INV_SM_TW);
+    const vec2* s_twT = reinterpret_cast<const vec2*>(smem + INV_SM_TWT);
+    const ivec4* s_col = reinterpret_cast<const ivec4*>(smem + INV_SM_COL);
+    const avse_inverse_args& A = P.a;
+
+    const int n_items = A.B * P.chunks;
+    const int n_warps = gridDim.x * INV_WARPS;
+#pragma unroll 1
+    for (int item = blockIdx.x * INV_WARPS + warp; item < n_items; item += n_warps) {
+        const int u = item / P.chunks;
+        const int c = item - u * P.chunks;
+        const int g0 = c * P.cg;
+        if (g0 >= P.G && !(c == 0)) continue;
+        int g1 = g0 + P.cg;
+        const bool last_chunk = g1 >= P.G;
+        if (last_chunk) g1 = P.G;
+        const int g_first = g0 > 0 ? g0 - 1 : 0;          // warm-up group rebuilds the overlap-add carry
+        const int g_last = last_chunk ? P.G : g1 - 1;     // the last chunk also drains the carry (group G)
+
+        InvTile tl;
+        tl.pcm = A.mixed_pcm + (size_t)u * A.pcm_stride;
+        tl.L = A.L;
+        int valid = A.len_pcm ? A.len_pcm[u] : A.L;
+        tl.valid = valid < A.L ? valid : A.L;
+        tl.T = P.T;
+        tl.T_use = P.T_use;
+        const float* ycoef = A.work + (size_t)u * A.work_stride;
+        float* out = A.out_pcm + (size_t)u * A.out_stride;
+
+        float acc[INV_SIDE_ROWS];
+#pragma unroll
+        for (int J = 0; J < INV_SIDE_ROWS; ++J) acc[J] = 0.0f;
+        for (int i = lane; i < INV_SIDE_F; i += 32) side[i] = 0.0f;
+        __syncwarp();
+
+#pragma unroll 1
+        for (int g = g_first; g <= g_last; ++g) {
+            tl.t0 = g * INV_FPG;
+            if (tl.t0 < P.T_use) {
+                // coefficients of the 4 frames -> ybuf[band][4]
+                for (int m = lane; m < NMEL; m += 32)
+                    *reinterpret_cast<float4*>(ybuf + 4 * m) = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0);
+                if (A.phase == nullptr) {
+                    inv_stage_pass1(tl, lane, s_win, s_tw, frames);
+                    __syncwarp();
+                    {
+                        float xr[40], xi[40];
+                        pass2_compute(lane, frames, xr, xi);
+                        __syncwarp();
+                        pass2_store(lane, frames, xr, xi);
+                    }
+                    __syncwarp();
+                    inv_stage_post<false>(lane, s_col, ybuf, frames, nullptr, nullptr);
+                } else {
+                    __syncwarp();
+                    const int tA = tl.t0 + 2 * (lane & 1);
+                    const vec2* ph = reinterpret_cast<const vec2*>(A.phase) + (size_t)u * A.phase_stride;
+                    const vec2* phA = tA < P.T_use ? ph + (size_t)tA * NBINS : nullptr;
+                    const vec2* phB = tA + 1 < P.T_use ? ph + (size_t)(tA + 1) * NBINS : nullptr;
+                    inv_stage_post<true>(lane, s_col, ybuf, frames, phA, phB);
+                }
+                __syncwarp();
+                {
+                    float xr[40], xi[40];
+                    inv_passA_compute(lane, s_twT, frames, xr, xi);
+                    __syncwarp();
+                    inv_passA_store(lane, frames, xr, xi);
+                }
+                __syncwarp();
+                inv_stage_passB_main(lane, s_win, frames, acc);
+                inv_stage_passB_side(lane, 0, s_win, frames, side);
+                __syncwarp();
+                inv_stage_passB_side(lane, 1, s_win, frames, side);
+                __syncwarp();
+            }
+            const bool write = g >= g0;
+            inv_stage_emit_main(lane, tl.t0, P.T_use, P.out_len, write, s_win, out, acc);
+            {
+                float keep[4], carry[4];
+                inv_stage_emit_side(lane, tl.t0, P.T_use, P.out_len, write, s_win, out, side, keep, carry);
+                inv_stage_rotate_side(lane, side, carry);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+extern "C" int avse_inverse_work_elems(int n_frames_use, long long* per_utterance) {
+    if (n_frames_use <= 0 || per_utterance == nullptr) return avse_fail(AVSE_E_ARG, "avse_inverse_work_elems: bad argument");
+    const int G = (n_frames_use + INV_FPG - 1) / INV_FPG;
+    *per_utterance = (long long)NMEL * (INV_FPG * (G + 1));
+    return 0;
+}
+
+extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream) {
+    if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL argument");
+    const avse_inverse_args& a = *args;
+    if (!a.mel_db || (!a.mixed_pcm && !a.phase) || !a.out_pcm || !a.work) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
+    if (a.B <= 0 || (!a.phase && a.L <= HALF)) return avse_fail(AVSE_E_ARG, "avse_inverse: need B > 0 and L > 320");
+    if (a.layout != AVSE_LAYOUT_SLICES && a.layout != AVSE_LAYOUT_SPEC) return avse_fail(AVSE_E_ARG, "avse_inverse: bad layout");
+    InvParams P;
+    P.a = a;
+    P.T = a.phase ? a.phase_frames : 1 + a.L / HOP;
+    const int t_mel = a.layout == AVSE_LAYOUT_SLICES ? a.n_slices * AVSE_SPSS : a.n_frames;
+    if (t_mel <= 0) return avse_fail(AVSE_E_ARG, "avse_inverse: no mel frames");
+    P.T_use = t_mel < P.T ? t_mel : P.T;                       // dp:68
+    if (P.T_use < 2) return avse_fail(AVSE_E_ARG, "avse_inverse: fewer than 2 frames gives an empty signal");
+    P.G = (P.T_use + INV_FPG - 1) / INV_FPG;
+    P.T_pad = INV_FPG * (P.G + 1);
+    P.out_len = HOP * (P.T_use - 1);
+    if (a.layout == AVSE_LAYOUT_SPEC && a.ld_t < P.T_use) return avse_fail(AVSE_E_ARG, "avse_inverse: ld_t < frames used");
+    if (a.work_stride < (long long)NMEL * P.T_pad) return avse_fail(AVSE_E_ARG, "avse_inverse: work_stride too small (see avse_inverse_work_elems)");
+    if (((size_t)a.work & 15) || (a.work_stride & 3)) return avse_fail(AVSE_E_ARG, "avse_inverse: work must be 16-byte aligned with work_stride % 4 == 0");
+    if (a.out_stride < P.out_len) return avse_fail(AVSE_E_ARG, "avse_inverse: out_stride < 160 (T_use - 1)");
+    if (a.phase && a.phase_stride < (long long)P.T_use * NBINS) return avse_fail(AVSE_E_ARG, "avse_inverse: phase_stride too small");
+    if (!a.phase && !a.len_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_inverse: pcm_stride < L needs len_pcm");
+    P.window = ctx->fwd.window;
+    P.tw1t = ctx->fwd.tw1t;
+    P.col_band = ctx->d_col_band;
+    P.col_w = ctx->d_col_w;
+
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_inverse: current device differs from the context's device");
+    static thread_local int configured_dev = -1;
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        configured_dev = dev;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        dim3 grid((unsigned)((P.T_pad + 127) / 128), (unsigned)a.B);
+        avse_mel_to_coef_kernel<<<grid, 128, 0, st>>>(a.mel_db, a.layout, a.ld_t, a.mel_stride, P.T_use, P.T_pad, ctx->d_tri_w,
+                                                      ctx->d_tri_ipiv, ctx->d_tri_sup, a.work, a.work_stride);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // chunking: enough (utterance, chunk) items to keep every resident warp busy for ~3 rounds, but chunks of
+    // >= 8 groups so that the one warm-up group per chunk stays a small overhead
+    const long long n_warps = 2LL * ctx->num_sms * INV_WARPS;
+    long long chunks = (3 * n_warps + a.B - 1) / a.B;
+    const long long max_chunks = P.G / 8 > 0 ? P.G / 8 : 1;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    P.cg = (int)((P.G + chunks - 1) / chunks);
+    P.chunks = (P.G + P.cg - 1) / P.cg;
+    long long blocks = 2LL * ctx->num_sms;
+    const long long need = ((long long)a.B * P.chunks + INV_WARPS - 1) / INV_WARPS;
+    if (blocks > need) blocks = need;
+    avse_inverse_kernel<<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -226,10 +226,8 @@ class SpectralEngine(object):
         res = self.forward_raw(signals, None, L=L, len_speech=lengths, layout=LAYOUT_SLICES, n_slices=n, want=("speech",), mixed_pcm=False)
         return self.floor_(res["speech"], res["max_key"], 0)
 
-    def reconstruct(self, mixed_pcm, mel_slices, lengths=None):
+    def reconstruct(self, mixed_pcm, mel_slices, lengths=None, out=None, work=None):
         """Batched reconstruct_speech_signal (dp:60-74): mixture PCM [B, L] + dB slices [B, n, 80, 20] -> PCM [B, 160*(min(20n, T)-1)]."""
-        if not hasattr(self._lib, "avse_inverse"):
-            raise RuntimeError("libavse_b200.so was built without avse_inverse")
         mixed_pcm = self._as_batch(mixed_pcm)
         mel = mel_slices if mel_slices.dtype == torch.float32 else mel_slices.to(torch.float32)
         if mel.dim() == 3:
@@ -239,13 +237,65 @@ class SpectralEngine(object):
         n = mel.shape[1]
         T_use = min(SPSS * n, self.n_frames(L))
         out_len = HOP * (T_use - 1)
-        out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
+        per = ctypes.c_longlong(0)
+        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        if work is None or work.numel() < B * per.value:
+            work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
-        a.mel_db, a.layout, a.n_slices, a.ld_t = _ptr(mel), LAYOUT_SLICES, n, 0
+        a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SLICES, n, 0, 0
         a.mel_stride = _rs(mel)
         a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), _rs(mixed_pcm), _ptr(lengths)
         a.B, a.L = B, L
         a.out_pcm, a.out_stride = _ptr(out), _rs(out)
+        a.work, a.work_stride = _ptr(work), per.value
+        check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
+        return out
+
+    def reconstruct_with_phase(self, mel_db, phase):
+        """reconstruct_signal_from_spectrogram(mel=True, db=True) (dp:99-116) with an explicit phase:
+        mel_db [B, 80, T] dB, phase [B, T_ph, 321] complex64 (frame-major).  Returns PCM [B, 160*(min(T, T_ph)-1)]."""
+        mel = mel_db.to(torch.float32).contiguous()
+        ph = torch.view_as_real(phase.to(torch.complex64).contiguous())
+        B, _, T_mel = mel.shape
+        T_ph = phase.shape[1]
+        T_use = min(T_mel, T_ph)
+        out = torch.empty((B, HOP * (T_use - 1)), dtype=torch.float32, device=self.device)
+        per = ctypes.c_longlong(0)
+        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        a = InverseArgs()
+        a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, T_mel, T_mel
+        a.mel_stride = _rs(mel)
+        a.mixed_pcm, a.pcm_stride, a.len_pcm = 0, 0, 0
+        a.B, a.L = B, 0
+        a.out_pcm, a.out_stride = _ptr(out), _rs(out)
+        a.work, a.work_stride = _ptr(work), per.value
+        a.phase, a.phase_stride, a.phase_frames = ph.data_ptr(), T_ph * N_BINS, T_ph
+        check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
+        return out
+
+    def reconstruct_spec(self, mixed_pcm, mel_db, lengths=None):
+        """Same with a SPEC-layout spectrogram [B, 80, T_mel] (dp:99-116 called directly with mel=True, db=True)."""
+        mixed_pcm = self._as_batch(mixed_pcm)
+        mel = mel_db if mel_db.dtype == torch.float32 else mel_db.to(torch.float32)
+        if mel.dim() == 2:
+            mel = mel.unsqueeze(0)
+        mel = mel.contiguous()
+        B, L = mixed_pcm.shape
+        T_use = min(mel.shape[2], self.n_frames(L))
+        out = torch.empty((B, HOP * (T_use - 1)), dtype=torch.float32, device=self.device)
+        per = ctypes.c_longlong(0)
+        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        a = InverseArgs()
+        a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, mel.shape[2], mel.shape[2]
+        a.mel_stride = _rs(mel)
+        a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), _rs(mixed_pcm), _ptr(lengths)
+        a.B, a.L = B, L
+        a.out_pcm, a.out_stride = _ptr(out), _rs(out)
+        a.work, a.work_stride = _ptr(work), per.value
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
 

@@ -97,6 +97,36 @@ int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, i
                       float* slices, long long slices_stride, int n_slices, int B,
                       const int* max_key, int which, void* stream);
 
+typedef struct avse_inverse_args {
+    const float* mel_db;     /* dB log-mel: SLICES [B][n_slices][80][20] (np.concatenate(list(slices), axis=1), dp:66) or SPEC [B][80][ld_t] */
+    int layout;
+    int n_slices;            /* layout SLICES */
+    int n_frames;            /* layout SPEC: frames held in mel_db */
+    int ld_t;                /* layout SPEC: leading dimension */
+    long long mel_stride;    /* elements between utterances */
+    const float* mixed_pcm;  /* [B][pcm_stride] mixture waveform whose STFT phase is re-used (dp:64) */
+    long long pcm_stride;
+    const int* len_pcm;      /* [B] samples present (zeros beyond); NULL: L */
+    int B;
+    int L;                   /* mixture length; T = 1 + L/160 frames; frames used = min(mel frames, T) (dp:68) */
+    float* out_pcm;          /* [B][out_stride] reconstructed PCM, 160 * (frames_used - 1) samples each (librosa.istft, dp:114) */
+    long long out_stride;
+    float* work;             /* scratch [B][work_stride], work_stride >= avse_inverse_work_elems(frames_used) */
+    long long work_stride;
+    const float* phase;      /* optional complex64 [B][phase_frames][321] (re, im): explicit phase (dp:99 signature); when set,
+                                mixed_pcm / L are ignored and frames used = min(mel frames, phase_frames) */
+    long long phase_stride;  /* complex elements between utterances */
+    int phase_frames;
+} avse_inverse_args;
+
+/* reconstruct_speech_signal / reconstruct_signal_from_spectrogram (dp:60-74, dp:99-116) for a batch:
+ * db_to_amplitude -> pinv(mel fb) as a tridiagonal solve + 2-tap F^T -> x phase of the mixture's STFT (recomputed
+ * on the fly) -> irfft + Hann + overlap-add / window sum-square, centre trim.  Two kernels on `stream`. */
+int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream);
+
+/* Scratch floats per utterance needed by avse_inverse for `n_frames_use` reconstructed frames. */
+int avse_inverse_work_elems(int n_frames_use, long long* per_utterance);
+
 /* Sets n running-max keys to "minus infinity" (needed before avse_forward when avse_snr_factor,
  * which also resets them, is not part of the sequence, e.g. single-signal spectrograms). */
 int avse_reset_max(avse_ctx* ctx, int* max_key, int n, void* stream);

@@ -1,0 +1,113 @@
+// Host emulation of the inverse kernel's warp stages (TEST INFRASTRUCTURE, not a product path).
+// Same idea as avse_emul.cpp: csrc/avse_inv_stages.cuh is compiled with g++ and one warp is run as a
+// loop over 32 lanes per stage; per-lane registers that live across a __syncwarp() are kept in arrays.
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include "../../audio-visual-speech-enhancement_b200/csrc/avse_common.h"
+#include "../../audio-visual-speech-enhancement_b200/csrc/avse_tables.h"
+#include "../../audio-visual-speech-enhancement_b200/csrc/avse_inv_stages.cuh"
+
+using namespace avse;
+
+namespace {
+
+struct InvWarp {
+    alignas(16) float smem[INV_WARP_SMEM_F];
+    float xr[32][40], xi[32][40];
+    float acc[32][INV_SIDE_ROWS];
+    float keep[32][4], carry[32][4];
+};
+
+// avse_mel_to_coef_kernel restated for the host (float32, same operation order)
+void mel_to_coef(const HostTables& h, const float* mel_slices, int T_use, int T_pad, std::vector<float>& work) {
+    work.assign((size_t)NMEL * T_pad, 0.0f);
+    const float K = 0.16609640474436813f;
+    for (int t = 0; t < T_use; ++t) {
+        const int s = t / SPSS, tt = t - s * SPSS;
+        float d[NMEL];
+        for (int m = 0; m < NMEL; ++m) d[m] = exp2f(K * mel_slices[((size_t)s * NMEL + m) * SPSS + tt]);
+        for (int m = 1; m < NMEL; ++m) d[m] -= h.tri_w[m] * d[m - 1];
+        d[NMEL - 1] *= h.tri_ipiv[NMEL - 1];
+        for (int m = NMEL - 2; m >= 0; --m) d[m] = (d[m] - h.tri_sup[m] * d[m + 1]) * h.tri_ipiv[m];
+        for (int m = 0; m < NMEL; ++m) work[(size_t)m * T_pad + t] = d[m];
+    }
+}
+
+}  // namespace
+
+// chunks > 1 splits the utterance like the kernel does (warm-up group per chunk) to test the carry logic.
+extern "C" int emul_inverse(const float* mel_slices, int n_slices, const float* pcm, int L, int valid, float* out, int out_cap,
+                            int chunks, int sample_rate, double fmin, double fmax) {
+    HostTables h;
+    if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
+    const int T = 1 + L / HOP;
+    const int T_use = n_slices * SPSS < T ? n_slices * SPSS : T;
+    const int G = (T_use + INV_FPG - 1) / INV_FPG;
+    const int T_pad = INV_FPG * (G + 1);
+    const int out_len = HOP * (T_use - 1);
+    if (out_cap < out_len) return -1;
+    std::vector<float> work;
+    mel_to_coef(h, mel_slices, T_use, T_pad, work);
+
+    // tables as the kernel stages them
+    std::vector<vec2> tw(N1 * N2), twT(N1 * N2);
+    for (int k1 = 0; k1 < N1; ++k1)
+        for (int n2 = 0; n2 < N2; ++n2) {
+            vec2 v; v.x = h.tw1t[(k1 * N2 + n2) * 2]; v.y = h.tw1t[(k1 * N2 + n2) * 2 + 1];
+            tw[k1 * N2 + n2] = v;
+            twT[n2 * N1 + k1] = v;
+        }
+    std::vector<ivec4> col(SCAN_BINS);
+    for (int k = 0; k < SCAN_BINS; ++k) {
+        ivec4 e; e.x = e.y = e.z = e.w = 0;
+        if (k < NBINS) {
+            e.x = h.col_band[2 * k]; e.y = h.col_band[2 * k + 1];
+            union { float f; int i; } u0, u1; u0.f = h.col_w[2 * k]; u1.f = h.col_w[2 * k + 1];
+            e.z = u0.i; e.w = u1.i;
+        }
+        col[k] = e;
+    }
+    const float* s_win = h.window.data();
+
+    static InvWarp w;
+    const int cg = (G + chunks - 1) / chunks;
+    const int n_chunks = (G + cg - 1) / cg;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int g0 = c * cg;
+        int g1 = g0 + cg;
+        const bool last_chunk = g1 >= G;
+        if (last_chunk) g1 = G;
+        const int g_first = g0 > 0 ? g0 - 1 : 0;
+        const int g_last = last_chunk ? G : g1 - 1;
+        memset(w.smem, 0, sizeof(w.smem));
+        memset(w.acc, 0, sizeof(w.acc));
+        float* frames = w.smem;
+        float* ybuf = frames + 2 * FRAME_F;
+        float* side = ybuf + INV_Y_F;
+        InvTile tl{};
+        tl.pcm = pcm; tl.L = L; tl.valid = valid < L ? valid : L; tl.T = T; tl.T_use = T_use;
+        for (int g = g_first; g <= g_last; ++g) {
+            tl.t0 = g * INV_FPG;
+            if (tl.t0 < T_use) {
+                for (int m = 0; m < NMEL; ++m)
+                    for (int e = 0; e < 4; ++e) ybuf[4 * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
+                for (int lane = 0; lane < 32; ++lane) inv_stage_pass1(tl, lane, s_win, tw.data(), frames);
+                for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) pass2_store(lane, frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_stage_post<false>(lane, col.data(), ybuf, frames, nullptr, nullptr);
+                for (int lane = 0; lane < 32; ++lane) inv_passA_compute(lane, twT.data(), frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_passA_store(lane, frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_stage_passB_main(lane, s_win, frames, w.acc[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_stage_passB_side(lane, 0, s_win, frames, side);
+                for (int lane = 0; lane < 32; ++lane) inv_stage_passB_side(lane, 1, s_win, frames, side);
+            }
+            const bool write = g >= g0;
+            for (int lane = 0; lane < 32; ++lane) inv_stage_emit_main(lane, tl.t0, T_use, out_len, write, s_win, out, w.acc[lane]);
+            for (int lane = 0; lane < 32; ++lane)
+                inv_stage_emit_side(lane, tl.t0, T_use, out_len, write, s_win, out, side, w.keep[lane], w.carry[lane]);
+            for (int lane = 0; lane < 32; ++lane) inv_stage_rotate_side(lane, side, w.carry[lane]);
+        }
+    }
+    return out_len;
+}

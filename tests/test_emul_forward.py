@@ -31,7 +31,8 @@ def emul():
     out_dir = os.path.join(ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libavse_emul.so")
-    srcs = [os.path.join(ROOT, "tests", "emul", "avse_emul.cpp"), os.path.join(CSRC, "avse_tables.cpp")]
+    srcs = [os.path.join(ROOT, "tests", "emul", "avse_emul.cpp"), os.path.join(ROOT, "tests", "emul", "avse_emul_inv.cpp"),
+            os.path.join(CSRC, "avse_tables.cpp")]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so] + srcs)
     lib = ctypes.CDLL(so)
     lib.emul_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,

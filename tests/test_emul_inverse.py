@@ -1,0 +1,66 @@
+"""CPU-side check of the inverse kernel's warp stages (csrc/avse_inv_stages.cuh) against the float64 oracle and golden vectors."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import avse_oracle as O
+from tests.cases import GOLDEN_CASES, SR, oracle_pair
+from tests.test_emul_forward import emul, _p, GOLD, TOL_PCM  # noqa: F401  (session fixture that builds the emulation library)
+
+
+def _run(emul, mel, pcm, valid, chunks):
+    emul.emul_inverse.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    T_use = min(20 * mel.shape[0], 1 + len(pcm) // 160)
+    out = np.zeros(160 * (T_use - 1), np.float32)
+    n = emul.emul_inverse(_p(mel), mel.shape[0], _p(pcm), len(pcm), valid, _p(out), len(out), chunks, SR, 0.0, 8000.0)
+    assert n == len(out)
+    return out
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_inverse_stage_code_matches_oracle_and_golden(emul, case, chunks):
+    ref = oracle_pair(case)
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    mel = np.ascontiguousarray(gold["speech"])          # float32 dB slices, as the network would hand them over
+    pcm = np.ascontiguousarray(gold["mixed_pcm"])
+    out = _run(emul, mel, pcm, len(pcm), chunks)
+    want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    scale = np.max(np.abs(ref["mixed_pcm"]))
+    assert out.shape == want.shape == gold["recon"].shape
+    assert np.max(np.abs(out - want)) <= TOL_PCM * scale
+    assert np.max(np.abs(out - gold["recon"])) <= TOL_PCM * scale
+
+
+def test_inverse_fewer_slices_than_frames_and_more(emul):
+    # dp:68: frames used = min(20 n, T)
+    case = GOLDEN_CASES[3]
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    pcm = np.ascontiguousarray(gold["mixed_pcm"])
+    for n in (7, 15):
+        mel = np.ascontiguousarray(gold["speech"][:n])
+        out = _run(emul, mel, pcm, len(pcm), 2)
+        want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+        assert out.shape == want.shape
+        assert np.max(np.abs(out - want)) <= TOL_PCM * np.max(np.abs(pcm))
+    # mixture shorter than the spectrogram: T = 1 + L/160 limits
+    short = np.ascontiguousarray(pcm[:20000])
+    mel = np.ascontiguousarray(gold["speech"][:10])
+    out = _run(emul, mel, short, len(short), 1)
+    want = O.reconstruct_speech_signal(O.AudioSignal(short.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    assert out.shape == want.shape == (160 * 125,)
+    assert np.max(np.abs(out - want)) <= TOL_PCM * np.max(np.abs(pcm))
+
+
+def test_inverse_silent_frames_keep_unit_phase(emul):
+    # digital silence inside the mixture: D == 0 -> phase 1+0j (librosa.magphase); packed partner frames must not leak
+    rng = np.random.RandomState(5)
+    pcm = (0.1 * rng.randn(16000)).astype(np.float32)
+    pcm[4000:9000] = 0.0
+    mel = (rng.rand(5, 80, 20) * 40.0 - 60.0).astype(np.float32)
+    out = _run(emul, mel, pcm, len(pcm), 1)
+    want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    assert np.max(np.abs(out - want)) <= TOL_PCM * max(1.0, np.max(np.abs(want)))

@@ -1,0 +1,85 @@
+"""GPU parity tests of the inverse path (avse_inverse through the C ABI) vs the float64 oracle and golden vectors."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import avse_oracle as O
+from tests.cases import GOLDEN_CASES, SR, FPS, oracle_pair
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_PCM = 1e-4   # of full scale (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+    return mod.SpectralEngine(SR, FPS, 200, device="cuda:0")
+
+
+@pytest.fixture(scope="module")
+def dp():
+    return importlib.import_module("audio-visual-speech-enhancement_b200.data_processor")
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+def test_reconstruct_matches_oracle_and_golden(eng, case):
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    out = eng.reconstruct(_dev(gold["mixed_pcm"][None]), _dev(gold["speech"][None]))[0].cpu().numpy()
+    want = O.reconstruct_speech_signal(O.AudioSignal(gold["mixed_pcm"].astype(np.float64), SR), gold["speech"].astype(np.float64), FPS).get_data()
+    scale = np.max(np.abs(gold["mixed_pcm"]))
+    assert out.shape == want.shape
+    assert np.max(np.abs(out - want)) <= TOL_PCM * scale
+    assert np.max(np.abs(out - gold["recon"])) <= TOL_PCM * scale
+
+
+def test_batch_every_utterance_matches_its_own_oracle(eng):
+    golds = [np.load(os.path.join(GOLD, c["name"] + ".npz")) for c in GOLDEN_CASES[:3]]
+    pcm = np.stack([g["mixed_pcm"] for g in golds])
+    mel = np.stack([g["speech"] for g in golds])
+    out = eng.reconstruct(_dev(pcm), _dev(mel)).cpu().numpy()
+    for i, g in enumerate(golds):
+        assert np.max(np.abs(out[i] - g["recon"])) <= TOL_PCM * np.max(np.abs(g["mixed_pcm"]))
+
+
+def test_forward_then_inverse_round_trip_full_size(eng):
+    # BASELINE config 4 scale (1000 x 3 s): the chain forward -> inverse must equal, utterance by utterance, the same
+    # chain run on a 4-utterance sub-batch (batch-size / chunking independence) and stay finite everywhere.
+    B, L = 1000, 48000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    s = torch.randn((B, L), generator=g, device="cuda") * 0.1
+    n = torch.randn((B, L), generator=g, device="cuda") * 0.05
+    mixed, speech, noise, pcm = eng.preprocess_pairs(s, n, 15)
+    rec = eng.reconstruct(pcm, mixed)
+    assert rec.shape == (B, 47840) and torch.isfinite(rec).all()
+    idx = torch.tensor([0, 1, 500, 999], device="cuda")
+    m2, s2, n2, p2 = eng.preprocess_pairs(s[idx].contiguous(), n[idx].contiguous(), 15)
+    rec2 = eng.reconstruct(p2, m2)
+    assert torch.equal(m2, mixed[idx]) and torch.equal(rec2, rec[idx])
+    # reconstructing from the mixture's own log-mel + its own phase must resemble the mixture (lossy mel round trip)
+    err = (rec - pcm[:, :47840]).pow(2).mean().sqrt() / pcm.pow(2).mean().sqrt()
+    assert err.item() < 0.6
+
+
+def test_explicit_phase_and_data_processor_signatures(eng, dp):
+    gold = np.load(os.path.join(GOLD, GOLDEN_CASES[0]["name"] + ".npz"))
+    pcm = gold["mixed_pcm"]
+    sig = dp.AudioSignal(pcm.copy(), SR)
+    rec = dp.reconstruct_speech_signal(sig, gold["speech"], FPS)
+    assert rec.get_number_of_samples() == 15840 and rec.get_sample_rate() == SR
+    assert np.max(np.abs(rec.get_data() - gold["recon"])) <= TOL_PCM * np.max(np.abs(pcm))
+    # dp:99-116 form: explicit magnitude (80, T) + phase (321, T)
+    osig = O.AudioSignal(pcm.astype(np.float64), SR)
+    mag, phase = O.signal_to_spectrogram(osig, 640, 160)
+    want = O.reconstruct_signal_from_spectrogram(mag, phase, SR, 640, 160).get_data()
+    got = dp.reconstruct_signal_from_spectrogram(mag, phase, SR, 640, 160).get_data()
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= TOL_PCM * np.max(np.abs(pcm))
