@@ -42,7 +42,7 @@ class InverseArgs(_c.Structure):
 EXPORTS = [
     "avse_create", "avse_destroy", "avse_last_error", "avse_version", "avse_get_filterbank",
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
-    "avse_inverse", "avse_inverse_work_elems",
+    "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3",
 ]
 
 
@@ -74,6 +74,8 @@ def load(build=True):
     lib.avse_forward.restype = i32
     lib.avse_floor_inplace.argtypes = [vp, vp, ll, ll, i32, vp, i32, vp]
     lib.avse_floor_inplace.restype = i32
+    lib.avse_floor_inplace3.argtypes = [vp, vp, vp, vp, ll, ll, i32, vp, vp]
+    lib.avse_floor_inplace3.restype = i32
     lib.avse_floor_gather.argtypes = [vp, vp, ll, i32, vp, ll, i32, i32, vp, i32, vp]
     lib.avse_floor_gather.restype = i32
     lib.avse_reset_max.argtypes = [vp, vp, i32, vp]

@@ -391,19 +391,41 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
 // ---------------------------------------------------------------------------------------------
 // top_db floor (dp:94) in place, and floor + segment gather (dp:49-57)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restrict__ data, long long stride, long long n_per_utt,
-                                                                 const int* __restrict__ max_key, int which) {
+// blockIdx.z selects the signal (data0/1/2 with max_key column which0 + z).  Only 16-byte groups that actually
+// hold a value below the floor are written back, so the pass costs one read of the data plus a few stores.
+__global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restrict__ data0, float* __restrict__ data1,
+                                                                 float* __restrict__ data2, long long stride, long long n_per_utt,
+                                                                 const int* __restrict__ max_key, int which0) {
     const int u = blockIdx.y;
-    const float thr = key_to_float(max_key[3 * u + which]) - TOP_DB;
+    const int z = blockIdx.z;
+    float* data = z == 0 ? data0 : (z == 1 ? data1 : data2);
+    const float thr = key_to_float(max_key[3 * u + which0 + z]) - TOP_DB;
     float* p = data + (size_t)u * stride;
     const long long n4 = n_per_utt >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<float4*>(p)[i];
-        v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
-        reinterpret_cast<float4*>(p)[i] = v;
+        if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < thr) {
+            v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+            reinterpret_cast<float4*>(p)[i] = v;
+        }
     }
     for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_utt; i += (long long)gridDim.x * blockDim.x)
         p[i] = fmaxf(p[i], thr);
+}
+
+extern "C" int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, float* mixed, long long stride, long long n_per_utt,
+                                   int B, const int* max_key, void* stream) {
+    if (!ctx || !speech || !noise || !mixed || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: NULL argument");
+    if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: bad sizes");
+    if ((((size_t)speech | (size_t)noise | (size_t)mixed) & 15) || (stride & 3))
+        return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: data must be 16-byte aligned with stride % 4 == 0");
+    long long bx = (n_per_utt / 4 + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    dim3 grid((unsigned)bx, (unsigned)B, 3);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B, const int* max_key,
@@ -415,7 +437,7 @@ extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, 
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
     dim3 grid((unsigned)bx, (unsigned)B);
-    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, stride, n_per_utt, max_key, which);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, which);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

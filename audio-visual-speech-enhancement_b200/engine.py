@@ -163,6 +163,14 @@ class SpectralEngine(object):
               "avse_floor_inplace")
         return data
 
+    def floor3_(self, speech, noise, mixed, max_key):
+        """The top_db floor for the three outputs of a pair batch in one launch."""
+        B = speech.shape[0]
+        n = speech[0].numel()
+        assert _rs(speech) == _rs(noise) == _rs(mixed)
+        check(self._lib.avse_floor_inplace3(self._ctx, _ptr(speech), _ptr(noise), _ptr(mixed), _rs(speech), n, B, _ptr(max_key),
+                                            self._stream()), "avse_floor_inplace3")
+
     def floor_gather(self, spec, max_key, which, n_slices):
         """dp:49-57: SPEC [B,80,ld_t] (un-floored) -> floored slices [B,n_slices,80,20]."""
         B, _, ld_t = spec.shape
@@ -198,9 +206,7 @@ class SpectralEngine(object):
         factor, max_key = self.snr_factor(speech[:, :stats_L], noise[:, :stats_L], lengths=fl, snr_db=snr_db)
         res = self.forward_raw(speech, noise, L=L, len_speech=fl, len_noise=fl, factor=factor, layout=LAYOUT_SLICES,
                                n_slices=n, max_key=max_key, out=out)
-        self.floor_(res["speech"], max_key, 0)
-        self.floor_(res["noise"], max_key, 1)
-        self.floor_(res["mixed"], max_key, 2)
+        self.floor3_(res["speech"], res["noise"], res["mixed"], max_key)
         return res["mixed"], res["speech"], res["noise"], res["mixed_pcm"]
 
     def spectrogram(self, signals, lengths=None, stft=False):

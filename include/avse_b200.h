@@ -92,6 +92,10 @@ int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream);
 int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B,
                        const int* max_key, int which, void* stream);
 
+/* The same floor for the three outputs of a pair batch (speech, noise, mixed: max_key columns 0, 1, 2) in one launch. */
+int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, float* mixed, long long stride, long long n_per_utt,
+                        int B, const int* max_key, void* stream);
+
 /* dp:49-57 segment gather with the floor applied: SPEC [B][80][ld_t] -> SLICES [B][n_slices][80][20]. */
 int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, int ld_t,
                       float* slices, long long slices_stride, int n_slices, int B,
