@@ -306,6 +306,14 @@ class SpectralEngine(object):
         return out
 
 
+def shard_range(n_utterances, rank, world_size):
+    """Contiguous utterance range [lo, hi) owned by `rank`: utterances are independent units, ranks own
+    disjoint ranges and no collective is needed on the data path.  Sizes differ by at most one."""
+    base, rem = divmod(int(n_utterances), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 def fit_noise(noise, n_noise, n_speech_max, lengths=None):
     """dp:125-128 for a batch: periodic tiling noise[i mod n_noise] up to the speech length (torch gather; host-side prep)."""
     idx = torch.arange(n_speech_max, device=noise.device) % int(n_noise)
