@@ -42,24 +42,25 @@ AVSE_HD bool inv_group_interior(const InvTile& tl) {
     return tl.t0 * HOP - HALF >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.valid && tl.t0 + 3 < tl.T;
 }
 
-// ---------------------------------------------------------------------------------------
-// pass 1: complex FFT f packs mixture frames tA = t0 + 2f (real part) and tA + 1 (imaginary part);
-// the second is the first shifted by 4 strides of 40 samples, so one batch of 20 loads serves both.
-// ---------------------------------------------------------------------------------------
 // An all-zero windowed frame (zero padding dp:40, digital silence) has D == 0 exactly in the reference and
 // therefore phase 1 + 0j (librosa.magphase).  Packed with a non-zero partner frame its unpacked spectrum
 // would be rounding noise with a random phase, so pass 1 records per packed frame whether any windowed
 // sample is non-zero (all writers store the same value: no race) and the post stage forces 1 + 0j otherwise.
 // Flags live in the frame region's otherwise unused floats [FRAME_ZERO_F, FRAME_ZERO_F + 2).
-AVSE_HD void inv_mark_nonzero(const float (&xr)[16], const float (&xi)[16], float* frame_base) {
+AVSE_HD void inv_mark_nonzero(const cpx (&x)[16], float* frame_base) {
     bool nr = false, ni = false;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { nr = nr || (xr[j] != 0.0f); ni = ni || (xi[j] != 0.0f); }
+    for (int j = 0; j < 16; ++j) { nr = nr || (cre(x[j]) != 0.0f); ni = ni || (cim(x[j]) != 0.0f); }
     if (nr) frame_base[FRAME_ZERO_F] = 1.0f;
     if (ni) frame_base[FRAME_ZERO_F + 1] = 1.0f;
 }
 
-AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+// ---------------------------------------------------------------------------------------
+// pass 1: complex FFT f packs mixture frames tA = t0 + 2f (real part) and tA + 1 (imaginary part);
+// the second is the first shifted by 4 strides of 40 samples, so one batch of 20 loads serves both.
+// s_win2: [640] (w, w) pairs.
+// ---------------------------------------------------------------------------------------
+AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win2, const vec2* s_tw, float* frames) {
     const bool interior = inv_group_interior(tl);
 #pragma unroll 1
     for (int round = 0; round < 3; ++round) {
@@ -67,35 +68,28 @@ AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win, co
         const int f = round < 2 ? round : (lane >> 3) & 1;
         const int n2 = round < 2 ? lane : 32 + (lane & 7);
         const int tA = tl.t0 + 2 * f;
-        float raw[20];
+        cpx x[16];
         if (interior) {
             const float* p = tl.pcm + tA * HOP - HALF + n2;
+            float raw[20];
 #pragma unroll
             for (int j = 0; j < 20; ++j) raw[j] = p[N2 * j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j], raw[j + 4]);
         } else {
-            // frames beyond the last one are clamped (their coefficients are zero, so they contribute nothing)
+            // frames beyond the last one are clamped (their coefficients are zero, so they contribute nothing);
+            // reflection breaks the shift relation: load both frames explicitly
             const int ta = tA < tl.T ? tA : tl.T - 1;
             const int tb = tA + 1 < tl.T ? tA + 1 : tl.T - 1;
             const int ba = ta * HOP - HALF + n2, bb = tb * HOP - HALF + n2;
-            // reflection breaks the shift relation: load both frames explicitly
-            float xa[16], xb[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                xa[j] = load_sample_edge(tl.pcm, ba + N2 * j, tl.L, tl.valid);
-                xb[j] = load_sample_edge(tl.pcm, bb + N2 * j, tl.L, tl.valid);
-            }
-            float xr[16], xi[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] = xa[j] * w; xi[j] = xb[j] * w; }
-            inv_mark_nonzero(xr, xi, frames + f * FRAME_F);
-            pass1_column(xr, xi, f, n2, s_tw, frames);
-            continue;
+            for (int j = 0; j < 16; ++j)
+                x[j] = cmake(load_sample_edge(tl.pcm, ba + N2 * j, tl.L, tl.valid), load_sample_edge(tl.pcm, bb + N2 * j, tl.L, tl.valid));
         }
-        float xr[16], xi[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; xr[j] = raw[j] * w; xi[j] = raw[j + 4] * w; }
-        inv_mark_nonzero(xr, xi, frames + f * FRAME_F);
-        pass1_column(xr, xi, f, n2, s_tw, frames);
+        for (int j = 0; j < 16; ++j) x[j] = cmul_pp(x[j], cload(s_win2 + 2 * (N2 * j + n2)));
+        inv_mark_nonzero(x, frames + f * FRAME_F);
+        pass1_column(x, f, n2, s_tw, frames);
     }
 }
 
@@ -106,6 +100,8 @@ AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win, co
 //   lin_t[k] = w0 c_t[b0] + w1 c_t[b1]                                    (F^T c, dp:112)
 //   Y = lin * phase;  V_k = conj(Y_A + i Y_B), V_{N-k} = conj(conj(Y_A) + i conj(Y_B))   (in place)
 // s_col: [SCAN_BINS] (b0, b1, w0, w1) as ivec4 bit patterns; ybuf: [80][4] coefficients of the group.
+// EXT: the phase is read from a caller-supplied array (reconstruct_signal_from_spectrogram, dp:99) instead of
+// the recomputed mixture STFT; phA / phB point at the [321] complex rows of frames tA and tA + 1 (or nullptr).
 // ---------------------------------------------------------------------------------------
 AVSE_HD float inv_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
@@ -125,8 +121,6 @@ AVSE_HD float bits_to_float(int b) {
 #endif
 }
 
-// EXT: the phase is read from a caller-supplied array (reconstruct_signal_from_spectrogram, dp:99) instead of
-// the recomputed mixture STFT; phA / phB point at the [321] complex rows of frames tA and tA + 1 (or nullptr).
 template <bool EXT>
 AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, float* frames, const vec2* phA, const vec2* phB) {
     const int f = lane & 1, p = lane >> 1;
@@ -142,20 +136,13 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
 #pragma unroll 3
     for (int i = 0; i < POST_CHUNK; ++i) {
         if (i >= LAST_N && last) {
-            if (i == LAST_N) { vec2 z; z.x = 0.0f; z.y = 0.0f; *reinterpret_cast<vec2*>(za + 2 * i) = z; }   // Nyquist bin: lin = 0
+            if (i == LAST_N) cstore(za + 2 * i, cmake(0.0f, 0.0f));   // Nyquist bin: lin = 0
             continue;
         }
-        vec2 a, c;
-        if (!EXT) {
-            a = *reinterpret_cast<const vec2*>(za + 2 * i);
-            c = *reinterpret_cast<const vec2*>(zc - 2 * i);
-        }
         const ivec4 t = tab[i];
-        const vec2 y0 = *reinterpret_cast<const vec2*>(yb + 4 * t.x);
-        const vec2 y1 = *reinterpret_cast<const vec2*>(yb + 4 * t.y);
-        const float w0 = bits_to_float(t.z), w1 = bits_to_float(t.w);
-        const float linA = w0 * y0.x + w1 * y1.x;
-        const float linB = w0 * y0.y + w1 * y1.y;
+        const cpx y0 = cload(yb + 4 * t.x), y1 = cload(yb + 4 * t.y);
+        // (lin_A, lin_B) = w0 (c_A, c_B)[b0] + w1 (c_A, c_B)[b1]
+        const cpx lin = cfma_s(y1, bits_to_float(t.w), cmul_s(y0, bits_to_float(t.z)));
         float par, pai, pbr, pbi;
         if (EXT) {
             const int k = POST_CHUNK * p + i;
@@ -163,21 +150,20 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
             const vec2 qb = phB != nullptr ? phB[k] : vec2{1.0f, 0.0f};
             par = qa.x; pai = qa.y; pbr = qb.x; pbi = qb.y;
         } else {
-            const float ar = a.x + c.x, ai = a.y - c.y;     // 2 X_A
-            const float br = a.y + c.y, bi = c.x - a.x;     // 2 X_B
-            const float na = ar * ar + ai * ai, nb = br * br + bi * bi;
+            const cpx a = cload(za + 2 * i);
+            const cpx c = cload(zc - 2 * i);
+            const cpx xa = cfma_pp(c, cmake(1.0f, -1.0f), a);             // 2 X_A
+            const cpx xb = cmake(cim(a) + cim(c), cre(c) - cre(a));       // 2 X_B
+            const float na = cre(xa) * cre(xa) + cim(xa) * cim(xa), nb = cre(xb) * cre(xb) + cim(xb) * cim(xb);
             const float ia = inv_rsqrt(na), ib = inv_rsqrt(nb);
             const bool okA = na > 0.0f && liveA, okB = nb > 0.0f && liveB;
-            par = okA ? ar * ia : 1.0f; pai = okA ? ai * ia : 0.0f;
-            pbr = okB ? br * ib : 1.0f; pbi = okB ? bi * ib : 0.0f;
+            par = okA ? cre(xa) * ia : 1.0f; pai = okA ? cim(xa) * ia : 0.0f;
+            pbr = okB ? cre(xb) * ib : 1.0f; pbi = okB ? cim(xb) * ib : 0.0f;
         }
-        const float yar = linA * par, yai = linA * pai;
-        const float ybr = linB * pbr, ybi = linB * pbi;
-        vec2 v1, v2;
-        v1.x = yar - ybi; v1.y = -(yai + ybr);          // conj(Y_A + i Y_B)
-        v2.x = yar + ybi; v2.y = yai - ybr;             // conj(conj(Y_A) + i conj(Y_B))
-        *reinterpret_cast<vec2*>(za + 2 * i) = v1;
-        *reinterpret_cast<vec2*>(zc - 2 * i) = v2;
+        const float yar = cre(lin) * par, yai = cre(lin) * pai;
+        const float ybr = cim(lin) * pbr, ybi = cim(lin) * pbi;
+        cstore(za + 2 * i, cmake(yar - ybi, -(yai + ybr)));   // conj(Y_A + i Y_B)
+        cstore(zc - 2 * i, cmake(yar + ybi, yai - ybr));      // conj(conj(Y_A) + i conj(Y_B))
     }
 }
 
@@ -186,15 +172,12 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
 // W_640^{n1' k2'}; after a warp sync the 40 results are written as row n1' = [k2'].
 // s_twT: [40][16] vec2, W_640^{n1' k2'} with n1' minor (conflict-free for lane = n1').
 // ---------------------------------------------------------------------------------------
-AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames, float (&xr)[40], float (&xi)[40]) {
+AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames, cpx (&x)[40]) {
     const int f = lane >> 4, n1 = lane & 15;
     const float* z = frames + f * FRAME_F + 2 * n1;
 #pragma unroll
-    for (int n2 = 0; n2 < 40; ++n2) {
-        const vec2 v = *reinterpret_cast<const vec2*>(z + 2 * N1 * n2);
-        xr[n2] = v.x; xi[n2] = v.y;
-    }
-    dft40_inplace(xr, xi);
+    for (int n2 = 0; n2 < 40; ++n2) x[n2] = cload(z + 2 * N1 * n2);
+    dft40_inplace(x);
 #pragma unroll
     for (int c = 0; c < 5; ++c)
 #pragma unroll
@@ -202,13 +185,11 @@ AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames,
             const int idx = (8 * c + 5 * d) % 40, k2 = (16 * c + 25 * d) % 40;
             if (k2 == 0) continue;
             const vec2 t = s_twT[k2 * N1 + n1];
-            const float r = xr[idx] * t.x - xi[idx] * t.y;
-            const float im = xr[idx] * t.y + xi[idx] * t.x;
-            xr[idx] = r; xi[idx] = im;
+            x[idx] = cmul(x[idx], t.x, t.y);
         }
 }
 
-AVSE_HD void inv_passA_store(int lane, float* frames, const float (&xr)[40], const float (&xi)[40]) {
+AVSE_HD void inv_passA_store(int lane, float* frames, const cpx (&x)[40]) {
     const int f = lane >> 4, n1 = lane & 15;
     float* row = frames + f * FRAME_F + n1 * ROW_F;
     if (n1 == 0) { frames[f * FRAME_F + FRAME_ZERO_F] = 0.0f; frames[f * FRAME_F + FRAME_ZERO_F + 1] = 0.0f; }   // re-arm inv_mark_nonzero
@@ -217,8 +198,7 @@ AVSE_HD void inv_passA_store(int lane, float* frames, const float (&xr)[40], con
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
             const int idx = (8 * c + 5 * d) % 40, k2 = (16 * c + 25 * d) % 40;
-            vec2 v; v.x = xr[idx]; v.y = xi[idx];
-            *reinterpret_cast<vec2*>(row + 2 * k2) = v;
+            cstore(row + 2 * k2, x[idx]);
         }
 }
 
@@ -228,55 +208,52 @@ AVSE_HD void inv_passA_store(int lane, float* frames, const float (&xr)[40], con
 // 160 t0 + 40 J + lane.  Round 2 (k2' = 32 + lane%8, f = lane/8, lanes 0..15): shared side buffer
 // side[J][r], two ordered phases (f = 0 then f = 1) so the adds never race.
 // ---------------------------------------------------------------------------------------
-AVSE_HD void inv_passB_column(int f, int k2, const float* s_win, const float* frames, float (&c)[20]) {
+AVSE_HD void inv_passB_column(int f, int k2, const float* s_win2, const float* frames, float (&c)[20]) {
     const float* col = frames + f * FRAME_F + 2 * k2;
-    float xr[16], xi[16];
+    cpx x[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const vec2 v = *reinterpret_cast<const vec2*>(col + n1 * ROW_F);
-        xr[n1] = v.x; xi[n1] = v.y;
-    }
-    dft16(xr, xi);
+    for (int n1 = 0; n1 < 16; ++n1) x[n1] = cload(col + n1 * ROW_F);
+    dft16(x);
 #pragma unroll
     for (int j = 0; j < 20; ++j) c[j] = 0.0f;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-        const float w = s_win[N2 * k1 + k2] * INV_SCALE;
-        c[k1] += xr[k1] * w;           // frame tA sample 40 k1 + k2
-        c[k1 + 4] -= xi[k1] * w;       // frame tA + 1, one hop (4 rows) later
+        const cpx y = cmul_pp(x[k1], cmul_pp(cload(s_win2 + 2 * (N2 * k1 + k2)), cmake(INV_SCALE, -INV_SCALE)));
+        c[k1] += cre(y);           // frame tA sample 40 k1 + k2
+        c[k1 + 4] += cim(y);       // frame tA + 1 (= -Im / 640), one hop (4 rows) later
     }
 }
 
-AVSE_HD void inv_stage_passB_main(int lane, const float* s_win, const float* frames, float (&acc)[INV_SIDE_ROWS]) {
+AVSE_HD void inv_stage_passB_main(int lane, const float* s_win2, const float* frames, float (&acc)[INV_SIDE_ROWS]) {
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
         float c[20];
-        inv_passB_column(f, lane, s_win, frames, c);
+        inv_passB_column(f, lane, s_win2, frames, c);
 #pragma unroll
         for (int j = 0; j < 20; ++j) acc[j + 8 * f] += c[j];
     }
 }
 
 // side-buffer phase ph (0 or 1): lanes with f == ph add their column into side[J][r]
-AVSE_HD void inv_stage_passB_side(int lane, int ph, const float* s_win, const float* frames, float* side) {
+AVSE_HD void inv_stage_passB_side(int lane, int ph, const float* s_win2, const float* frames, float* side) {
     if (lane >= 16) return;
     const int f = lane >> 3, r = lane & 7;
     if (f != ph) return;
     float c[20];
-    inv_passB_column(f, 32 + r, s_win, frames, c);
+    inv_passB_column(f, 32 + r, s_win2, frames, c);
 #pragma unroll
     for (int j = 0; j < 20; ++j) side[(j + 8 * f) * 8 + r] += c[j];
 }
 
 // librosa.istft window sum-square at padded position P for T_use frames (Appendix A.1): sum over the
 // (<= 4) frames t = P/160 - q that exist.  Interior value is exactly 1.5 for the periodic Hann at hop N/4.
-AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win) {
+AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win2) {
     const int h = P / HOP, r = P - h * HOP;
     float s = 0.0f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int t = h - q;
-        const float w = s_win[r + HOP * q];
+        const float w = s_win2[2 * (r + HOP * q)];
         if (t >= 0 && t < T_use) s += w * w;
     }
     return s > 1.17549435e-38f ? 1.0f / s : 1.0f;   // "> tiny(float32)" guard of librosa.istft
@@ -284,7 +261,7 @@ AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win) {
 
 // Emit the 4 finished hops of the group (rows J = 0..15) and rotate the overlap-add state.
 // out: trimmed PCM of this utterance (index o = P - 320), out_len = 160 (T_use - 1).
-AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win, float* out,
+AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, float* out,
                                  float (&acc)[INV_SIDE_ROWS]) {
     if (write) {
         const bool interior = t0 >= 3 && t0 + 3 < T_use;   // every row has its 4 frames
@@ -293,7 +270,7 @@ AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool 
             const int P = t0 * HOP + N2 * J + lane;
             const int o = P - HALF;
             if (o >= 0 && o < out_len) {
-                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win);
+                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win2);
                 out[o] = acc[J] * rw;
             }
         }
@@ -305,9 +282,8 @@ AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool 
 }
 
 // side buffer: lane = (row J = lane/2, half = lane%2): 4 samples each, then rotate rows.
-AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool write, const float* s_win, float* out,
+AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, float* out,
                                  const float* side, float (&keep)[4], float (&carry)[4]) {
-    // reads only: caller performs the rotation after a warp sync (see inv_stage_rotate_side)
     const int J = lane >> 1, hf = lane & 1;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -321,7 +297,7 @@ AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool 
             const int P = t0 * HOP + N2 * J + 32 + 4 * hf + e;
             const int o = P - HALF;
             if (o >= 0 && o < out_len) {
-                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win);
+                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win2);
                 out[o] = keep[e] * rw;
             }
         }

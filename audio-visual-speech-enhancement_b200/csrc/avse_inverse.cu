@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) avse_mel_to_coef_kernel(const float* __re
 constexpr int INV_WARPS = 6;
 constexpr int INV_THREADS = INV_WARPS * 32;
 constexpr int INV_SM_WIN = INV_WARPS * INV_WARP_SMEM_F;      // [640]
-constexpr int INV_SM_TW = INV_SM_WIN + NFFT;                 // [16][40] vec2   W^{n2 k1}, n2 minor
+constexpr int INV_SM_TW = INV_SM_WIN + 2 * NFFT;             // [16][40] vec2   W^{n2 k1}, n2 minor  (window: (w, w) pairs)
 constexpr int INV_SM_TWT = INV_SM_TW + N1 * N2 * 2;          // [40][16] vec2   W^{n1' k2'}, n1' minor
 constexpr int INV_SM_COL = INV_SM_TWT + N1 * N2 * 2;         // [SCAN_BINS] ivec4
 constexpr int INV_SMEM_F = INV_SM_COL + SCAN_BINS * 4;
@@ -83,7 +83,7 @@ struct InvParams {
 __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __grid_constant__ InvParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NFFT; i += INV_THREADS) smem[INV_SM_WIN + i] = P.window[i];
+    for (int i = threadIdx.x; i < 2 * NFFT; i += INV_THREADS) smem[INV_SM_WIN + i] = P.window[i];
     for (int i = threadIdx.x; i < N1 * N2; i += INV_THREADS) {
         const int k1 = i / N2, n2 = i - k1 * N2;
         const float re = P.tw1t[2 * i], im = P.tw1t[2 * i + 1];
@@ -150,10 +150,10 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                     inv_stage_pass1(tl, lane, s_win, s_tw, frames);
                     __syncwarp();
                     {
-                        float xr[40], xi[40];
-                        pass2_compute(lane, frames, xr, xi);
+                        cpx x[40];
+                        pass2_compute(lane, frames, x);
                         __syncwarp();
-                        pass2_store(lane, frames, xr, xi);
+                        pass2_store(lane, frames, x);
                     }
                     __syncwarp();
                     inv_stage_post<false>(lane, s_col, ybuf, frames, nullptr, nullptr);
@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                 }
                 __syncwarp();
                 {
-                    float xr[40], xi[40];
-                    inv_passA_compute(lane, s_twT, frames, xr, xi);
+                    cpx x[40];
+                    inv_passA_compute(lane, s_twT, frames, x);
                     __syncwarp();
-                    inv_passA_store(lane, frames, xr, xi);
+                    inv_passA_store(lane, frames, x);
                 }
                 __syncwarp();
                 inv_stage_passB_main(lane, s_win, frames, acc);
@@ -220,7 +220,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (a.out_stride < P.out_len) return avse_fail(AVSE_E_ARG, "avse_inverse: out_stride < 160 (T_use - 1)");
     if (a.phase && a.phase_stride < (long long)P.T_use * NBINS) return avse_fail(AVSE_E_ARG, "avse_inverse: phase_stride too small");
     if (!a.phase && !a.len_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_inverse: pcm_stride < L needs len_pcm");
-    P.window = ctx->fwd.window;
+    P.window = ctx->fwd.window2;   // (w, w) pairs
     P.tw1t = ctx->fwd.tw1t;
     P.col_band = ctx->d_col_band;
     P.col_w = ctx->d_col_w;

@@ -57,6 +57,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
         {h.tri_ipiv.data(), h.tri_ipiv.size() * 4, 0}, {h.tri_sup.data(), h.tri_sup.size() * 4, 0},
         {h.col_band.data(), h.col_band.size() * 4, 0}, {h.col_w.data(), h.col_w.size() * 4, 0},
         {h.scan_w.data(), h.scan_w.size() * 4, 0},     {h.scan_loc.data(), h.scan_loc.size() * 4, 0},
+        {h.scan_mask.data(), h.scan_mask.size() * 4, 0}, {h.window2.data(), h.window2.size() * 4, 0},
     };
     size_t total = 0;
     for (auto& s : secs) { s.off = total; total += (s.bytes + 255) / 256 * 256; }
@@ -79,6 +80,8 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->d_col_w = (const float*)(b + secs[9].off);
     c->fwd.scan_w = (const float*)(b + secs[10].off);
     c->fwd.scan_loc = (const int*)(b + secs[11].off);
+    c->fwd.scan_mask = (const int*)(b + secs[12].off);
+    c->fwd.window2 = (const float*)(b + secs[13].off);
     c->std_tables = h.scan_ok;   // fused post+mel scan kernel; otherwise the generic band-gather kernel
     cudaSetDevice(prev);
     *out = c;
@@ -174,11 +177,12 @@ constexpr int FWD_CTAS = AVSE_FWD_CTAS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
 // shared memory: per-warp frame buffers, then CTA-shared tables: window, twiddles, then either the
 // scan tables (SCAN kernel) or the banded weight tables (generic kernel)
-constexpr int FWD_SM_WIN = FWD_WARPS * WARP_SMEM_F;               // [640]
-constexpr int FWD_SM_TW = FWD_SM_WIN + NFFT;                      // [16][40] vec2
+constexpr int FWD_SM_WIN = FWD_WARPS * WARP_SMEM_F;               // [640] (w, w) pairs
+constexpr int FWD_SM_TW = FWD_SM_WIN + 2 * NFFT;                  // [16][40] vec2
 constexpr int FWD_SM_MODE = FWD_SM_TW + N1 * N2 * 2;
-constexpr int FWD_SM_SCANW = FWD_SM_MODE;                         // SCAN: [SCAN_BINS] vec2
-constexpr int FWD_SM_SCANLOC = FWD_SM_SCANW + SCAN_BINS * 2;      // SCAN: [80] ivec4
+constexpr int FWD_SM_SCANW = FWD_SM_MODE;                         // SCAN: [SCAN_BINS] vec4
+constexpr int FWD_SM_SCANMASK = FWD_SM_SCANW + SCAN_BINS * 4;     // SCAN: [16] int
+constexpr int FWD_SM_SCANLOC = FWD_SM_SCANMASK + 16;              // SCAN: [80] ivec4
 constexpr int FWD_SM_MELW = FWD_SM_MODE;                          // generic: [80][MEL_WROW]
 constexpr int FWD_SM_MELLO = FWD_SM_MELW + NMEL * MEL_WROW;       // generic: [80] int
 constexpr int FWD_SM_ROUNDW = FWD_SM_MELLO + NMEL;                // generic: [16] int
@@ -204,14 +208,15 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (SCAN) {
-        for (int i = threadIdx.x; i < SCAN_BINS * 2; i += FWD_THREADS) smem[FWD_SM_SCANW + i] = P.tb.scan_w[i];
+        for (int i = threadIdx.x; i < SCAN_BINS * 4; i += FWD_THREADS) smem[FWD_SM_SCANW + i] = P.tb.scan_w[i];
+        if (threadIdx.x < 16) reinterpret_cast<int*>(smem + FWD_SM_SCANMASK)[threadIdx.x] = P.tb.scan_mask[threadIdx.x];
         for (int i = threadIdx.x; i < NMEL * 4; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_SCANLOC)[i] = P.tb.scan_loc[i];
     } else {
         for (int i = threadIdx.x; i < NMEL * MEL_WROW; i += FWD_THREADS) smem[FWD_SM_MELW + i] = P.tb.mel_w[i];
         for (int i = threadIdx.x; i < NMEL; i += FWD_THREADS) reinterpret_cast<int*>(smem + FWD_SM_MELLO)[i] = P.tb.mel_lo[i];
         if (threadIdx.x < MEL_ROUNDS) reinterpret_cast<int*>(smem + FWD_SM_ROUNDW)[threadIdx.x] = P.tb.mel_roundw[threadIdx.x];
     }
-    for (int i = threadIdx.x; i < NFFT; i += FWD_THREADS) smem[FWD_SM_WIN + i] = P.tb.window[i];
+    for (int i = threadIdx.x; i < 2 * NFFT; i += FWD_THREADS) smem[FWD_SM_WIN + i] = P.tb.window2[i];
     for (int i = threadIdx.x; i < N1 * N2 * 2; i += FWD_THREADS) smem[FWD_SM_TW + i] = P.tb.tw1t[i];
     float* frames = smem + warp * WARP_SMEM_F;
     // keep never-written pad slots finite (they are multiplied by exact-zero weights)
@@ -278,10 +283,10 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
 
         // ---- pass 2 ----
         {
-            float yr[40], yi[40];
-            pass2_compute(lane, frames, yr, yi);
+            cpx x[40];
+            pass2_compute(lane, frames, x);
             __syncwarp();
-            pass2_store(lane, frames, yr, yi);
+            pass2_store(lane, frames, x);
         }
         __syncwarp();
 
@@ -292,9 +297,10 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
             if (A.stft_speech != nullptr && tf < P.T)
                 srow = reinterpret_cast<vec2*>(A.stft_speech) + ((size_t)u * P.T + tf) * NBINS;
             if (SCAN) {
-                const vec2* s_scan = reinterpret_cast<const vec2*>(smem + FWD_SM_SCANW);
-                if (A.stft_speech != nullptr) stage_post_scan<true>(lane, factor, s_scan, frames, srow);
-                else stage_post_scan<false>(lane, factor, s_scan, frames, nullptr);
+                const vec4* s_scan = reinterpret_cast<const vec4*>(smem + FWD_SM_SCANW);
+                const int* s_mask = reinterpret_cast<const int*>(smem + FWD_SM_SCANMASK);
+                if (A.stft_speech != nullptr) stage_post_scan<true>(lane, factor, s_scan, s_mask, frames, srow);
+                else stage_post_scan<false>(lane, factor, s_scan, s_mask, frames, nullptr);
             } else {
                 if (A.stft_speech != nullptr) stage_post<true>(lane, factor, frames, srow);
                 else stage_post<false>(lane, factor, frames, nullptr);
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
         if (!SCAN) {
             // ---- generic mel (results staged over the now-dead frame buffer 0) ----
             float acc[MEL_ROUNDS][3];
-            stage_mel<false>(lane, s_roundw, s_melw, s_mello, frames, acc);
+            stage_mel(lane, s_roundw, s_melw, s_mello, frames, acc);
             __syncwarp();
             stage_mel_store(lane, acc, frames);
             __syncwarp();

@@ -137,8 +137,11 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
     // and band j (rising edge, accumulator B).  Lane chunk p scans bins 21p..21p+20 (p = 15: 315..319) and
     // emits A whenever the segment index advances; the two accumulators left at the chunk end are flushed.
     // Every band must end up with at most two partial sums ("locations") or the scan is not usable.
+    t.window2.resize(2 * NFFT);
+    for (int n = 0; n < NFFT; ++n) { t.window2[2 * n] = t.window[n]; t.window2[2 * n + 1] = t.window[n]; }
     t.scan_ok = true;
-    t.scan_w.assign((size_t)SCAN_BINS * 2, 0.0f);
+    t.scan_w.assign((size_t)SCAN_BINS * 4, 0.0f);
+    t.scan_mask.assign(16, 0);
     t.scan_loc.assign((size_t)NMEL * 4, 0);
     std::vector<int> seg(NBINS, 0);
     for (int k = 0; k < NBINS; ++k) {
@@ -153,8 +156,8 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
             if (t.fb[(size_t)m * NBINS + k] != 0.0 && m != j - 1 && m != j) t.scan_ok = false;   // not a 2-tap triangular bank
         const double wa = (j >= 1 && j - 1 < NMEL) ? t.fb[(size_t)(j - 1) * NBINS + k] : 0.0;
         const double wb = (j < NMEL) ? t.fb[(size_t)j * NBINS + k] : 0.0;
-        t.scan_w[k * 2 + 0] = (float)(0.5 * wa);
-        t.scan_w[k * 2 + 1] = (float)(0.5 * wb);
+        t.scan_w[k * 4 + 0] = t.scan_w[k * 4 + 1] = (float)(0.5 * wa);
+        t.scan_w[k * 4 + 2] = t.scan_w[k * 4 + 3] = (float)(0.5 * wb);
     }
     std::vector<int> nloc(NMEL, 0);
     auto add_loc = [&](int band, int off_sn, int off_m) {
@@ -171,8 +174,7 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
             if (seg[k] == seg[k - 1]) continue;
             if (seg[k] != seg[k - 1] + 1) { t.scan_ok = false; break; }   // empty segment
             // emission before bin k: A (band seg[k-1]-1) is written over bin k's own (already read) slots
-            t.scan_w[k * 2 + 0] = -t.scan_w[k * 2 + 0];
-            if (t.scan_w[k * 2 + 0] == 0.0f) t.scan_w[k * 2 + 0] = -0.0f;
+            t.scan_mask[p] |= 1 << (k - k0);
             add_loc(seg[k - 1] - 1, 2 * k, 2 * (NFFT - k));
         }
         // chunk-end flush: A -> band seg[k1]-1, B -> band seg[k1]

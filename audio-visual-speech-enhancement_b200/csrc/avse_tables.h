@@ -24,7 +24,9 @@ struct HostTables {
 
     // fused post+mel "scan" (see avse_fwd_stages.cuh stage_post_scan): valid when scan_ok
     bool scan_ok = false;
-    std::vector<float> scan_w;        // [SCAN_BINS][2]  (wA | emit flag in the sign bit, wB), 0.5 * weights
+    std::vector<float> scan_w;        // [SCAN_BINS][4]  (wA, wA, wB, wB), 0.5 * weights (pairs feed packed FFMA2)
+    std::vector<int> scan_mask;       // [16]  bit i of chunk p: a band is finished before bin 21p + i (emit accumulator A)
+    std::vector<float> window2;       // [640][2]  (w, w) pairs of the periodic Hann window
     std::vector<int> scan_loc;        // [80][4]  frame-relative float offsets (SN0, M0, SN1, M1) of each band's <= 2 partial sums
 
     // inverse path

@@ -34,15 +34,15 @@ extern "C" int emul_tables_info(int sample_rate, double fmin, double fmax, int* 
 // a __syncwarp() in the kernel.
 struct EmulWarp {
     alignas(16) float frames[WARP_SMEM_F];
-    float yr[32][40], yi[32][40];
+    cpx x[32][40];
     float acc[32][MEL_ROUNDS][3];
 };
 
-static void emul_fft_stages(EmulWarp& w, const HostTables& h, const FwdTile& tl) {
+static void emul_fft_stages(EmulWarp& w, const HostTables& h, const float* win2, const FwdTile& tl) {
     const vec2* s_tw = reinterpret_cast<const vec2*>(h.tw1t.data());
-    for (int lane = 0; lane < 32; ++lane) stage_pass1(tl, lane, h.window.data(), s_tw, w.frames);
-    for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, w.frames, w.yr[lane], w.yi[lane]);
-    for (int lane = 0; lane < 32; ++lane) pass2_store(lane, w.frames, w.yr[lane], w.yi[lane]);
+    for (int lane = 0; lane < 32; ++lane) stage_pass1(tl, lane, win2, s_tw, w.frames);
+    for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, w.frames, w.x[lane]);
+    for (int lane = 0; lane < 32; ++lane) pass2_store(lane, w.frames, w.x[lane]);
 }
 
 // 640-point FFT of one complex frame through pass 1 (with unit window) + pass 2: checks the
@@ -50,7 +50,7 @@ static void emul_fft_stages(EmulWarp& w, const HostTables& h, const FwdTile& tl)
 extern "C" int emul_fft640(const float* re, const float* im, float* out_re, float* out_im) {
     HostTables h;
     if (!build_tables(h, 16000, 0.0, 8000.0)) return -2;
-    for (auto& v : h.window) v = 1.0f;
+    std::vector<float> ones(2 * NFFT, 1.0f);
     static EmulWarp w;
     memset(w.frames, 0, sizeof(w.frames));
     const int L = 8 * NFFT;
@@ -60,7 +60,7 @@ extern "C" int emul_fft640(const float* re, const float* im, float* out_re, floa
     FwdTile tl{};
     tl.sp = s.data(); tl.nz = n.data(); tl.L = L; tl.valid_s = L; tl.valid_n = L; tl.vmin = L; tl.T = 1 + L / HOP; tl.t0 = 8;
     tl.factor = 0.0f; tl.mixed_pcm = nullptr;
-    emul_fft_stages(w, h, tl);
+    emul_fft_stages(w, h, ones.data(), tl);
     for (int k = 0; k < NFFT; ++k) { out_re[k] = w.frames[2 * k]; out_im[k] = w.frames[2 * k + 1]; }
     return 0;
 }
@@ -86,18 +86,20 @@ extern "C" int emul_forward_mode(const float* speech, const float* noise, int L,
     out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
     out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
     float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    const vec2* s_scan = reinterpret_cast<const vec2*>(h.scan_w.data());
+    std::vector<vec4> scanw(SCAN_BINS);
+    for (int k = 0; k < SCAN_BINS; ++k) { scanw[k].x = h.scan_w[4 * k]; scanw[k].y = h.scan_w[4 * k + 1]; scanw[k].z = h.scan_w[4 * k + 2]; scanw[k].w = h.scan_w[4 * k + 3]; }
     std::vector<ivec4> loc(NMEL);
     for (int m = 0; m < NMEL; ++m) { loc[m].x = h.scan_loc[4 * m]; loc[m].y = h.scan_loc[4 * m + 1]; loc[m].z = h.scan_loc[4 * m + 2]; loc[m].w = h.scan_loc[4 * m + 3]; }
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * FPG;
-        emul_fft_stages(w, h, tl);
+        emul_fft_stages(w, h, h.window2.data(), tl);
         if (scan) {
-            for (int lane = 0; lane < 32; ++lane) stage_post_scan<false>(lane, tl.factor, s_scan, w.frames, nullptr);
+            for (int lane = 0; lane < 32; ++lane)
+                stage_post_scan<false>(lane, tl.factor, scanw.data(), h.scan_mask.data(), w.frames, nullptr);
         } else {
             for (int lane = 0; lane < 32; ++lane) stage_post<false>(lane, tl.factor, w.frames, nullptr);
             for (int lane = 0; lane < 32; ++lane)
-                stage_mel<false>(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
+                stage_mel(lane, h.mel_roundw.data(), h.mel_w.data(), h.mel_lo.data(), w.frames, w.acc[lane]);
             for (int lane = 0; lane < 32; ++lane) stage_mel_store(lane, w.acc[lane], w.frames);
         }
         for (int q = 0; q < 3; ++q)

@@ -14,7 +14,7 @@ namespace {
 
 struct InvWarp {
     alignas(16) float smem[INV_WARP_SMEM_F];
-    float xr[32][40], xi[32][40];
+    cpx x[32][40];
     float acc[32][INV_SIDE_ROWS];
     float keep[32][4], carry[32][4];
 };
@@ -68,7 +68,7 @@ extern "C" int emul_inverse(const float* mel_slices, int n_slices, const float* 
         }
         col[k] = e;
     }
-    const float* s_win = h.window.data();
+    const float* s_win = h.window2.data();   // (w, w) pairs
 
     static InvWarp w;
     const int cg = (G + chunks - 1) / chunks;
@@ -93,11 +93,11 @@ extern "C" int emul_inverse(const float* mel_slices, int n_slices, const float* 
                 for (int m = 0; m < NMEL; ++m)
                     for (int e = 0; e < 4; ++e) ybuf[4 * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
                 for (int lane = 0; lane < 32; ++lane) inv_stage_pass1(tl, lane, s_win, tw.data(), frames);
-                for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, frames, w.xr[lane], w.xi[lane]);
-                for (int lane = 0; lane < 32; ++lane) pass2_store(lane, frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) pass2_compute(lane, frames, w.x[lane]);
+                for (int lane = 0; lane < 32; ++lane) pass2_store(lane, frames, w.x[lane]);
                 for (int lane = 0; lane < 32; ++lane) inv_stage_post<false>(lane, col.data(), ybuf, frames, nullptr, nullptr);
-                for (int lane = 0; lane < 32; ++lane) inv_passA_compute(lane, twT.data(), frames, w.xr[lane], w.xi[lane]);
-                for (int lane = 0; lane < 32; ++lane) inv_passA_store(lane, frames, w.xr[lane], w.xi[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_passA_compute(lane, twT.data(), frames, w.x[lane]);
+                for (int lane = 0; lane < 32; ++lane) inv_passA_store(lane, frames, w.x[lane]);
                 for (int lane = 0; lane < 32; ++lane) inv_stage_passB_main(lane, s_win, frames, w.acc[lane]);
                 for (int lane = 0; lane < 32; ++lane) inv_stage_passB_side(lane, 0, s_win, frames, side);
                 for (int lane = 0; lane < 32; ++lane) inv_stage_passB_side(lane, 1, s_win, frames, side);
