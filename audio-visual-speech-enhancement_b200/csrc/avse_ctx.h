@@ -8,6 +8,8 @@
 struct avse_ctx {
     int device = 0;
     int num_sms = 148;
+    bool f4_tables = false;       // scan4 tables usable -> F4 kernel for pair batches
+    bool force_f2 = false;        // AVSE_FORCE_F2=1: keep the 2-frame kernel (tests / A-B runs)
     bool std_tables = false;      // mel round widths equal AVSE_STD_ROUNDW -> unrolled kernels
     avse::HostTables host;
     void* dbase = nullptr;        // one device allocation holding every table

@@ -1,0 +1,290 @@
+// Warp-stage functions of the fast forward kernel ("F4": one warp owns FOUR consecutive STFT frames).
+//
+// Same arithmetic as avse_fwd_stages.cuh (packed z = s + i n, 640 = 16 x 40, STFT linearity for the
+// mixture, fused unpack + mel scan, dB); what changes is the mapping onto the SM, chosen from the ncu
+// profile of the 2-frame kernel, whose limiter was the shared-memory / LSU data pipe (77 % busy):
+//
+//   * pass 1: lane = n2 for ALL four frames, so the 16 window values and 15 twiddles of a lane are the
+//     same for every frame and every group: they live in registers for the whole kernel (no table loads),
+//     and the four frames of a group (hop = 4 strides of 40 samples) share one batch of 28 strided loads
+//     per signal (each sample is loaded once per group instead of 2.3 times).  The 8 residues
+//     n2 = 32..39 of the four frames form a fifth full round (lane = (frame, n2 - 32)).
+//     4 x 40 columns = 5 rounds of 32 lanes: every lane busy (the 2-frame kernel wasted 1/6 of pass 1).
+//   * pass 2: 64 rows = 2 rounds (lane = (frame pair, k1)).
+//   * scan:  lane = (frame, chunk of 41 bins); finished band sums are written DENSELY over the chunk's
+//     own already-consumed slots, so the dB stage (lane = band) reads them without bank conflicts.
+//   * dB:    lane = band; the four frames of a group are 16 contiguous bytes of the slice layout.
+//
+// 8 warps per SM with up to 255 registers each (instead of 16 x 128).
+// Reference semantics: /root/reference/data_processor.py:77-96, :130-133, :35-57.
+#pragma once
+#include "avse_common.h"
+#include "avse_dft.cuh"
+#include "avse_fwd_stages.cuh"
+
+#if !defined(AVSE_SCAN4_UNROLL)
+#define AVSE_SCAN4_UNROLL 8
+#endif
+
+namespace avse {
+
+constexpr int F4 = 4;                          // frames per group
+constexpr int CHUNK4 = 41;                     // bins per scan lane (odd: bank spread); 8 x 41 = 328 >= 321
+constexpr int SCAN4_BINS = 8 * CHUNK4;         // 328
+constexpr int FRAME4_F = N1 * ROW_F + 16;      // 1360 floats per frame buffer, == 16 (mod 32)
+constexpr int FLUSH4_F = 1284;                 // chunk-end partial sums: 8 chunks x 6 floats in [1284, 1332)
+constexpr int WARP4_SMEM_F = F4 * FRAME4_F;    // 5440 floats = 21760 B per warp
+constexpr int RAW4 = 16 + 4 * (F4 - 1);        // 28 strides of 40 samples cover the four frames of a group
+static_assert(FLUSH4_F + 48 <= FRAME4_F && (FLUSH4_F % 2) == 0, "flush area");
+
+// Loop-invariant per-lane constants of pass 1 (n2 = lane): registers for the whole kernel.
+struct Lane4Const {
+    float win[16];   // Hann w[40 j + lane]
+    vec2 tw[16];     // W_640^{lane * k1}  (tw[0] unused)
+};
+
+AVSE_HD void lane4_const_init(int lane, const float* s_win, const vec2* s_tw, Lane4Const& lc) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { lc.win[j] = s_win[N2 * j + lane]; lc.tw[j] = s_tw[j * N2 + lane]; }
+}
+
+// A group is "interior" when its four frames exist and need neither reflection nor zero padding.
+AVSE_HD bool group4_interior(const FwdTile& tl) {
+    return tl.nz != nullptr && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.vmin && tl.t0 + 3 < tl.T;
+}
+
+// DFT-16 over n1, twiddle, store column as rows [k1][n2] of one frame buffer (dst = frame + 2 n2).
+AVSE_HD void p4_column(cpx (&x)[16], const vec2 (&tw)[16], float* dst) {
+    dft16(x);
+    cstore(dst, x[0]);
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) cstore(dst + k1 * ROW_F, cmul(x[k1], tw[k1].x, tw[k1].y));
+}
+
+// The 28 strided samples per signal that the lane's column needs for the four frames (interior groups).
+AVSE_HD void p4_load_raw(const FwdTile& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
+    const int o = tl.t0 * HOP - HALF + lane;
+    const float* ps = tl.sp + o;
+    const float* pn = tl.nz + o;
+#pragma unroll
+    for (int j = 0; j < RAW4; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+}
+
+// Rounds 0..3 of an interior group: frame f, column n2 = lane.  Also stores the mixture PCM (dp:133) of the
+// group's own four hops (strides 8..23 of the batch) for the residues n2 < 32.
+AVSE_HD void stage4_pass1_main(const FwdTile& tl, int lane, const float (&rs)[RAW4], const float (&rn)[RAW4],
+                               const Lane4Const& lc, float* frames) {
+    if (tl.mixed_pcm != nullptr) {
+        float* pm = tl.mixed_pcm + tl.t0 * HOP + lane;
+#pragma unroll
+        for (int j = 8; j < 24; ++j) pm[N2 * (j - 8)] = rs[j] + tl.factor * rn[j];
+    }
+#pragma unroll
+    for (int f = 0; f < F4; ++f) {
+        cpx x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = cmake(rs[4 * f + j] * lc.win[j], rn[4 * f + j] * lc.win[j]);
+        p4_column(x, lc.tw, frames + f * FRAME4_F + 2 * lane);
+    }
+}
+
+// Round 4 of an interior group: lane = (f = lane / 8, r = lane % 8), column n2 = 32 + r of frame f.
+// Window / twiddles come from the CTA's shared tables (8 distinct addresses per load: one wavefront).
+AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    const int f = lane >> 3, n2 = 32 + (lane & 7);
+    const int o = (tl.t0 + f) * HOP - HALF + n2;
+    const float* ps = tl.sp + o;
+    const float* pn = tl.nz + o;
+    float rs[16], rn[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+    vec2 tw[16];
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw[k1 * N2 + n2];
+    tw[0].x = 1.0f; tw[0].y = 0.0f;
+    if (tl.mixed_pcm != nullptr) {
+        float* pm = tl.mixed_pcm + o + HALF;    // this frame's own hop: strides 8..11
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pm[N2 * j] = rs[8 + j] + tl.factor * rn[8 + j];
+    }
+    cpx x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; x[j] = cmake(rs[j] * w, rn[j] * w); }
+    p4_column(x, tw, frames + f * FRAME4_F + 2 * n2);
+}
+
+// Edge / generic groups (first and last frames of an utterance, short or zero-padded signals): every sample
+// goes through the reflect + zero-pad loader.  Cold code, rolled over the five rounds.
+AVSE_HD void stage4_pass1_edge(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+#pragma unroll 1
+    for (int round = 0; round < 5; ++round) {
+        const int f = round < 4 ? round : lane >> 3;
+        const int n2 = round < 4 ? lane : 32 + (lane & 7);
+        const int t_raw = tl.t0 + f;
+        const int t = t_raw < tl.T ? t_raw : tl.T - 1;   // frames past the end duplicate the last one (never stored)
+        const int base = t * HOP - HALF + n2;
+        float rs[16], rn[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            rs[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
+            rn[j] = load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n);
+        }
+        if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = t * HOP + N2 * j + n2;     // this frame's own hop: strides 8..11
+                if (i < tl.L) tl.mixed_pcm[i] = rs[8 + j] + tl.factor * rn[8 + j];
+            }
+        }
+        vec2 tw[16];
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw[k1 * N2 + n2];
+        tw[0].x = 1.0f; tw[0].y = 0.0f;
+        cpx x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; x[j] = cmake(rs[j] * w, rn[j] * w); }
+        p4_column(x, tw, frames + f * FRAME4_F + 2 * n2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 2, round r: lane = (f = 2 r + lane / 16, k1 = lane % 16): row -> in-place DFT-40 -> (after a warp
+// sync) natural order Z[k1 + 16 k2] over the same frame buffer.
+// ---------------------------------------------------------------------------------------
+AVSE_HD void p4_pass2_compute(int lane, int r, const float* frames, cpx (&x)[40]) {
+    const int f = 2 * r + (lane >> 4), k1 = lane & 15;
+    const float* row = frames + f * FRAME4_F + k1 * ROW_F;
+#pragma unroll
+    for (int q = 0; q < 20; ++q) cload2(row + 4 * q, x[2 * q], x[2 * q + 1]);
+    dft40_inplace(x);
+}
+
+AVSE_HD void p4_pass2_store(int lane, int r, float* frames, const cpx (&x)[40]) {
+    const int f = 2 * r + (lane >> 4), k1 = lane & 15;
+    float* z = frames + f * FRAME4_F + 2 * k1;
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int idx = (8 * c + 5 * d) % 40;     // register holding output (c, d)
+            const int k2 = (16 * c + 25 * d) % 40;    // its frequency index within the DFT-40
+            cstore(z + 2 * N1 * k2, x[idx]);          // Z[k1 + 16 k2]
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused unpack + mel scan: lane = (f = lane / 8, chunk p = lane % 8) walks bins k = 41 p + i, i = 0..40.
+//   S' = Z_k + conj Z_{N-k}, N' = (Z_k - conj Z_{N-k}) / i, M' = S' + factor N'   (2 x the three spectra)
+//   band sums: A = band seg-1 (falling edge), B = band seg (rising edge), weights (wa, wb) = 0.5 F[.][k].
+// When the segment advances before bin i (bit i of the chunk's mask) A is complete for this lane: its
+// (speech, noise) pair goes to complex slot 41 p + e and its mixture sum to float 1281 - 82 p - e, e = number
+// of earlier emissions of the lane (both locations were consumed by this lane in an earlier iteration).
+// The two sums left at the end go to the flush area.  s_w: [SCAN4_BINS] (wa, wb).
+// ---------------------------------------------------------------------------------------
+AVSE_HD void stage4_scan(int lane, float factor, const vec2* s_w, unsigned mask_lo, unsigned mask_hi, float* frames) {
+    const int f = lane >> 3, p = lane & 7;
+    float* fr = frames + f * FRAME4_F;
+    const float* za = fr + 2 * CHUNK4 * p;            // slot k      = za + 2 i
+    const float* zc = fr + 2 * (NFFT - CHUNK4 * p);   // slot 640-k  = zc - 2 i
+    const vec2* tab = s_w + CHUNK4 * p;
+    float* esn = fr + 2 * CHUNK4 * p;                 // next (speech, noise) emission slot
+    float* em = fr + 2 * (NFFT - CHUNK4 * p) + 1;     // next mixture emission float
+    float As = 0.0f, An = 0.0f, Am = 0.0f, Bs = 0.0f, Bn = 0.0f, Bm = 0.0f;
+    AVSE_UNROLL_N_(AVSE_SCAN4_UNROLL)
+    for (int i = 0; i < CHUNK4; ++i) {
+        const cpx a = cload(za + 2 * i);
+        const cpx c = cload(zc - 2 * i);
+        const vec2 w = tab[i];
+        const bool emit = i < 32 ? ((mask_lo >> i) & 1u) != 0u : ((mask_hi >> (i - 32)) & 1u) != 0u;
+        if (emit) {
+            cstore(esn, cmake(As, An));
+            *em = Am;
+            esn += 2;
+            em -= 1;
+            As = Bs; An = Bn; Am = Bm;
+            Bs = 0.0f; Bn = 0.0f; Bm = 0.0f;
+        }
+        const cpx s = cfma_pp(c, cmake(1.0f, -1.0f), a);                 // 2 X_speech[k] = Z_k + conj Z_{N-k}
+        const cpx n = cmake(cim(a) + cim(c), cre(c) - cre(a));           // 2 X_noise[k]  = (Z_k - conj Z_{N-k}) / i
+        const cpx m = cfma_s(n, factor, s);                              // 2 X_mixed[k]
+        const float ms = fast_sqrt(cre(s) * cre(s) + cim(s) * cim(s));
+        const float mn = fast_sqrt(cre(n) * cre(n) + cim(n) * cim(n));
+        const float mm = fast_sqrt(cre(m) * cre(m) + cim(m) * cim(m));
+        As += w.x * ms; An += w.x * mn; Am += w.x * mm;
+        Bs += w.y * ms; Bn += w.y * mn; Bm += w.y * mm;
+    }
+    float* fl = fr + FLUSH4_F + 6 * p;
+    cstore(fl + 0, cmake(As, An));
+    cstore(fl + 2, cmake(Bs, Bn));
+    cstore(fl + 4, cmake(Am, Bm));
+}
+
+// ---------------------------------------------------------------------------------------
+// dB stage: lane = band m = 32 q + lane.  s_loc[m] = (main, extra1, extra2, -): each a packed pair of
+// frame-relative float offsets (speech/noise pair | mixture << 16) of one partial sum; extras are -1
+// when absent (a band cut by a chunk boundary has up to three partial sums).
+// ---------------------------------------------------------------------------------------
+AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const float* frames, const FwdOut& out, int t0, int T,
+                       float (&mx)[3]) {
+    const int m = 32 * q + lane;
+    if (m >= NMEL) return;
+    const ivec4 loc = s_loc[m];
+    float mel[3][F4];
+#pragma unroll
+    for (int f = 0; f < F4; ++f) {
+        const float* fr = frames + f * FRAME4_F;
+        const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.x & 0xffff));
+        mel[0][f] = sn.x; mel[1][f] = sn.y; mel[2][f] = fr[loc.x >> 16];
+    }
+    if (loc.y >= 0) {
+#pragma unroll
+        for (int f = 0; f < F4; ++f) {
+            const float* fr = frames + f * FRAME4_F;
+            const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.y & 0xffff));
+            mel[0][f] += sn.x; mel[1][f] += sn.y; mel[2][f] += fr[loc.y >> 16];
+        }
+    }
+    if (loc.z >= 0) {
+#pragma unroll
+        for (int f = 0; f < F4; ++f) {
+            const float* fr = frames + f * FRAME4_F;
+            const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.z & 0xffff));
+            mel[0][f] += sn.x; mel[1][f] += sn.y; mel[2][f] += fr[loc.z >> 16];
+        }
+    }
+    const int nvalid = T - t0 < F4 ? T - t0 : F4;   // >= 1
+    int off;
+    bool store = true;
+    if (out.layout == 0) {
+        const int sl = t0 / SPSS, tt = t0 - sl * SPSS;   // 4 | t0 and 4 | 20: a group never straddles slices
+        off = (sl * NMEL + m) * SPSS + tt;
+        store = sl < out.n_slices;                        // implies nvalid == 4 (n_slices <= T / 20)
+    } else {
+        off = m * out.ld_t + t0;
+    }
+#pragma unroll
+    for (int sig = 0; sig < 3; ++sig) {
+        const float scale = sig == 1 ? factor : 1.0f;
+        float d[F4];
+        float lm = neg_inf();
+#pragma unroll
+        for (int f = 0; f < F4; ++f) {
+            d[f] = amp_to_db(mel[sig][f] * scale);
+            if (f < nvalid && d[f] > lm) lm = d[f];
+        }
+        mx[sig] = lm > mx[sig] ? lm : mx[sig];
+        float* dst = out.dst[sig];
+        if (dst != nullptr && store) {
+            if (out.layout == 0) {
+                vec4 o; o.x = d[0]; o.y = d[1]; o.z = d[2]; o.w = d[3];
+                *reinterpret_cast<vec4*>(dst + off) = o;     // 16-byte aligned: off % 4 == 0
+            } else {
+#pragma unroll
+                for (int f = 0; f < F4; ++f)
+                    if (f < nvalid) dst[off + f] = d[f];
+            }
+        }
+    }
+}
+
+}  // namespace avse

@@ -77,6 +77,9 @@ struct FwdTables {
     const float* scan_w;      // [SCAN_BINS][4]      scan path: (wA, wA, wB, wB), 0.5 * weights
     const int* scan_mask;     // [16]                scan path: bit i of chunk p = "band finished before bin 21p+i"
     const int* scan_loc;      // [80][4]             scan path: partial-sum locations of each band
+    const float* scan4_w;     // [328][2]            F4 kernel: (wa, wb)
+    const unsigned* scan4_mask;   // [8][2]          F4 kernel: emission masks (lo, hi)
+    const int* scan4_loc;     // [80][4]             F4 kernel: packed partial-sum offsets
 };
 
 // One group of FPG frames of one utterance.

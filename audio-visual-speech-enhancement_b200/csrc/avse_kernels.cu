@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <new>
@@ -11,6 +12,7 @@
 #include "avse_tables.h"
 #include "avse_ctx.h"
 #include "avse_fwd_stages.cuh"
+#include "avse_fwd4_stages.cuh"
 
 using namespace avse;
 
@@ -42,6 +44,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     if (e != cudaSuccess || ndev == 0) { delete c; return avse_fail(AVSE_E_NOCUDA, "avse_create: no CUDA device (this library has no CPU path)"); }
     if (device < 0 || device >= ndev) { delete c; return avse_fail(AVSE_E_ARG, "avse_create: bad device index"); }
     c->device = device;
+    { const char* e2 = getenv("AVSE_FORCE_F2"); c->force_f2 = e2 != nullptr && e2[0] == '1'; }   // testing: 2-frame kernel only
     int prev = 0;
     cudaGetDevice(&prev);
     CUDA_TRY(cudaSetDevice(device));
@@ -58,6 +61,8 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
         {h.col_band.data(), h.col_band.size() * 4, 0}, {h.col_w.data(), h.col_w.size() * 4, 0},
         {h.scan_w.data(), h.scan_w.size() * 4, 0},     {h.scan_loc.data(), h.scan_loc.size() * 4, 0},
         {h.scan_mask.data(), h.scan_mask.size() * 4, 0}, {h.window2.data(), h.window2.size() * 4, 0},
+        {h.scan4_w.data(), h.scan4_w.size() * 4, 0},   {h.scan4_mask.data(), h.scan4_mask.size() * 4, 0},
+        {h.scan4_loc.data(), h.scan4_loc.size() * 4, 0},
     };
     size_t total = 0;
     for (auto& s : secs) { s.off = total; total += (s.bytes + 255) / 256 * 256; }
@@ -82,6 +87,10 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->fwd.scan_loc = (const int*)(b + secs[11].off);
     c->fwd.scan_mask = (const int*)(b + secs[12].off);
     c->fwd.window2 = (const float*)(b + secs[13].off);
+    c->fwd.scan4_w = (const float*)(b + secs[14].off);
+    c->fwd.scan4_mask = (const unsigned*)(b + secs[15].off);
+    c->fwd.scan4_loc = (const int*)(b + secs[16].off);
+    c->f4_tables = h.scan4_ok;   // fast F4 kernel (4 frames per warp)
     c->std_tables = h.scan_ok;   // fused post+mel scan kernel; otherwise the generic band-gather kernel
     cudaSetDevice(prev);
     *out = c;
@@ -347,6 +356,144 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
     if (!fresh) flush_max(u);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// F4 forward kernel (pair batches with the standard 2-tap filterbank): one warp = four frames, 8 warps per SM,
+// up to 255 registers per thread so that the pass-1 window / twiddle values stay in registers for the whole
+// kernel.  See avse_fwd4_stages.cuh for the stage functions and the reasoning.
+// ---------------------------------------------------------------------------------------------
+#ifndef AVSE_F4_WARPS
+#define AVSE_F4_WARPS 8
+#endif
+constexpr int F4_WARPS = AVSE_F4_WARPS;
+constexpr int F4_THREADS = F4_WARPS * 32;
+constexpr int F4_SM_WIN = F4_WARPS * WARP4_SMEM_F;             // [640]
+constexpr int F4_SM_TW = F4_SM_WIN + NFFT;                     // [16][40] vec2
+constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec2
+constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 2;        // [80] ivec4
+constexpr int F4_SMEM_F = F4_SM_LOC + NMEL * 4;
+constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
+static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
+static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
+
+__global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NFFT; i += F4_THREADS) smem[F4_SM_WIN + i] = P.tb.window[i];
+    for (int i = threadIdx.x; i < N1 * N2 * 2; i += F4_THREADS) smem[F4_SM_TW + i] = P.tb.tw1t[i];
+    for (int i = threadIdx.x; i < SCAN4_BINS * 2; i += F4_THREADS) smem[F4_SM_SCANW + i] = P.tb.scan4_w[i];
+    for (int i = threadIdx.x; i < NMEL * 4; i += F4_THREADS) reinterpret_cast<int*>(smem + F4_SM_LOC)[i] = P.tb.scan4_loc[i];
+    float* frames = smem + warp * WARP4_SMEM_F;
+    for (int i = lane; i < WARP4_SMEM_F; i += 32) frames[i] = 0.0f;   // pad slots stay finite (they meet exact-zero weights)
+    __syncthreads();
+
+    const float* s_win = smem + F4_SM_WIN;
+    const vec2* s_tw = reinterpret_cast<const vec2*>(smem + F4_SM_TW);
+    const vec2* s_scanw = reinterpret_cast<const vec2*>(smem + F4_SM_SCANW);
+    const ivec4* s_loc = reinterpret_cast<const ivec4*>(smem + F4_SM_LOC);
+
+    Lane4Const lc;
+    lane4_const_init(lane, s_win, s_tw, lc);
+    const unsigned mask_lo = P.tb.scan4_mask[2 * (lane & 7)], mask_hi = P.tb.scan4_mask[2 * (lane & 7) + 1];
+
+    const avse_forward_args& A = P.a;
+    const int gw = blockIdx.x * F4_WARPS + warp;
+    int tile = gw * P.per_warp;
+    int n_tiles = P.total_tiles - tile;
+    n_tiles = n_tiles < P.per_warp ? n_tiles : P.per_warp;
+    if (n_tiles <= 0) return;
+    int u = tile / P.G;
+    int g = tile - u * P.G;
+
+    float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
+    float factor = 0.0f;
+    int vs = 0, vn = 0;
+    bool fresh = true;
+
+    auto flush_max = [&](int uu) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            float v = mx[s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) atomicMax(A.max_key + 3 * uu + s, float_to_key(v));
+            mx[s] = neg_inf();
+        }
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < n_tiles; ++it) {
+        if (fresh) {
+            fresh = false;
+            vs = A.len_speech ? A.len_speech[u] : A.L;
+            vn = A.len_noise ? A.len_noise[u] : vs;
+            vs = vs < A.L ? vs : A.L;
+            vn = vn < A.L ? vn : A.L;
+            factor = A.factor ? A.factor[u] : 1.0f;
+        }
+        FwdTile tl;
+        tl.sp = A.speech + (size_t)u * A.in_stride;
+        tl.nz = A.noise + (size_t)u * A.in_stride;
+        tl.L = A.L;
+        tl.valid_s = vs;
+        tl.valid_n = vn;
+        tl.vmin = vs < vn ? vs : vn;
+        tl.T = P.T;
+        tl.t0 = g * F4;
+        tl.factor = factor;
+        tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
+
+        // ---- pass 1 ----
+        if (group4_interior(tl)) {
+            {
+                float rs[RAW4], rn[RAW4];
+                p4_load_raw(tl, lane, rs, rn);
+                stage4_pass1_main(tl, lane, rs, rn, lc, frames);
+            }
+            stage4_pass1_tail(tl, lane, s_win, s_tw, frames);
+        } else {
+            stage4_pass1_edge(tl, lane, s_win, s_tw, frames);
+        }
+        __syncwarp();
+
+        // ---- pass 2 ----
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            cpx x[40];
+            p4_pass2_compute(lane, r, frames, x);
+            __syncwarp();
+            p4_pass2_store(lane, r, frames, x);
+        }
+        __syncwarp();
+
+        // ---- unpack + mel scan ----
+        stage4_scan(lane, factor, s_scanw, mask_lo, mask_hi, frames);
+        __syncwarp();
+
+        // ---- dB + stores ----
+        {
+            FwdOut out;
+            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
+            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
+            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+            out.layout = A.layout;
+            out.n_slices = A.n_slices;
+            out.ld_t = A.ld_t;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) stage4_db(lane, q, factor, s_loc, frames, out, g * F4, P.T, mx);
+        }
+        __syncwarp();
+
+        if (++g == P.G) {
+            flush_max(u);
+            g = 0;
+            ++u;
+            fresh = true;
+        }
+    }
+    if (!fresh) flush_max(u);
+}
+
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_forward: NULL argument");
     const avse_forward_args& a = *args;
@@ -377,6 +524,26 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
+    // F4 kernel: pair batches (noise present), standard 2-tap filterbank, no complex STFT output
+    const bool use_f4 = ctx->f4_tables && a.noise != nullptr && a.stft_speech == nullptr && !ctx->force_f2;
+    if (use_f4) {
+        static thread_local int configured4_dev = -1;
+        if (configured4_dev != dev) {
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            configured4_dev = dev;
+        }
+        P.G = (P.T + F4 - 1) / F4;
+        const long long total4 = (long long)a.B * P.G;
+        long long blocks4 = ctx->num_sms;
+        const long long need4 = (total4 + F4_WARPS - 1) / F4_WARPS;
+        if (blocks4 > need4) blocks4 = need4;
+        const long long nwarps4 = blocks4 * F4_WARPS;
+        P.total_tiles = (int)total4;
+        P.per_warp = (int)((total4 + nwarps4 - 1) / nwarps4);
+        avse_forward4_kernel<<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (configured_dev != dev) {
         CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(avse_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));

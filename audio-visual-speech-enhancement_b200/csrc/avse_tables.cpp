@@ -186,6 +186,48 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
         if (nloc[m] == 0) { t.scan_ok = false; break; }
         for (int c = nloc[m]; c < 2; ++c) { t.scan_loc[m * 4 + 2 * c] = FRAME_ZERO_F; t.scan_loc[m * 4 + 2 * c + 1] = FRAME_ZERO_F + 2; }
     }
+
+    // ---- F4 kernel scan tables: 8 chunks of CHUNK4 = 41 bins, emissions written densely ----
+    // (constants restated from avse_fwd4_stages.cuh, which this plain-C++ file does not include)
+    {
+        constexpr int CH = 41, NCH = 8, FLUSH = 1284;
+        t.scan4_ok = t.scan_ok;
+        t.scan4_w.assign((size_t)NCH * CH * 2, 0.0f);
+        t.scan4_mask.assign(NCH * 2, 0u);
+        t.scan4_loc.assign((size_t)NMEL * 4, -1);
+        std::vector<int> n4(NMEL, 0);
+        auto add4 = [&](int band, int off_sn, int off_m) {
+            if (band < 0 || band >= NMEL) return;
+            if (n4[band] >= 3) { t.scan4_ok = false; return; }
+            t.scan4_loc[band * 4 + n4[band]] = off_sn | (off_m << 16);
+            ++n4[band];
+        };
+        for (int k = 0; k < NBINS - 1 && t.scan4_ok; ++k) {
+            const int j = seg[k];
+            const double wa = (j >= 1 && j - 1 < NMEL) ? t.fb[(size_t)(j - 1) * NBINS + k] : 0.0;
+            const double wb = (j < NMEL) ? t.fb[(size_t)j * NBINS + k] : 0.0;
+            t.scan4_w[k * 2 + 0] = (float)(0.5 * wa);
+            t.scan4_w[k * 2 + 1] = (float)(0.5 * wb);
+        }
+        for (int p = 0; p < NCH && t.scan4_ok; ++p) {
+            const int k0 = CH * p;
+            const int kl = std::min(k0 + CH - 1, NBINS - 2);   // last weighted bin of the chunk (<= 319)
+            int e = 0;
+            for (int k = k0 + 1; k <= kl; ++k) {
+                if (seg[k] == seg[k - 1]) continue;
+                if (seg[k] != seg[k - 1] + 1) { t.scan4_ok = false; break; }   // empty segment
+                const int i = k - k0;
+                t.scan4_mask[2 * p + (i >> 5)] |= 1u << (i & 31);
+                add4(seg[k - 1] - 1, 2 * (k0 + e), 2 * NFFT + 1 - 2 * k0 - e);
+                ++e;
+            }
+            const int fl = FLUSH + 6 * p;
+            add4(seg[kl] - 1, fl + 0, fl + 4);
+            add4(seg[kl], fl + 2, fl + 5);
+        }
+        for (int m = 0; m < NMEL && t.scan4_ok; ++m)
+            if (n4[m] == 0) t.scan4_ok = false;
+    }
     return true;
 }
 

@@ -29,6 +29,12 @@ struct HostTables {
     std::vector<float> window2;       // [640][2]  (w, w) pairs of the periodic Hann window
     std::vector<int> scan_loc;        // [80][4]  frame-relative float offsets (SN0, M0, SN1, M1) of each band's <= 2 partial sums
 
+    // F4 kernel (avse_fwd4_stages.cuh stage4_scan / stage4_db): 8 chunks of 41 bins, dense emission; valid when scan4_ok
+    bool scan4_ok = false;
+    std::vector<float> scan4_w;       // [328][2]  (wa, wb) = 0.5 * (F[seg-1][k], F[seg][k])
+    std::vector<unsigned> scan4_mask; // [8][2]    bit i of chunk p (lo, hi words): a band is finished before bin 41 p + i
+    std::vector<int> scan4_loc;       // [80][4]   (main, extra1, extra2, -) packed partial-sum offsets (sn | m << 16), -1 = absent
+
     // inverse path
     std::vector<float> tri_w;         // [80] Thomas forward multipliers (w[0] unused)
     std::vector<float> tri_ipiv;      // [80] 1 / pivot

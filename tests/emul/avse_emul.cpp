@@ -9,6 +9,7 @@
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_common.h"
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_tables.h"
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_fwd_stages.cuh"
+#include "../../audio-visual-speech-enhancement_b200/csrc/avse_fwd4_stages.cuh"
 
 using namespace avse;
 
@@ -120,4 +121,66 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
     const int rc = emul_forward_mode(speech, noise, L, valid_s, valid_n, factor, layout, n_slices, ld_t, out_sp, out_nz, out_mix,
                                      mixed_pcm, max3, sample_rate, fmin, fmax, 0);
     return rc < 0 ? rc : 0;
+}
+
+
+// ---- F4 kernel (avse_fwd4_stages.cuh): one emulated warp = four frames ----
+struct EmulWarp4 {
+    alignas(16) float frames[WARP4_SMEM_F];
+    cpx x[32][40];
+    float rs[32][RAW4], rn[32][RAW4];
+    Lane4Const lc[32];
+};
+
+// Returns 1 when the F4 tables are usable, -3 when they are not (the library then uses the 2-frame kernel).
+extern "C" int emul_forward4(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
+                             int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                             float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
+    HostTables h;
+    if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
+    if (!h.scan4_ok || noise == nullptr) return -3;
+    static EmulWarp4 w;
+    memset(w.frames, 0, sizeof(w.frames));
+    const int T = 1 + L / HOP, G = (T + F4 - 1) / F4;
+    const vec2* s_tw = reinterpret_cast<const vec2*>(h.tw1t.data());
+    const vec2* s_scanw = reinterpret_cast<const vec2*>(h.scan4_w.data());
+    std::vector<ivec4> loc(NMEL);
+    for (int m = 0; m < NMEL; ++m) { loc[m].x = h.scan4_loc[4 * m]; loc[m].y = h.scan4_loc[4 * m + 1]; loc[m].z = h.scan4_loc[4 * m + 2]; loc[m].w = h.scan4_loc[4 * m + 3]; }
+    for (int lane = 0; lane < 32; ++lane) lane4_const_init(lane, h.window.data(), s_tw, w.lc[lane]);
+    FwdTile tl{};
+    tl.sp = speech; tl.nz = noise; tl.L = L;
+    tl.valid_s = valid_s < L ? valid_s : L;
+    tl.valid_n = valid_n < L ? valid_n : L;
+    tl.vmin = tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n;
+    tl.T = T; tl.factor = factor; tl.mixed_pcm = mixed_pcm;
+    FwdOut out{};
+    out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
+    out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
+    float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int g = 0; g < G; ++g) {
+        tl.t0 = g * F4;
+        if (group4_interior(tl)) {
+            for (int lane = 0; lane < 32; ++lane) {
+                p4_load_raw(tl, lane, w.rs[lane], w.rn[lane]);
+                stage4_pass1_main(tl, lane, w.rs[lane], w.rn[lane], w.lc[lane], w.frames);
+            }
+            for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, lane, h.window.data(), s_tw, w.frames);
+        } else {
+            for (int lane = 0; lane < 32; ++lane) stage4_pass1_edge(tl, lane, h.window.data(), s_tw, w.frames);
+        }
+        for (int r = 0; r < 2; ++r) {
+            for (int lane = 0; lane < 32; ++lane) p4_pass2_compute(lane, r, w.frames, w.x[lane]);
+            for (int lane = 0; lane < 32; ++lane) p4_pass2_store(lane, r, w.frames, w.x[lane]);
+        }
+        for (int lane = 0; lane < 32; ++lane)
+            stage4_scan(lane, tl.factor, s_scanw, h.scan4_mask[2 * (lane & 7)], h.scan4_mask[2 * (lane & 7) + 1], w.frames);
+        for (int q = 0; q < 3; ++q)
+            for (int lane = 0; lane < 32; ++lane) {
+                float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
+                stage4_db(lane, q, tl.factor, loc.data(), w.frames, out, tl.t0, T, lm);
+                for (int s = 0; s < 3; ++s) if (lm[s] > mx[s]) mx[s] = lm[s];
+            }
+    }
+    for (int s = 0; s < 3; ++s) max3[s] = key_to_float(float_to_key(mx[s]));
+    return 1;
 }

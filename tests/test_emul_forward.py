@@ -161,3 +161,71 @@ def test_scan_and_generic_paths_agree_with_oracle(emul):
         _, g = _run_mode(emul, s, nf, L, fac, 5, mode, 50.0, 7000.0)
         got_full = np.concatenate(list(g[2]), axis=1)
         assert np.max(np.abs(got_full - want[:, :100])) <= TOL_DB, mode
+
+
+# ---- F4 kernel (avse_fwd4_stages.cuh): four frames per warp, dense emission ----
+def _run_emul4(emul, s, nf, L, fac, ns, valid=None, fmin=0.0, fmax=8000.0):
+    emul.emul_forward4.argtypes = emul.emul_forward.argtypes
+    outs = [np.zeros((ns, 80, 20), np.float32) for _ in range(3)]
+    pcm = np.zeros(L, np.float32)
+    mx = np.zeros(3, np.float32)
+    v = len(s) if valid is None else valid
+    rc = emul.emul_forward4(_p(s), _p(nf), L, v, v, fac, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm), _p(mx),
+                            SR, fmin, fmax)
+    assert rc == 1
+    floored = [np.maximum(o, m - 80.0) for o, m in zip(outs, mx)]
+    return dict(speech=floored[0], noise=floored[1], mixed=floored[2], mixed_pcm=pcm, max=mx)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+def test_f4_stage_code_matches_oracle_and_golden(emul, case):
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    L = 3200 * case["nvs"]
+    fac = O.AudioMixer.snr_factor(O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(nf.astype(np.float64), SR), case["snr"])
+    ns = min(case["nvs"], (1 + L // 160) // 20)
+    got = _run_emul4(emul, s, nf, L, fac, ns)
+    ref = oracle_pair(case)
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    for k in ("mixed", "speech", "noise"):
+        assert np.max(np.abs(got[k] - ref[k])) <= TOL_DB, k
+        assert np.max(np.abs(got[k] - gold[k])) <= TOL_DB + 2e-5, k
+    scale = np.max(np.abs(ref["mixed_pcm"]))
+    assert np.max(np.abs(got["mixed_pcm"] - ref["mixed_pcm"])) <= TOL_PCM * scale
+
+
+def test_f4_agrees_with_two_frame_kernel_and_other_filterbank(emul):
+    case = GOLDEN_CASES[0]
+    s, n = make_inputs(case)
+    nf = fitted_noise(s, n)
+    L = 3200 * case["nvs"]
+    fac = O.AudioMixer.snr_factor(O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(nf.astype(np.float64), SR), case["snr"])
+    got4 = _run_emul4(emul, s, nf, L, fac, 5)
+    _, got2 = _run_mode(emul, s, nf, L, fac, 5, 0)
+    for k, o in zip(("speech", "noise", "mixed"), got2):
+        assert np.max(np.abs(got4[k] - o)) <= 2e-4, k      # same arithmetic up to summation order of the band sums
+    fb = O.mel_filterbank(SR, 640, 80, 50.0, 7000.0)
+    mix = s.astype(np.float64) + fac * nf.astype(np.float64)
+    want = O.amplitude_to_db(fb @ np.abs(O.stft(mix[:L], 640, 160)))
+    g = _run_emul4(emul, s, nf, L, fac, 5, fmin=50.0, fmax=7000.0)
+    assert np.max(np.abs(np.concatenate(list(g["mixed"]), axis=1) - want[:, :100])) <= TOL_DB
+
+
+@pytest.mark.parametrize("n_valid,nvs", [(16000, 5), (10000, 5), (7013, 3), (3200, 1), (330, 1)])
+def test_f4_ragged_and_zero_padded_lengths(emul, n_valid, nvs):
+    """pad_with_zeros (dp:40) / short utterances: every group takes the edge path or mixes edge and interior groups."""
+    rng = np.random.RandomState(n_valid)
+    L = 3200 * nvs
+    s = np.zeros(L, np.float32)
+    nf = np.zeros(L, np.float32)
+    nv = min(n_valid, L)
+    s[:nv] = O.synth_speech(nv, SR, 3).astype(np.float32)
+    nf[:nv] = (0.05 * rng.randn(nv)).astype(np.float32)
+    fac = 0.7
+    ns = min(nvs, (1 + L // 160) // 20)
+    got = _run_emul4(emul, s, nf, L, fac, ns, valid=nv)
+    for k, x in (("speech", s.astype(np.float64)), ("noise", fac * nf.astype(np.float64)), ("mixed", s.astype(np.float64) + fac * nf.astype(np.float64))):
+        ref, _ = O.signal_to_spectrogram(O.AudioSignal(x, SR), 640, 160)
+        want = np.stack([ref[:, 20 * i:20 * i + 20] for i in range(ns)])
+        assert np.max(np.abs(got[k] - want)) <= TOL_DB, k
+        assert abs(got["max"][("speech", "noise", "mixed").index(k)] - ref.max()) <= TOL_DB
