@@ -90,20 +90,24 @@ AVSE_HD void stage4_pass1_main(const FwdTile& tl, int lane, const float (&rs)[RA
 
 // Round 4 of an interior group: lane = (f = lane / 8, r = lane % 8), column n2 = 32 + r of frame f.
 // Window / twiddles come from the CTA's shared tables (8 distinct addresses per load: one wavefront).
-AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+AVSE_HD void p4_load_tail_raw(const FwdTile& tl, int lane, float (&rs)[16], float (&rn)[16]) {
     const int f = lane >> 3, n2 = 32 + (lane & 7);
     const int o = (tl.t0 + f) * HOP - HALF + n2;
     const float* ps = tl.sp + o;
     const float* pn = tl.nz + o;
-    float rs[16], rn[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+}
+
+AVSE_HD void stage4_pass1_tail_compute(const FwdTile& tl, int lane, const float (&rs)[16], const float (&rn)[16], const float* s_win,
+                                       const vec2* s_tw, float* frames) {
+    const int f = lane >> 3, n2 = 32 + (lane & 7);
     vec2 tw[16];
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw[k1 * N2 + n2];
     tw[0].x = 1.0f; tw[0].y = 0.0f;
     if (tl.mixed_pcm != nullptr) {
-        float* pm = tl.mixed_pcm + o + HALF;    // this frame's own hop: strides 8..11
+        float* pm = tl.mixed_pcm + (tl.t0 + f) * HOP + n2;    // this frame's own hop: strides 8..11
 #pragma unroll
         for (int j = 0; j < 4; ++j) pm[N2 * j] = rs[8 + j] + tl.factor * rn[8 + j];
     }
@@ -111,6 +115,12 @@ AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, 
 #pragma unroll
     for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + n2]; x[j] = cmake(rs[j] * w, rn[j] * w); }
     p4_column(x, tw, frames + f * FRAME4_F + 2 * n2);
+}
+
+AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+    float rs[16], rn[16];
+    p4_load_tail_raw(tl, lane, rs, rn);
+    stage4_pass1_tail_compute(tl, lane, rs, rn, s_win, s_tw, frames);
 }
 
 // Edge / generic groups (first and last frames of an utterance, short or zero-padded signals): every sample

@@ -362,6 +362,12 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
 // up to 255 registers per thread so that the pass-1 window / twiddle values stay in registers for the whole
 // kernel.  See avse_fwd4_stages.cuh for the stage functions and the reasoning.
 // ---------------------------------------------------------------------------------------------
+#ifndef AVSE_F4_SWP
+#define AVSE_F4_SWP 1
+#endif
+#ifndef AVSE_F4_PREFETCH
+#define AVSE_F4_PREFETCH 2
+#endif
 #ifndef AVSE_F4_WARPS
 #define AVSE_F4_WARPS 8
 #endif
@@ -421,6 +427,116 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         }
     };
 
+    auto prefetch_ahead = [&](int it, int u, int g) {
+#if AVSE_F4_PREFETCH > 0
+        // L2 prefetch of the samples this warp first touches AVSE_F4_PREFETCH groups from now (own tiles only)
+        if (it + AVSE_F4_PREFETCH < n_tiles) {
+            int g2 = g + AVSE_F4_PREFETCH, u2 = u;
+            if (g2 >= P.G) { g2 -= P.G; ++u2; }
+            const int lo = g2 == 0 ? 0 : g2 * (F4 * HOP) + HOP;      // first sample not covered by group g2 - 1
+            const int hi = g2 * (F4 * HOP) + (NFFT + HOP);           // window end of group g2 (exclusive)
+            const int i0 = (lo & ~31) + 32 * lane;                   // one 128-byte line per lane
+            if (i0 < hi && i0 < A.L && i0 < A.in_stride && lane < 22) {
+                const size_t o = (size_t)u2 * A.in_stride + i0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.speech + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noise + o));
+            }
+        }
+#endif
+    };
+#if AVSE_F4_SWP
+    // Software-pipelined tile loop: the raw samples of tile it+1 are loaded into registers before the dB stage of
+    // tile it, so their HBM/L2 latency is covered by the dB arithmetic and stores instead of stalling pass 1.
+    auto load_utt = [&](int uu, int& ovs, int& ovn, float& of) {
+        ovs = A.len_speech ? A.len_speech[uu] : A.L;
+        ovn = A.len_noise ? A.len_noise[uu] : ovs;
+        ovs = ovs < A.L ? ovs : A.L;
+        ovn = ovn < A.L ? ovn : A.L;
+        of = A.factor ? A.factor[uu] : 1.0f;
+    };
+    auto make_tile = [&](int uu, int gg, int tvs, int tvn, float tf) {
+        FwdTile t;
+        t.sp = A.speech + (size_t)uu * A.in_stride;
+        t.nz = A.noise + (size_t)uu * A.in_stride;
+        t.L = A.L;
+        t.valid_s = tvs;
+        t.valid_n = tvn;
+        t.vmin = tvs < tvn ? tvs : tvn;
+        t.T = P.T;
+        t.t0 = gg * F4;
+        t.factor = tf;
+        t.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)uu * A.pcm_stride : nullptr;
+        return t;
+    };
+    load_utt(u, vs, vn, factor);
+    FwdTile tl = make_tile(u, g, vs, vn, factor);
+    bool interior = group4_interior(tl);
+    float rs[RAW4], rn[RAW4], ts[16], tn[16];
+    if (interior) {
+        p4_load_raw(tl, lane, rs, rn);
+        p4_load_tail_raw(tl, lane, ts, tn);
+    }
+#pragma unroll 1
+    for (int it = 0; it < n_tiles; ++it) {
+        prefetch_ahead(it, u, g);
+        // ---- pass 1 ----
+        if (interior) {
+            stage4_pass1_main(tl, lane, rs, rn, lc, frames);
+            stage4_pass1_tail_compute(tl, lane, ts, tn, s_win, s_tw, frames);
+        } else {
+            stage4_pass1_edge(tl, lane, s_win, s_tw, frames);
+        }
+        __syncwarp();
+
+        // ---- pass 2 ----
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            cpx x[40];
+            p4_pass2_compute(lane, r, frames, x);
+            __syncwarp();
+            p4_pass2_store(lane, r, frames, x);
+        }
+        __syncwarp();
+
+        // ---- unpack + mel scan ----
+        stage4_scan(lane, tl.factor, s_scanw, mask_lo, mask_hi, frames);
+        __syncwarp();
+
+        // ---- next tile: issue its loads now ----
+        int u2 = u, g2 = g + 1;
+        int vs2 = vs, vn2 = vn;
+        float factor2 = tl.factor;
+        const bool last_of_utt = g2 == P.G;
+        const bool have_next = it + 1 < n_tiles;
+        if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, vs2, vn2, factor2); }
+        FwdTile tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
+        const bool interior2 = have_next && group4_interior(tnx);
+        if (interior2) {
+            p4_load_raw(tnx, lane, rs, rn);
+            p4_load_tail_raw(tnx, lane, ts, tn);
+        }
+
+        // ---- dB + stores ----
+        {
+            FwdOut out;
+            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
+            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
+            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+            out.layout = A.layout;
+            out.n_slices = A.n_slices;
+            out.ld_t = A.ld_t;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) stage4_db(lane, q, tl.factor, s_loc, frames, out, g * F4, P.T, mx);
+        }
+        __syncwarp();
+
+        if (last_of_utt || !have_next) flush_max(u);
+        u = u2; g = g2; vs = vs2; vn = vn2;
+        tl = tnx;
+        interior = interior2;
+    }
+}
+#else
 #pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
         if (fresh) {
@@ -443,6 +559,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         tl.factor = factor;
         tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
 
+        prefetch_ahead(it, u, g);
         // ---- pass 1 ----
         if (group4_interior(tl)) {
             {
@@ -493,6 +610,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     }
     if (!fresh) flush_max(u);
 }
+#endif
 
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_forward: NULL argument");
