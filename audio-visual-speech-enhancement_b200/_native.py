@@ -24,6 +24,7 @@ class ForwardArgs(_c.Structure):
         ("mixed_pcm", _c.c_void_p), ("pcm_stride", _c.c_longlong),
         ("max_key", _c.c_void_p),
         ("stft_speech", _c.c_void_p),
+        ("min_key", _c.c_void_p),
     ]
 
 
@@ -68,17 +69,17 @@ def load(build=True):
     lib.avse_version.restype = _c.c_char_p
     lib.avse_get_filterbank.argtypes = [vp, vp]
     lib.avse_get_filterbank.restype = i32
-    lib.avse_snr_factor.argtypes = [vp, vp, vp, ll, vp, i32, i32, vp, vp, vp, vp]
+    lib.avse_snr_factor.argtypes = [vp, vp, vp, ll, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.avse_snr_factor.restype = i32
     lib.avse_forward.argtypes = [vp, _c.POINTER(ForwardArgs), vp]
     lib.avse_forward.restype = i32
-    lib.avse_floor_inplace.argtypes = [vp, vp, ll, ll, i32, vp, i32, vp]
+    lib.avse_floor_inplace.argtypes = [vp, vp, ll, ll, i32, vp, vp, i32, vp]
     lib.avse_floor_inplace.restype = i32
-    lib.avse_floor_inplace3.argtypes = [vp, vp, vp, vp, ll, ll, i32, vp, vp]
+    lib.avse_floor_inplace3.argtypes = [vp, vp, vp, vp, ll, ll, i32, vp, vp, vp]
     lib.avse_floor_inplace3.restype = i32
     lib.avse_floor_gather.argtypes = [vp, vp, ll, i32, vp, ll, i32, i32, vp, i32, vp]
     lib.avse_floor_gather.restype = i32
-    lib.avse_reset_max.argtypes = [vp, vp, i32, vp]
+    lib.avse_reset_max.argtypes = [vp, vp, vp, i32, vp]
     lib.avse_reset_max.restype = i32
     lib.avse_max_db.argtypes = [vp, vp, i32, vp, vp]
     lib.avse_max_db.restype = i32

@@ -234,8 +234,11 @@ AVSE_HD void stage4_scan(int lane, float factor, const vec2* s_w, unsigned mask_
 // frame-relative float offsets (speech/noise pair | mixture << 16) of one partial sum; extras are -1
 // when absent (a band cut by a chunk boundary has up to three partial sums).
 // ---------------------------------------------------------------------------------------
+// mx[sig]: running max over ALL frames < T (librosa's max is over the whole (80, T) array, dp:94);
+// mn[32 sig + lane]: per-lane running min over the values actually STORED (lets the floor pass skip utterances that need
+// no clipping); kept in shared memory because three more loop-carried registers cost 12 % of the kernel (255-register cliff).
 AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const float* frames, const FwdOut& out, int t0, int T,
-                       float (&mx)[3]) {
+                       float (&mx)[3], float* mn) {
     const int m = 32 * q + lane;
     if (m >= NMEL) return;
     const ivec4 loc = s_loc[m];
@@ -276,14 +279,17 @@ AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const 
     for (int sig = 0; sig < 3; ++sig) {
         const float scale = sig == 1 ? factor : 1.0f;
         float d[F4];
-        float lm = neg_inf();
+        float lm = neg_inf(), ln = -neg_inf();
 #pragma unroll
         for (int f = 0; f < F4; ++f) {
             d[f] = amp_to_db(mel[sig][f] * scale);
-            if (f < nvalid && d[f] > lm) lm = d[f];
+            const bool v = f < nvalid;
+            lm = v ? fmaxf(lm, d[f]) : lm;     // branch-free: selects, no divergent code in the hot dB loop
+            ln = v ? fminf(ln, d[f]) : ln;
         }
-        mx[sig] = lm > mx[sig] ? lm : mx[sig];
+        mx[sig] = fmaxf(lm, mx[sig]);
         float* dst = out.dst[sig];
+        mn[32 * sig + lane] = fminf(mn[32 * sig + lane], (dst != nullptr && store) ? ln : -neg_inf());
         if (dst != nullptr && store) {
             if (out.layout == 0) {
                 vec4 o; o.x = d[0]; o.y = d[1]; o.z = d[2]; o.w = d[3];

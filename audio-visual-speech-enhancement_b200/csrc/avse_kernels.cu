@@ -121,7 +121,7 @@ extern "C" int avse_get_filterbank(const avse_ctx* ctx, double* host_out) {
 __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const float* __restrict__ speech, const float* __restrict__ noise,
                                                               long long stride, const int* __restrict__ lengths, int L,
                                                               const float* __restrict__ snr_db, float* __restrict__ factor_out,
-                                                              int* __restrict__ max_key) {
+                                                              int* __restrict__ max_key, int* __restrict__ min_key) {
     const int u = blockIdx.x;
     const int n = lengths ? lengths[u] : L;
     const float* s = speech + (size_t)u * stride;
@@ -160,14 +160,15 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const float* __res
         const double db = snr_db ? (double)snr_db[u] : 0.0;
         factor_out[u] = (float)(sqrt(vs / vn) * pow(10.0, -db / 20.0));
         if (max_key) { max_key[3 * u] = (int)0x80000000; max_key[3 * u + 1] = (int)0x80000000; max_key[3 * u + 2] = (int)0x80000000; }
+        if (min_key) { min_key[3 * u] = 0x7fffffff; min_key[3 * u + 1] = 0x7fffffff; min_key[3 * u + 2] = 0x7fffffff; }
     }
 }
 
 extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride, const int* lengths,
-                               int B, int L, const float* snr_db, float* factor_out, int* max_key, void* stream) {
+                               int B, int L, const float* snr_db, float* factor_out, int* max_key, int* min_key, void* stream) {
     if (!ctx || !speech || !noise || !factor_out) return avse_fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
     if (B <= 0 || L <= 0 || stride < L) return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
-    avse_snr_factor_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key);
+    avse_snr_factor_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -377,7 +378,8 @@ constexpr int F4_SM_WIN = F4_WARPS * WARP4_SMEM_F;             // [640]
 constexpr int F4_SM_TW = F4_SM_WIN + NFFT;                     // [16][40] vec2
 constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec2
 constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 2;        // [80] ivec4
-constexpr int F4_SMEM_F = F4_SM_LOC + NMEL * 4;
+constexpr int F4_SM_MIN = F4_SM_LOC + NMEL * 4;                // [warps][3][32] per-lane running minima
+constexpr int F4_SMEM_F = F4_SM_MIN + F4_WARPS * 96;
 constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
 static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
@@ -412,6 +414,8 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     int g = tile - u * P.G;
 
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
+    float* mn = smem + F4_SM_MIN + warp * 96;
+    mn[lane] = -neg_inf(); mn[32 + lane] = -neg_inf(); mn[64 + lane] = -neg_inf();
     float factor = 0.0f;
     int vs = 0, vn = 0;
     bool fresh = true;
@@ -419,11 +423,18 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     auto flush_max = [&](int uu) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-            float v = mx[s];
+            float v = mx[s], w = mn[32 * s + lane];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) atomicMax(A.max_key + 3 * uu + s, float_to_key(v));
+            for (int o = 16; o > 0; o >>= 1) {
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                w = fminf(w, __shfl_xor_sync(0xffffffffu, w, o));
+            }
+            if (lane == 0) {
+                atomicMax(A.max_key + 3 * uu + s, float_to_key(v));
+                if (A.min_key) atomicMin(A.min_key + 3 * uu + s, float_to_key(w));
+            }
             mx[s] = neg_inf();
+            mn[32 * s + lane] = -neg_inf();
         }
     };
 
@@ -526,7 +537,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
 #pragma unroll 1
-            for (int q = 0; q < 3; ++q) stage4_db(lane, q, tl.factor, s_loc, frames, out, g * F4, P.T, mx);
+            for (int q = 0; q < 3; ++q) stage4_db(lane, q, tl.factor, s_loc, frames, out, g * F4, P.T, mx, mn);
         }
         __syncwarp();
 
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
 #pragma unroll 1
-            for (int q = 0; q < 3; ++q) stage4_db(lane, q, factor, s_loc, frames, out, g * F4, P.T, mx);
+            for (int q = 0; q < 3; ++q) stage4_db(lane, q, factor, s_loc, frames, out, g * F4, P.T, mx, mn);
         }
         __syncwarp();
 
@@ -611,6 +622,8 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     if (!fresh) flush_max(u);
 }
 #endif
+
+__global__ void avse_reset_max_kernel(int* __restrict__ max_key, int* __restrict__ min_key, int n, int min_value);
 
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_forward: NULL argument");
@@ -676,59 +689,82 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     if (ctx->std_tables) avse_forward_kernel<true><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     else avse_forward_kernel<false><<<(unsigned)blocks, FWD_THREADS, FWD_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     CUDA_TRY(cudaGetLastError());
+    if (a.min_key) {   // these kernels do not track the stored minimum: "minus infinity" makes the floor pass always run
+        avse_reset_max_kernel<<<(3 * a.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nullptr, a.min_key, 3 * a.B, (int)0x80000000);
+        CUDA_TRY(cudaGetLastError());
+    }
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // top_db floor (dp:94) in place, and floor + segment gather (dp:49-57)
 // ---------------------------------------------------------------------------------------------
-// blockIdx.z selects the signal (data0/1/2 with max_key column which0 + z).  Only 16-byte groups that actually
-// hold a value below the floor are written back, so the pass costs one read of the data plus a few stores.
+// blockIdx.z selects the signal (data0/1/2 with key column which0 + z).  Only 16-byte groups that actually hold a value
+// below the floor are written back, and an utterance whose stored minimum (min_key, tracked by avse_forward) is already
+// >= max - 80 is skipped without being read: the pass then costs one key load per CTA.
 __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restrict__ data0, float* __restrict__ data1,
                                                                  float* __restrict__ data2, long long stride, long long n_per_utt,
-                                                                 const int* __restrict__ max_key, int which0) {
+                                                                 const int* __restrict__ max_key, const int* __restrict__ min_key,
+                                                                 int which0) {
     const int u = blockIdx.y;
     const int z = blockIdx.z;
     float* data = z == 0 ? data0 : (z == 1 ? data1 : data2);
     const float thr = key_to_float(max_key[3 * u + which0 + z]) - TOP_DB;
+    if (min_key != nullptr && key_to_float(min_key[3 * u + which0 + z]) >= thr) return;
     float* p = data + (size_t)u * stride;
     const long long n4 = n_per_utt >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * step < n4; i += 4 * step) {          // four independent 16-byte loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = reinterpret_cast<float4*>(p)[i + k * step];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (fminf(fminf(v[k].x, v[k].y), fminf(v[k].z, v[k].w)) < thr) {
+                v[k].x = fmaxf(v[k].x, thr); v[k].y = fmaxf(v[k].y, thr); v[k].z = fmaxf(v[k].z, thr); v[k].w = fmaxf(v[k].w, thr);
+                reinterpret_cast<float4*>(p)[i + k * step] = v[k];
+            }
+    }
+    for (; i < n4; i += step) {
         float4 v = reinterpret_cast<float4*>(p)[i];
         if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < thr) {
             v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
             reinterpret_cast<float4*>(p)[i] = v;
         }
     }
-    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_utt; i += (long long)gridDim.x * blockDim.x)
-        p[i] = fmaxf(p[i], thr);
+    for (long long j = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_per_utt; j += step)
+        p[j] = fmaxf(p[j], thr);
+}
+
+static unsigned floor_grid_x(long long n_per_utt) {
+    long long bx = (n_per_utt / 4 + 256 * 8 - 1) / (256 * 8);    // >= 8 float4 per thread
+    if (bx < 1) bx = 1;
+    if (bx > 256) bx = 256;
+    return (unsigned)bx;
 }
 
 extern "C" int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, float* mixed, long long stride, long long n_per_utt,
-                                   int B, const int* max_key, void* stream) {
+                                   int B, const int* max_key, const int* min_key, void* stream) {
     if (!ctx || !speech || !noise || !mixed || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: NULL argument");
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: bad sizes");
+    if (B > 65535) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: B > 65535; split the batch");
     if ((((size_t)speech | (size_t)noise | (size_t)mixed) & 15) || (stride & 3))
         return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: data must be 16-byte aligned with stride % 4 == 0");
-    long long bx = (n_per_utt / 4 + 255) / 256;
-    if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)B, 3);
-    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, 0);
+    dim3 grid(floor_grid_x(n_per_utt), (unsigned)B, 3);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, min_key, 0);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B, const int* max_key,
-                                  int which, void* stream) {
+                                  const int* min_key, int which, void* stream) {
     if (!ctx || !data || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: NULL argument");
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: bad sizes");
+    if (B > 65535) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: B > 65535; split the batch");
     if (((size_t)data & 15) || (stride & 3)) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: data must be 16-byte aligned with stride % 4 == 0");
-    long long bx = (n_per_utt / 4 + 255) / 256;
-    if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)B);
-    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, which);
+    dim3 grid(floor_grid_x(n_per_utt), (unsigned)B);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, min_key, which);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -762,14 +798,17 @@ extern "C" int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spe
     return 0;
 }
 
-__global__ void avse_reset_max_kernel(int* __restrict__ max_key, int n) {
+__global__ void avse_reset_max_kernel(int* __restrict__ max_key, int* __restrict__ min_key, int n, int min_value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) max_key[i] = (int)0x80000000;
+    if (i < n) {
+        if (max_key) max_key[i] = (int)0x80000000;
+        if (min_key) min_key[i] = min_value;
+    }
 }
 
-extern "C" int avse_reset_max(avse_ctx* ctx, int* max_key, int n, void* stream) {
+extern "C" int avse_reset_max(avse_ctx* ctx, int* max_key, int* min_key, int n, void* stream) {
     if (!ctx || !max_key || n <= 0) return avse_fail(AVSE_E_ARG, "avse_reset_max: bad argument");
-    avse_reset_max_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_key, n);
+    avse_reset_max_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_key, min_key, n, 0x7fffffff);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

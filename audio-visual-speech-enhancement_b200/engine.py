@@ -30,6 +30,25 @@ def _rs(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t[0].numel())
 
 
+class DbKeys(object):
+    """Per-utterance running dB extrema of (speech, noise, mixed) as order-preserving int32 keys, device resident:
+    `max` [B, 3] over all frames (librosa's top_db reference, dp:94) and `min` [B, 3] over the stored values
+    (lets the floor pass skip utterances that need no clipping)."""
+    __slots__ = ("buf", "max", "min")
+
+    def __init__(self, B, device):
+        self.buf = torch.empty((2, B, 3), dtype=torch.int32, device=device)
+        self.max = self.buf[0]
+        self.min = self.buf[1]
+
+
+def _keys(k):
+    """(max_key tensor, min_key tensor or None) of a DbKeys or of a bare [B, 3] max-key tensor."""
+    if isinstance(k, DbKeys):
+        return k.max, k.min
+    return k, None
+
+
 def geometry(sample_rate, video_frame_rate, slice_duration_ms=200):
     """dp:36, dp:44-45, dp:49 integer geometry."""
     samples_per_slice = int((float(slice_duration_ms) / 1000) * sample_rate)
@@ -95,15 +114,16 @@ class SpectralEngine(object):
 
     # ------------------------------------------------------------------ a3: SNR factor
     def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None):
-        """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], max_key[B,3])."""
+        """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], DbKeys) with the keys reset."""
         speech, noise = self._as_batch(speech), self._as_batch(noise)
         B, L = speech.shape
         assert noise.shape == speech.shape and _rs(noise) == _rs(speech)
         factor = torch.empty(B, dtype=torch.float32, device=self.device)
         if max_key is None:
-            max_key = torch.empty((B, 3), dtype=torch.int32, device=self.device)
+            max_key = DbKeys(B, self.device)
+        kmax, kmin = _keys(max_key)
         check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), _rs(speech), _ptr(lengths), B, L,
-                                        _ptr(snr_db), _ptr(factor), _ptr(max_key), self._stream()), "avse_snr_factor")
+                                        _ptr(snr_db), _ptr(factor), _ptr(kmax), _ptr(kmin), self._stream()), "avse_snr_factor")
         return factor, max_key
 
     # ------------------------------------------------------------------ a1/a4/a5: forward
@@ -135,8 +155,9 @@ class SpectralEngine(object):
         else:
             res.setdefault("mixed_pcm", None)
         if max_key is None:
-            max_key = torch.empty((B, 3), dtype=torch.int32, device=self.device)
-            check(self._lib.avse_reset_max(self._ctx, _ptr(max_key), 3 * B, self._stream()), "avse_reset_max")
+            max_key = DbKeys(B, self.device)
+            check(self._lib.avse_reset_max(self._ctx, _ptr(max_key.max), _ptr(max_key.min), 3 * B, self._stream()), "avse_reset_max")
+        kmax, kmin = _keys(max_key)
         res["max_key"] = max_key
         res["stft"] = torch.empty((B, T, N_BINS), dtype=torch.complex64, device=self.device) if stft else None
         ref = res["speech"]
@@ -149,7 +170,8 @@ class SpectralEngine(object):
         a.out_stride = _rs(ref)
         a.mixed_pcm = _ptr(res["mixed_pcm"])
         a.pcm_stride = _rs(res["mixed_pcm"])
-        a.max_key = _ptr(max_key)
+        a.max_key = _ptr(kmax)
+        a.min_key = _ptr(kmin)
         a.stft_speech = _ptr(res["stft"])
         check(self._lib.avse_forward(self._ctx, ctypes.byref(a), self._stream()), "avse_forward")
         res["T"], res["ld_t"], res["n_slices"], res["layout"] = T, ld_t, n_slices, layout
@@ -159,7 +181,8 @@ class SpectralEngine(object):
         """amplitude_to_db's top_db floor (dp:94), in place, per utterance."""
         B = data.shape[0]
         n = data[0].numel()
-        check(self._lib.avse_floor_inplace(self._ctx, _ptr(data), _rs(data), n, B, _ptr(max_key), which, self._stream()),
+        kmax, kmin = _keys(max_key)
+        check(self._lib.avse_floor_inplace(self._ctx, _ptr(data), _rs(data), n, B, _ptr(kmax), _ptr(kmin), which, self._stream()),
               "avse_floor_inplace")
         return data
 
@@ -168,7 +191,8 @@ class SpectralEngine(object):
         B = speech.shape[0]
         n = speech[0].numel()
         assert _rs(speech) == _rs(noise) == _rs(mixed)
-        check(self._lib.avse_floor_inplace3(self._ctx, _ptr(speech), _ptr(noise), _ptr(mixed), _rs(speech), n, B, _ptr(max_key),
+        kmax, kmin = _keys(max_key)
+        check(self._lib.avse_floor_inplace3(self._ctx, _ptr(speech), _ptr(noise), _ptr(mixed), _rs(speech), n, B, _ptr(kmax), _ptr(kmin),
                                             self._stream()), "avse_floor_inplace3")
 
     def floor_gather(self, spec, max_key, which, n_slices):
@@ -176,12 +200,21 @@ class SpectralEngine(object):
         B, _, ld_t = spec.shape
         out = torch.empty((B, n_slices, N_MELS, SPSS), dtype=torch.float32, device=self.device)
         check(self._lib.avse_floor_gather(self._ctx, _ptr(spec), _rs(spec), ld_t, _ptr(out), _rs(out), n_slices, B,
-                                          _ptr(max_key), which, self._stream()), "avse_floor_gather")
+                                          _ptr(_keys(max_key)[0]), which, self._stream()), "avse_floor_gather")
         return out
 
     def max_db(self, max_key):
+        """Decoded running maxima [B, 3] in dB."""
+        max_key = _keys(max_key)[0]
         out = torch.empty(max_key.shape, dtype=torch.float32, device=self.device)
         check(self._lib.avse_max_db(self._ctx, _ptr(max_key), max_key.numel(), _ptr(out), self._stream()), "avse_max_db")
+        return out
+
+    def min_db(self, keys):
+        """Decoded running minima [B, 3] of the stored dB values (same key encoding as the maxima)."""
+        kmin = _keys(keys)[1]
+        out = torch.empty(kmin.shape, dtype=torch.float32, device=self.device)
+        check(self._lib.avse_max_db(self._ctx, _ptr(kmin), kmin.numel(), _ptr(out), self._stream()), "avse_max_db")
         return out
 
     # ------------------------------------------------------------------ batched reference-level operations

@@ -53,11 +53,12 @@ int avse_get_filterbank(const avse_ctx* ctx, double* host_out);
 /* AudioMixer.snr_factor (dp:130): factor[u] = sqrt(var(speech_u) / var(noise_u)) * 10^(-snr_db[u]/20),
  * population variance over the first lengths[u] samples (lengths == NULL: L for all).
  * Accumulates in float64.  snr_db == NULL means 0 dB for every utterance (the reference).
- * Also resets max_key[u][0..2] (the running dB maxima used by avse_forward / avse_floor_*).
+ * Also resets max_key[u][0..2] (the running dB maxima used by avse_forward / avse_floor_*) and, when
+ * given, min_key[u][0..2] (the running minima of the stored values).
  * speech/noise: [B][stride] with stride >= L. */
 int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride,
                     const int* lengths, int B, int L, const float* snr_db,
-                    float* factor_out, int* max_key, void* stream);
+                    float* factor_out, int* max_key, int* min_key, void* stream);
 
 typedef struct avse_forward_args {
     /* inputs */
@@ -81,6 +82,8 @@ typedef struct avse_forward_args {
     long long pcm_stride;
     int* max_key;            /* [B][3] running maxima (speech, noise, mixed) as ordered-int keys; required */
     float* stft_speech;      /* optional complex64 [B][T][321] (re, im interleaved): librosa.stft of `speech` (dp:79), frame-major */
+    int* min_key;            /* optional [B][3] running minima of the STORED dB values (same key encoding): lets avse_floor_*
+                                skip every utterance whose minimum is already >= max - 80 (nothing to clip) */
 } avse_forward_args;
 
 /* preprocess_audio_pair's arithmetic (dp:130-137) / signal_to_spectrogram (dp:77-96) for a batch:
@@ -88,13 +91,14 @@ typedef struct avse_forward_args {
 int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream);
 
 /* amplitude_to_db's top_db floor (dp:94): x = max(x, max_u - 80), in place on a SLICES or SPEC
- * output of avse_forward.  which: 0 speech, 1 noise, 2 mixed (selects max_key column). */
+ * output of avse_forward.  which: 0 speech, 1 noise, 2 mixed (selects the key column).
+ * min_key (may be NULL): minima written by avse_forward; utterances with min >= max - 80 are skipped unread. */
 int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, long long n_per_utt, int B,
-                       const int* max_key, int which, void* stream);
+                       const int* max_key, const int* min_key, int which, void* stream);
 
 /* The same floor for the three outputs of a pair batch (speech, noise, mixed: max_key columns 0, 1, 2) in one launch. */
 int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, float* mixed, long long stride, long long n_per_utt,
-                        int B, const int* max_key, void* stream);
+                        int B, const int* max_key, const int* min_key, void* stream);
 
 /* dp:49-57 segment gather with the floor applied: SPEC [B][80][ld_t] -> SLICES [B][n_slices][80][20]. */
 int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, int ld_t,
@@ -131,9 +135,9 @@ int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream);
 /* Scratch floats per utterance needed by avse_inverse for `n_frames_use` reconstructed frames. */
 int avse_inverse_work_elems(int n_frames_use, long long* per_utterance);
 
-/* Sets n running-max keys to "minus infinity" (needed before avse_forward when avse_snr_factor,
+/* Sets n running-max keys to "minus infinity" (and, when min_key != NULL, n running-min keys to "plus infinity") (needed before avse_forward when avse_snr_factor,
  * which also resets them, is not part of the sequence, e.g. single-signal spectrograms). */
-int avse_reset_max(avse_ctx* ctx, int* max_key, int n, void* stream);
+int avse_reset_max(avse_ctx* ctx, int* max_key, int* min_key, int n, void* stream);
 
 /* Decodes max_key[u][which] to float dB on the host side convention (device -> device). */
 int avse_max_db(avse_ctx* ctx, const int* max_key, int n, float* out_db, void* stream);

@@ -177,7 +177,8 @@ extern "C" int emul_forward4(const float* speech, const float* noise, int L, int
         for (int q = 0; q < 3; ++q)
             for (int lane = 0; lane < 32; ++lane) {
                 float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
-                stage4_db(lane, q, tl.factor, loc.data(), w.frames, out, tl.t0, T, lm);
+                float ln[96]; for (int i = 0; i < 96; ++i) ln[i] = INFINITY;
+                stage4_db(lane, q, tl.factor, loc.data(), w.frames, out, tl.t0, T, lm, ln);
                 for (int s = 0; s < 3; ++s) if (lm[s] > mx[s]) mx[s] = lm[s];
             }
     }

@@ -161,6 +161,36 @@ def test_linearity_and_scale_invariants_full_size(eng):
     assert torch.all(sp.amin(dim=(1, 2, 3)) >= mx[:, 0] - 80.0)
 
 
+def test_floor_skip_uses_the_stored_minimum(eng):
+    # min keys = min over the STORED un-floored values; the floor pass that skips on them equals the unconditional floor,
+    # both for utterances that need no clipping (white noise) and for ones that do (digital silence -> -100 dB).
+    B, L = 6, 16000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    s = torch.randn((B, L), generator=g, device="cuda") * 0.1
+    n = torch.randn((B, L), generator=g, device="cuda") * 0.05
+    s[1, 4000:9000] = 0.0
+    n[1, 4000:9000] = 0.0       # silence in both: every signal of utterance 1 hits amin
+    s[4, 2000:6000] = 0.0       # silence in the speech only
+    f, keys = eng.snr_factor(s, n)
+    r = eng.forward_raw(s, n, factor=f, n_slices=4, max_key=keys)   # 4 of 5 slices stored
+    mn, mx = eng.min_db(keys), eng.max_db(keys)
+    for j, k in enumerate(("speech", "noise", "mixed")):
+        assert torch.equal(mn[:, j], r[k].amin(dim=(1, 2, 3))), k
+        want = torch.maximum(r[k], (mx[:, j] - 80.0).view(B, 1, 1, 1))
+        got = r[k].clone()
+        eng.floor_(got, keys, j)            # with min keys (skips where possible)
+        assert torch.equal(got, want), k
+        got2 = r[k].clone()
+        eng.floor_(got2, keys.max, j)       # bare max keys: unconditional pass
+        assert torch.equal(got2, want), k
+    need = (mn < mx - 80.0).cpu().numpy()
+    assert need[1].all() and need[4, 0] and not need[0].any() and not need[4, 1]
+    sp, nz, mi = r["speech"].clone(), r["noise"].clone(), r["mixed"].clone()
+    eng.floor3_(sp, nz, mi, keys)
+    assert torch.equal(sp, torch.maximum(r["speech"], (mx[:, 0] - 80.0).view(B, 1, 1, 1)))
+    assert torch.equal(mi, torch.maximum(r["mixed"], (mx[:, 2] - 80.0).view(B, 1, 1, 1)))
+
+
 def test_data_processor_signatures(dp):
     case = GOLDEN_CASES[0]
     s, n = make_inputs(case)
