@@ -43,7 +43,7 @@ class InverseArgs(_c.Structure):
 EXPORTS = [
     "avse_create", "avse_destroy", "avse_last_error", "avse_version", "avse_get_filterbank",
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
-    "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3",
+    "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3", "avse_gather_rows",
 ]
 
 
@@ -87,6 +87,8 @@ def load(build=True):
     lib.avse_inverse.restype = i32
     lib.avse_inverse_work_elems.argtypes = [i32, _c.POINTER(ll)]
     lib.avse_inverse_work_elems.restype = i32
+    lib.avse_gather_rows.argtypes = [vp, vp, vp, vp, ll, ll, vp, ll, vp, vp, vp, vp, vp]
+    lib.avse_gather_rows.restype = i32
     _lib = lib
     return lib
 

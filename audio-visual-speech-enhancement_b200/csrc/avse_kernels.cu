@@ -824,3 +824,56 @@ extern "C" int avse_max_db(avse_ctx* ctx, const int* max_key, int n, float* out_
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// make_sample_set (speech_enhancer.py:241-262): np.concatenate over samples + ONE shared permutation, as a
+// row gather on the device: dst_a[i][:] = src_a[index[i]][:] for up to three arrays that share the index.
+// A row is one (80, 20) slice (6 400 bytes) -- or any multiple of 4 floats.  HBM-bound: 2 x row bytes per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avse_gather_rows_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
+                                                               const float* __restrict__ s2, long long src_rows,
+                                                               const long long* __restrict__ index, long long n_out, int row4,
+                                                               float* __restrict__ d0, float* __restrict__ d1, float* __restrict__ d2,
+                                                               int* __restrict__ bad) {
+    const int z = blockIdx.y;
+    const float4* src = reinterpret_cast<const float4*>(z == 0 ? s0 : (z == 1 ? s1 : s2));
+    float4* dst = reinterpret_cast<float4*>(z == 0 ? d0 : (z == 1 ? d1 : d2));
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n_out; i += nwarps) {       // one warp per output row: coalesced 512-byte bursts
+        const long long r = index[i];
+        if (r < 0 || r >= src_rows) { if (lane == 0) atomicExch(bad, 1); continue; }
+        const float4* sp = src + r * row4;
+        float4* dp = dst + i * row4;
+        int j = lane;
+        for (; j + 96 < row4; j += 128) {
+            const float4 a = sp[j], b = sp[j + 32], c = sp[j + 64], d = sp[j + 96];
+            dp[j] = a; dp[j + 32] = b; dp[j + 64] = c; dp[j + 96] = d;
+        }
+        for (; j < row4; j += 32) dp[j] = sp[j];
+    }
+}
+
+extern "C" int avse_gather_rows(avse_ctx* ctx, const float* src0, const float* src1, const float* src2, long long src_rows,
+                                long long row_elems, const long long* index, long long n_out, float* dst0, float* dst1, float* dst2,
+                                int* bad_index_flag, void* stream) {
+    if (!ctx || !src0 || !dst0 || !index) return avse_fail(AVSE_E_ARG, "avse_gather_rows: NULL argument");
+    if ((src1 == nullptr) != (dst1 == nullptr) || (src2 == nullptr) != (dst2 == nullptr) || (src2 && !src1))
+        return avse_fail(AVSE_E_ARG, "avse_gather_rows: src/dst arrays must be given in matching pairs, in order");
+    if (src_rows <= 0 || n_out <= 0 || row_elems <= 0 || (row_elems & 3) || row_elems > 0x7fffffffLL * 4)
+        return avse_fail(AVSE_E_ARG, "avse_gather_rows: row_elems must be a positive multiple of 4");
+    const float* ps[6] = {src0, src1, src2, dst0, dst1, dst2};
+    for (int i = 0; i < 6; ++i)
+        if ((size_t)ps[i] & 15) return avse_fail(AVSE_E_ARG, "avse_gather_rows: arrays must be 16-byte aligned");
+    if (!bad_index_flag) return avse_fail(AVSE_E_ARG, "avse_gather_rows: bad_index_flag (device int, zeroed by the caller) is required");
+    const int narr = src2 ? 3 : (src1 ? 2 : 1);
+    long long bx = (n_out + 7) / 8;                      // 8 warps per CTA
+    const long long cap = (long long)ctx->num_sms * 16;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)narr);
+    avse_gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src0, src1, src2, src_rows, index, n_out, (int)(row_elems / 4),
+                                                                    dst0, dst1, dst2, bad_index_flag);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -142,6 +142,15 @@ int avse_reset_max(avse_ctx* ctx, int* max_key, int* min_key, int n, void* strea
 /* Decodes max_key[u][which] to float dB on the host side convention (device -> device). */
 int avse_max_db(avse_ctx* ctx, const int* max_key, int n, float* out_db, void* stream);
 
+/* make_sample_set (speech_enhancer.py:241-262): the np.concatenate over samples followed by ONE shared random
+ * permutation, as a device row gather: dstK[i][0..row_elems) = srcK[index[i]][0..row_elems) for K = 0..2 (src1/dst1 and
+ * src2/dst2 optional, given in order).  Rows are dense (row stride == row_elems, a multiple of 4 floats; a slice is
+ * 80 * 20 = 1600).  index: int64 [n_out] on the device, values in [0, src_rows); an out-of-range value sets
+ * *bad_index_flag (device int the caller zeroed) and leaves that output row untouched. */
+int avse_gather_rows(avse_ctx* ctx, const float* src0, const float* src1, const float* src2, long long src_rows,
+                     long long row_elems, const long long* index, long long n_out, float* dst0, float* dst1, float* dst2,
+                     int* bad_index_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
