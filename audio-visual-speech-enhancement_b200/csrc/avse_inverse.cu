@@ -80,6 +80,9 @@ struct InvParams {
     int out_len;      // 160 (T_use - 1)
 };
 
+// EXT: explicit phase array (dp:99 signature) instead of the recomputed mixture STFT; a separate instantiation keeps each
+// kernel's code (instruction-cache footprint) small.
+template <bool EXT>
 __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __grid_constant__ InvParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                 // coefficients of the 4 frames -> ybuf[band][4]
                 for (int m = lane; m < NMEL; m += 32)
                     *reinterpret_cast<float4*>(ybuf + 4 * m) = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0);
-                if (A.phase == nullptr) {
+                if (!EXT) {
                     inv_stage_pass1(tl, lane, s_win, s_tw, frames);
                     __syncwarp();
                     {
@@ -174,10 +177,11 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                 }
                 __syncwarp();
                 inv_stage_passB_main(lane, s_win, frames, acc);
-                inv_stage_passB_side(lane, 0, s_win, frames, side);
-                __syncwarp();
-                inv_stage_passB_side(lane, 1, s_win, frames, side);
-                __syncwarp();
+#pragma unroll 1
+                for (int ph = 0; ph < 2; ++ph) {      // rolled: one copy of the column code for both side phases
+                    inv_stage_passB_side(lane, ph, s_win, frames, side);
+                    __syncwarp();
+                }
             }
             const bool write = g >= g0;
             inv_stage_emit_main(lane, tl.t0, P.T_use, P.out_len, write, s_win, out, acc);
@@ -230,7 +234,8 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_inverse: current device differs from the context's device");
     static thread_local int configured_dev = -1;
     if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
         configured_dev = dev;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -240,19 +245,27 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
                                                       ctx->d_tri_ipiv, ctx->d_tri_sup, a.work, a.work_stride);
         CUDA_TRY(cudaGetLastError());
     }
-    // chunking: enough (utterance, chunk) items to keep every resident warp busy for ~3 rounds, but chunks of
-    // >= 8 groups so that the one warm-up group per chunk stays a small overhead
+    // chunking: a warp streams through one (utterance, chunk) item at a time; every chunk but the first pays one
+    // recomputed warm-up group, and the launch ends when the warp with the most items finishes.  Pick the chunk count
+    // that minimises  rounds x (groups per chunk + warm-up)  with rounds = ceil(items / resident warps).
     const long long n_warps = 2LL * ctx->num_sms * INV_WARPS;
-    long long chunks = (3 * n_warps + a.B - 1) / a.B;
-    const long long max_chunks = P.G / 8 > 0 ? P.G / 8 : 1;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    P.cg = (int)((P.G + chunks - 1) / chunks);
+    const long long max_chunks = P.G / 4 > 0 ? P.G / 4 : 1;   // chunks of >= 4 groups
+    long long best_cost = -1;
+    int best_cg = P.G;
+    for (long long c = 1; c <= max_chunks; ++c) {
+        const int cg = (int)((P.G + c - 1) / c);
+        const long long chunks = (P.G + cg - 1) / cg;
+        const long long rounds = ((long long)a.B * chunks + n_warps - 1) / n_warps;
+        const long long cost = rounds * (cg + (chunks > 1 ? 2 : 1));   // + warm-up group, + drain / partial group
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_cg = cg; }
+    }
+    P.cg = best_cg;
     P.chunks = (P.G + P.cg - 1) / P.cg;
     long long blocks = 2LL * ctx->num_sms;
     const long long need = ((long long)a.B * P.chunks + INV_WARPS - 1) / INV_WARPS;
     if (blocks > need) blocks = need;
-    avse_inverse_kernel<<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    if (a.phase) avse_inverse_kernel<true><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    else avse_inverse_kernel<false><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
