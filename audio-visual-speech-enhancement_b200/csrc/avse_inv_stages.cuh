@@ -55,6 +55,29 @@ AVSE_HD void inv_mark_nonzero(const cpx (&x)[16], float* frame_base) {
     if (ni) frame_base[FRAME_ZERO_F + 1] = 1.0f;
 }
 
+AVSE_HD int float_bits(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(x);
+#else
+    union { float f; int i; } u; u.f = x; return u.i;
+#endif
+}
+
+// Interior groups: the same flags from the RAW samples (3-input integer ORs of the float bit patterns, ~4x fewer
+// instructions than comparing the 32 windowed values).  w[n] != 0 for every n except n = 0 (periodic Hann), so the
+// windowed frame is all-zero iff every raw sample except the one at n = 0 (j = 0 of column n2 = 0) is zero.
+AVSE_HD void inv_mark_nonzero_raw(const float (&raw)[20], int n2, float* frame_base) {
+    int mid = 0;
+#pragma unroll
+    for (int j = 5; j < 16; ++j) mid |= float_bits(raw[j]);
+    const int r0 = n2 != 0 ? float_bits(raw[0]) : 0;     // frame A's n = 0 sample meets w[0] = 0
+    const int r4 = float_bits(raw[4]);                   // frame A: n = 160 + n2; frame B: n = n2 (its n = 0 sample in column 0)
+    const int a = mid | r0 | float_bits(raw[1]) | float_bits(raw[2]) | float_bits(raw[3]) | r4;
+    const int b = mid | (n2 != 0 ? r4 : 0) | float_bits(raw[16]) | float_bits(raw[17]) | float_bits(raw[18]) | float_bits(raw[19]);
+    if ((a & 0x7fffffff) != 0) frame_base[FRAME_ZERO_F] = 1.0f;
+    if ((b & 0x7fffffff) != 0) frame_base[FRAME_ZERO_F + 1] = 1.0f;
+}
+
 // ---------------------------------------------------------------------------------------
 // pass 1: complex FFT f packs mixture frames tA = t0 + 2f (real part) and tA + 1 (imaginary part);
 // the second is the first shifted by 4 strides of 40 samples, so one batch of 20 loads serves both.
@@ -76,6 +99,7 @@ AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win2, c
             for (int j = 0; j < 20; ++j) raw[j] = p[N2 * j];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j], raw[j + 4]);
+            inv_mark_nonzero_raw(raw, n2, frames + f * FRAME_F);
         } else {
             // frames beyond the last one are clamped (their coefficients are zero, so they contribute nothing);
             // reflection breaks the shift relation: load both frames explicitly
@@ -88,7 +112,7 @@ AVSE_HD void inv_stage_pass1(const InvTile& tl, int lane, const float* s_win2, c
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = cmul_pp(x[j], cload(s_win2 + 2 * (N2 * j + n2)));
-        inv_mark_nonzero(x, frames + f * FRAME_F);
+        if (!interior) inv_mark_nonzero(x, frames + f * FRAME_F);
         pass1_column(x, f, n2, s_tw, frames);
     }
 }
@@ -264,14 +288,22 @@ AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win2) {
 AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, float* out,
                                  float (&acc)[INV_SIDE_ROWS]) {
     if (write) {
-        const bool interior = t0 >= 3 && t0 + 3 < T_use;   // every row has its 4 frames
+        // hot case: every row has its 4 frames and lies inside the trimmed output -> straight-line stores, no cold code
+        // in the instruction stream (the per-row edge branches showed up as instruction-fetch stalls in ncu)
+        const bool interior = t0 >= 3 && t0 + 3 < T_use && t0 * HOP - HALF >= 0 && t0 * HOP + N2 * 15 + 31 - HALF < out_len;
+        if (interior) {
+            float* o = out + (t0 * HOP - HALF + lane);
 #pragma unroll
-        for (int J = 0; J < 16; ++J) {
-            const int P = t0 * HOP + N2 * J + lane;
-            const int o = P - HALF;
-            if (o >= 0 && o < out_len) {
-                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win2);
-                out[o] = acc[J] * rw;
+            for (int J = 0; J < 16; ++J) o[N2 * J] = acc[J] * (1.0f / 1.5f);
+        } else {
+#pragma unroll 1
+            for (int J = 0; J < 16; ++J) {
+                const int P = t0 * HOP + N2 * J + lane;
+                const int o = P - HALF;
+                float a = acc[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) a = J == q ? acc[q] : a;      // register select (rolled cold loop)
+                if (o >= 0 && o < out_len) out[o] = a * inv_wss_recip(P, T_use, s_win2);
             }
         }
     }
@@ -291,14 +323,17 @@ AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool 
         carry[e] = (J + 16 < INV_SIDE_ROWS) ? side[(J + 16) * 8 + 4 * hf + e] : 0.0f;
     }
     if (write) {
-        const bool interior = t0 >= 3 && t0 + 3 < T_use;
+        const bool interior = t0 >= 3 && t0 + 3 < T_use && t0 * HOP - HALF >= 0 && t0 * HOP + N2 * 15 + 39 - HALF < out_len;
+        const int P0 = t0 * HOP + N2 * J + 32 + 4 * hf;
+        if (interior) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int P = t0 * HOP + N2 * J + 32 + 4 * hf + e;
-            const int o = P - HALF;
-            if (o >= 0 && o < out_len) {
-                const float rw = interior ? (1.0f / 1.5f) : inv_wss_recip(P, T_use, s_win2);
-                out[o] = keep[e] * rw;
+            for (int e = 0; e < 4; ++e) out[P0 - HALF + e] = keep[e] * (1.0f / 1.5f);
+        } else {
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+                const int o = P0 + e - HALF;
+                const float k = e == 0 ? keep[0] : (e == 1 ? keep[1] : (e == 2 ? keep[2] : keep[3]));
+                if (o >= 0 && o < out_len) out[o] = k * inv_wss_recip(P0 + e, T_use, s_win2);
             }
         }
     }

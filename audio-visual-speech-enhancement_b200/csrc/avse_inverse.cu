@@ -146,11 +146,28 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
         for (int g = g_first; g <= g_last; ++g) {
             tl.t0 = g * INV_FPG;
             if (tl.t0 < P.T_use) {
-                // coefficients of the 4 frames -> ybuf[band][4]
-                for (int m = lane; m < NMEL; m += 32)
-                    *reinterpret_cast<float4*>(ybuf + 4 * m) = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0);
+                // coefficients of the 4 frames -> ybuf[band][4]: loaded now, stored after pass 1 so that their latency is
+                // covered by pass 1 instead of stalling the warp at the top of the group
+                float4 cf[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int m = lane + 32 * q;
+                    if (m < NMEL) cf[q] = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0);
+                }
                 if (!EXT) {
+                    // L2 prefetch of the mixture samples first touched by the next group (one 128-byte line per lane)
+                    if (g < g_last) {
+                        const int i0 = (((tl.t0 + INV_FPG) * HOP + HALF - HOP) & ~31) + 32 * lane;
+                        if (lane < 22 && i0 < tl.valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(tl.pcm + i0));
+                    }
                     inv_stage_pass1(tl, lane, s_win, s_tw, frames);
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int m = lane + 32 * q;
+                    if (m < NMEL) *reinterpret_cast<float4*>(ybuf + 4 * m) = cf[q];
+                }
+                if (!EXT) {
                     __syncwarp();
                     {
                         cpx x[40];
