@@ -191,41 +191,64 @@ AVSE_HD void p4_pass2_store(int lane, int r, float* frames, const cpx (&x)[40]) 
 // of earlier emissions of the lane (both locations were consumed by this lane in an earlier iteration).
 // The two sums left at the end go to the flush area.  s_w: [SCAN4_BINS] (wa, wb).
 // ---------------------------------------------------------------------------------------
-AVSE_HD void stage4_scan(int lane, float factor, const vec2* s_w, unsigned mask_lo, unsigned mask_hi, float* frames) {
+AVSE_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+
+// One bin of the scan.  n' = Z_k - conj Z_{N-k} = i N' has the same magnitude as N', and the mixture follows from
+// M' = S' + factor N' = S' + factor (n'_im, -n'_re): bit-identical to forming N' first, with one packed op less.
+AVSE_HD void scan4_bin(const float* za, const float* zc, const vec4* tab, int j, bool emit, float factor, float nfactor,
+                       float*& esn, float*& em, cpx& Asn, cpx& Bsn, float& Am, float& Bm) {
+    const cpx a = cload(za + 2 * j);
+    const cpx c = cload(zc - 2 * j);
+    const vec4 w = tab[j];                                                // (wa, wa, wb, wb)
+    if (emit) {
+        cstore(esn, Asn);
+        *em = Am;
+        esn += 2;
+        em -= 1;
+        Asn = Bsn; Am = Bm;
+        Bsn = cmake(0.0f, 0.0f); Bm = 0.0f;
+    }
+    const cpx s = cfma_pp(c, cmake(1.0f, -1.0f), a);                      // 2 X_speech[k] = Z_k + conj Z_{N-k}
+    const cpx n = cfma_pp(c, cmake(-1.0f, 1.0f), a);                      // 2 i X_noise[k] = Z_k - conj Z_{N-k}
+    const float mr = fma_rn(factor, cim(n), cre(s));                      // 2 X_mixed[k]
+    const float mi = fma_rn(nfactor, cre(n), cim(s));
+    const float ms = fast_sqrt(fma_rn(cim(s), cim(s), cre(s) * cre(s)));
+    const float mn = fast_sqrt(fma_rn(cim(n), cim(n), cre(n) * cre(n)));
+    const float mm = fast_sqrt(fma_rn(mi, mi, mr * mr));
+    const cpx msn = cmake(ms, mn);
+    Asn = cfma_pp(msn, cmake(w.x, w.y), Asn);
+    Bsn = cfma_pp(msn, cmake(w.z, w.w), Bsn);
+    Am = fma_rn(w.x, mm, Am);
+    Bm = fma_rn(w.z, mm, Bm);
+}
+
+// s_w4: [SCAN4_BINS] (wa, wa, wb, wb).  Blocks of 8 bins with compile-time mask bit positions (the mask is shifted
+// once per block), so the emission test is a single predicate-setting logic op per bin.
+AVSE_HD void stage4_scan(int lane, float factor, const vec4* s_w4, unsigned mask_lo, unsigned mask_hi, float* frames) {
     const int f = lane >> 3, p = lane & 7;
     float* fr = frames + f * FRAME4_F;
     const float* za = fr + 2 * CHUNK4 * p;            // slot k      = za + 2 i
     const float* zc = fr + 2 * (NFFT - CHUNK4 * p);   // slot 640-k  = zc - 2 i
-    const vec2* tab = s_w + CHUNK4 * p;
+    const vec4* tab = s_w4 + CHUNK4 * p;
     float* esn = fr + 2 * CHUNK4 * p;                 // next (speech, noise) emission slot
     float* em = fr + 2 * (NFFT - CHUNK4 * p) + 1;     // next mixture emission float
-    float As = 0.0f, An = 0.0f, Am = 0.0f, Bs = 0.0f, Bn = 0.0f, Bm = 0.0f;
-    AVSE_UNROLL_N_(AVSE_SCAN4_UNROLL)
-    for (int i = 0; i < CHUNK4; ++i) {
-        const cpx a = cload(za + 2 * i);
-        const cpx c = cload(zc - 2 * i);
-        const vec2 w = tab[i];
-        const bool emit = i < 32 ? ((mask_lo >> i) & 1u) != 0u : ((mask_hi >> (i - 32)) & 1u) != 0u;
-        if (emit) {
-            cstore(esn, cmake(As, An));
-            *em = Am;
-            esn += 2;
-            em -= 1;
-            As = Bs; An = Bn; Am = Bm;
-            Bs = 0.0f; Bn = 0.0f; Bm = 0.0f;
-        }
-        const cpx s = cfma_pp(c, cmake(1.0f, -1.0f), a);                 // 2 X_speech[k] = Z_k + conj Z_{N-k}
-        const cpx n = cmake(cim(a) + cim(c), cre(c) - cre(a));           // 2 X_noise[k]  = (Z_k - conj Z_{N-k}) / i
-        const cpx m = cfma_s(n, factor, s);                              // 2 X_mixed[k]
-        const float ms = fast_sqrt(cre(s) * cre(s) + cim(s) * cim(s));
-        const float mn = fast_sqrt(cre(n) * cre(n) + cim(n) * cim(n));
-        const float mm = fast_sqrt(cre(m) * cre(m) + cim(m) * cim(m));
-        As += w.x * ms; An += w.x * mn; Am += w.x * mm;
-        Bs += w.y * ms; Bn += w.y * mn; Bm += w.y * mm;
+    cpx Asn = cmake(0.0f, 0.0f), Bsn = cmake(0.0f, 0.0f);
+    float Am = 0.0f, Bm = 0.0f;
+    const float nfactor = -factor;
+    unsigned mlo = mask_lo, mhi = mask_hi;
+    static_assert(CHUNK4 == 41, "5 blocks of 8 bins + 1");
+#pragma unroll 1
+    for (int ib = 0; ib < 40; ib += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scan4_bin(za, zc, tab, j, ((mlo >> j) & 1u) != 0u, factor, nfactor, esn, em, Asn, Bsn, Am, Bm);
+        za += 16; zc -= 16; tab += 8;
+        mlo = (mlo >> 8) | (mhi << 24);
+        mhi >>= 8;
     }
+    scan4_bin(za, zc, tab, 0, (mlo & 1u) != 0u, factor, nfactor, esn, em, Asn, Bsn, Am, Bm);
     float* fl = fr + FLUSH4_F + 6 * p;
-    cstore(fl + 0, cmake(As, An));
-    cstore(fl + 2, cmake(Bs, Bn));
+    cstore(fl + 0, Asn);
+    cstore(fl + 2, Bsn);
     cstore(fl + 4, cmake(Am, Bm));
 }
 
