@@ -381,6 +381,82 @@ class SpectralEngine(object):
         return tuple(outs[:2]) + (permutation,) + tuple(outs[2:])
 
 
+class HostPipeline(object):
+    """preprocess_audio_pair (dp:119-139) for a HOST-resident batch: pinned host waveforms in, pinned host slices out.
+
+    The reference's driver hands every (speech, noise) pair to a pool worker and gets numpy arrays back (dp:189-198).
+    Here the batch is cut into chunks of `chunk` utterances that go round-robin through `n_streams` CUDA streams, each
+    with its own device staging slot: host->device copy, SNR factor + fused forward + floor kernels, device->host copy.
+    Copies of one chunk overlap the kernels and copies of its neighbours, consecutive submit() calls keep the ring
+    going (no barrier between batches), and nothing synchronises with the host until synchronize()."""
+
+    def __init__(self, engine, L, n_video_slices, chunk=125, n_streams=3):
+        self.eng = engine
+        self.L = int(L)
+        self.n_video_slices = int(n_video_slices)
+        self.n_slices = min(self.n_video_slices, engine.n_frames(self.L) // SPSS)
+        self.chunk = int(chunk)
+        dev = engine.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        self.slots = []
+        for _ in range(n_streams):
+            self.slots.append({
+                "s": torch.empty((self.chunk, self.L), dtype=torch.float32, device=dev),
+                "n": torch.empty((self.chunk, self.L), dtype=torch.float32, device=dev),
+                "snr": torch.zeros((self.chunk,), dtype=torch.float32, device=dev),
+                "out": {},
+            })
+        self._next = 0
+        self.launches = 0
+
+    def begin_after(self, stream):
+        """Order all pipeline streams after the work already queued on `stream` (e.g. a timing event)."""
+        for st in self.streams:
+            st.wait_stream(stream)
+
+    def join(self, stream):
+        """Make `stream` wait for everything submitted so far."""
+        for st in self.streams:
+            stream.wait_stream(st)
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()
+
+    def submit(self, h_speech, h_noise, h_mixed, h_speech_out, h_noise_out, h_pcm, snr_db=None):
+        """Queue one batch.  h_speech / h_noise: pinned [B, L] float32 (noise fitted to the speech length, dp:125-128);
+        h_mixed / h_speech_out / h_noise_out: pinned [B, n_slices, 80, 20]; h_pcm: pinned [B, L]; snr_db: optional
+        pinned [B] float32 (None: 0 dB, dp:130).  Returns the number of chunks queued."""
+        B = h_speech.shape[0]
+        eng = self.eng
+        n_chunks = 0
+        for lo in range(0, B, self.chunk):
+            hi = min(B, lo + self.chunk)
+            k = self._next % len(self.streams)
+            self._next += 1
+            slot, st = self.slots[k], self.streams[k]
+            m = hi - lo
+            with torch.cuda.stream(st):
+                d_s, d_n = slot["s"][:m], slot["n"][:m]
+                d_s.copy_(h_speech[lo:hi], non_blocking=True)
+                d_n.copy_(h_noise[lo:hi], non_blocking=True)
+                snr = None
+                if snr_db is not None:
+                    snr = slot["snr"][:m]
+                    snr.copy_(snr_db[lo:hi], non_blocking=True)
+                out = slot["out"] if m == self.chunk else {}
+                factor, keys = eng.snr_factor(d_s, d_n, snr_db=snr, max_key=out.get("max_key"))
+                r = eng.forward_raw(d_s, d_n, L=self.L, factor=factor, n_slices=self.n_slices, max_key=keys, out=out)
+                eng.floor3_(r["speech"], r["noise"], r["mixed"], keys)
+                h_mixed[lo:hi].copy_(r["mixed"], non_blocking=True)
+                h_speech_out[lo:hi].copy_(r["speech"], non_blocking=True)
+                h_noise_out[lo:hi].copy_(r["noise"], non_blocking=True)
+                h_pcm[lo:hi].copy_(r["mixed_pcm"], non_blocking=True)
+            self.launches += 3
+            n_chunks += 1
+        return n_chunks
+
+
 def shard_range(n_utterances, rank, world_size):
     """Contiguous utterance range [lo, hi) owned by `rank`: utterances are independent units, ranks own
     disjoint ranges and no collective is needed on the data path.  Sizes differ by at most one."""

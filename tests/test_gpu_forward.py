@@ -209,3 +209,25 @@ def test_data_processor_signatures(dp):
     rmag, rphase = O.signal_to_spectrogram(O.AudioSignal(s.astype(np.float64), SR), 640, 160)
     assert mag.shape == (80, 101) and phase.shape == (321, 101)
     assert np.max(np.abs(mag - rmag)) <= TOL_DB
+
+
+def test_host_pipeline_equals_device_batch(eng):
+    # engine.HostPipeline (pinned host in/out, chunked over streams, ragged last chunk, two batches back to back)
+    # must reproduce preprocess_pairs on the same data bit for bit
+    mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+    B, L, nvs = 11, 16000, 5
+    g = torch.Generator().manual_seed(3)
+    hs = (torch.randn((B, L), generator=g) * 0.1).pin_memory()
+    hn = (torch.randn((B, L), generator=g) * 0.05).pin_memory()
+    snr = torch.tensor([-10.0, -5.0, 0.0, 5.0, 10.0, 0.0, 3.0, -3.0, 1.0, 2.0, 7.0]).pin_memory()
+    pipe = mod.HostPipeline(eng, L, nvs, chunk=4, n_streams=2)
+    outs = [[torch.zeros((B, 5, 80, 20)).pin_memory() for _ in range(3)] + [torch.zeros((B, L)).pin_memory()] for _ in range(2)]
+    pipe.begin_after(torch.cuda.current_stream())
+    assert pipe.submit(hs, hn, *outs[0], snr_db=snr) == 3
+    pipe.submit(hn, hs, *outs[1])            # second batch right behind the first (roles swapped, 0 dB)
+    pipe.synchronize()
+    ref0 = eng.preprocess_pairs(hs.cuda(), hn.cuda(), nvs, snr_db=snr.cuda())
+    ref1 = eng.preprocess_pairs(hn.cuda(), hs.cuda(), nvs)
+    for got, ref in ((outs[0], ref0), (outs[1], ref1)):
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b.cpu())
