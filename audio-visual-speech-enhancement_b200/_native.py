@@ -25,6 +25,7 @@ class ForwardArgs(_c.Structure):
         ("max_key", _c.c_void_p),
         ("stft_speech", _c.c_void_p),
         ("min_key", _c.c_void_p),
+        ("sample_format", _c.c_int),
     ]
 
 
@@ -37,6 +38,7 @@ class InverseArgs(_c.Structure):
         ("out_pcm", _c.c_void_p), ("out_stride", _c.c_longlong),
         ("work", _c.c_void_p), ("work_stride", _c.c_longlong),
         ("phase", _c.c_void_p), ("phase_stride", _c.c_longlong), ("phase_frames", _c.c_int),
+        ("out_format", _c.c_int),
     ]
 
 
@@ -69,7 +71,7 @@ def load(build=True):
     lib.avse_version.restype = _c.c_char_p
     lib.avse_get_filterbank.argtypes = [vp, vp]
     lib.avse_get_filterbank.restype = i32
-    lib.avse_snr_factor.argtypes = [vp, vp, vp, ll, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.avse_snr_factor.argtypes = [vp, vp, vp, i32, ll, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.avse_snr_factor.restype = i32
     lib.avse_forward.argtypes = [vp, _c.POINTER(ForwardArgs), vp]
     lib.avse_forward.restype = i32

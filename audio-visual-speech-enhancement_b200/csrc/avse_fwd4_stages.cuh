@@ -49,7 +49,8 @@ AVSE_HD void lane4_const_init(int lane, const float* s_win, const vec2* s_tw, La
 }
 
 // A group is "interior" when its four frames exist and need neither reflection nor zero padding.
-AVSE_HD bool group4_interior(const FwdTile& tl) {
+template <typename S>
+AVSE_HD bool group4_interior(const FwdTileT<S>& tl) {
     return tl.nz != nullptr && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.vmin && tl.t0 + 3 < tl.T;
 }
 
@@ -62,17 +63,19 @@ AVSE_HD void p4_column(cpx (&x)[16], const vec2 (&tw)[16], float* dst) {
 }
 
 // The 28 strided samples per signal that the lane's column needs for the four frames (interior groups).
-AVSE_HD void p4_load_raw(const FwdTile& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
+template <typename S>
+AVSE_HD void p4_load_raw(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
     const int o = tl.t0 * HOP - HALF + lane;
-    const float* ps = tl.sp + o;
-    const float* pn = tl.nz + o;
+    const S* ps = tl.sp + o;
+    const S* pn = tl.nz + o;
 #pragma unroll
-    for (int j = 0; j < RAW4; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+    for (int j = 0; j < RAW4; ++j) { rs[j] = (float)ps[N2 * j]; rn[j] = (float)pn[N2 * j]; }
 }
 
 // Rounds 0..3 of an interior group: frame f, column n2 = lane.  Also stores the mixture PCM (dp:133) of the
 // group's own four hops (strides 8..23 of the batch) for the residues n2 < 32.
-AVSE_HD void stage4_pass1_main(const FwdTile& tl, int lane, const float (&rs)[RAW4], const float (&rn)[RAW4],
+template <typename S>
+AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs)[RAW4], const float (&rn)[RAW4],
                                const Lane4Const& lc, float* frames) {
     if (tl.mixed_pcm != nullptr) {
         float* pm = tl.mixed_pcm + tl.t0 * HOP + lane;
@@ -90,16 +93,18 @@ AVSE_HD void stage4_pass1_main(const FwdTile& tl, int lane, const float (&rs)[RA
 
 // Round 4 of an interior group: lane = (f = lane / 8, r = lane % 8), column n2 = 32 + r of frame f.
 // Window / twiddles come from the CTA's shared tables (8 distinct addresses per load: one wavefront).
-AVSE_HD void p4_load_tail_raw(const FwdTile& tl, int lane, float (&rs)[16], float (&rn)[16]) {
+template <typename S>
+AVSE_HD void p4_load_tail_raw(const FwdTileT<S>& tl, int lane, float (&rs)[16], float (&rn)[16]) {
     const int f = lane >> 3, n2 = 32 + (lane & 7);
     const int o = (tl.t0 + f) * HOP - HALF + n2;
-    const float* ps = tl.sp + o;
-    const float* pn = tl.nz + o;
+    const S* ps = tl.sp + o;
+    const S* pn = tl.nz + o;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { rs[j] = ps[N2 * j]; rn[j] = pn[N2 * j]; }
+    for (int j = 0; j < 16; ++j) { rs[j] = (float)ps[N2 * j]; rn[j] = (float)pn[N2 * j]; }
 }
 
-AVSE_HD void stage4_pass1_tail_compute(const FwdTile& tl, int lane, const float (&rs)[16], const float (&rn)[16], const float* s_win,
+template <typename S>
+AVSE_HD void stage4_pass1_tail_compute(const FwdTileT<S>& tl, int lane, const float (&rs)[16], const float (&rn)[16], const float* s_win,
                                        const vec2* s_tw, float* frames) {
     const int f = lane >> 3, n2 = 32 + (lane & 7);
     vec2 tw[16];
@@ -117,7 +122,8 @@ AVSE_HD void stage4_pass1_tail_compute(const FwdTile& tl, int lane, const float 
     p4_column(x, tw, frames + f * FRAME4_F + 2 * n2);
 }
 
-AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+template <typename S>
+AVSE_HD void stage4_pass1_tail(const FwdTileT<S>& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
     float rs[16], rn[16];
     p4_load_tail_raw(tl, lane, rs, rn);
     stage4_pass1_tail_compute(tl, lane, rs, rn, s_win, s_tw, frames);
@@ -125,7 +131,8 @@ AVSE_HD void stage4_pass1_tail(const FwdTile& tl, int lane, const float* s_win, 
 
 // Edge / generic groups (first and last frames of an utterance, short or zero-padded signals): every sample
 // goes through the reflect + zero-pad loader.  Cold code, rolled over the five rounds.
-AVSE_HD void stage4_pass1_edge(const FwdTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+template <typename S>
+AVSE_HD void stage4_pass1_edge(const FwdTileT<S>& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
 #pragma unroll 1
     for (int round = 0; round < 5; ++round) {
         const int f = round < 4 ? round : lane >> 3;

@@ -83,9 +83,11 @@ struct FwdTables {
 };
 
 // One group of FPG frames of one utterance.
-struct FwdTile {
-    const float* sp;     // speech samples of this utterance
-    const float* nz;     // noise samples (already fitted to the speech length), may be nullptr
+// S: sample type in HBM (float, or short for raw int16 WAV samples, dp:122-123: the decode is fused into the loads)
+template <typename S>
+struct FwdTileT {
+    const S* sp;         // speech samples of this utterance
+    const S* nz;         // noise samples (already fitted to the speech length), may be nullptr
     int L;               // signal length after pad/truncate (dp:37-42); reflect domain
     int valid_s;         // samples present in sp (zeros beyond, dp:40)
     int valid_n;         // samples present in nz
@@ -95,13 +97,15 @@ struct FwdTile {
     float factor;        // SNR factor (dp:130); 0 when nz == nullptr
     float* mixed_pcm;    // [L] or nullptr: s + f*n (dp:133), zero-padded / truncated to L
 };
+using FwdTile = FwdTileT<float>;
 
-AVSE_HD float load_sample_edge(const float* p, int i, int L, int valid) {
+template <typename S>
+AVSE_HD float load_sample_edge(const S* p, int i, int L, int valid) {
     // np.pad(y, n_fft//2, mode='reflect') on the length-L (zero padded) signal
     i = i < 0 ? -i : i;
     i = i >= L ? 2 * (L - 1) - i : i;
     i = i < 0 ? 0 : i;
-    return (p != nullptr && i < valid) ? p[i] : 0.0f;
+    return (p != nullptr && i < valid) ? (float)p[i] : 0.0f;
 }
 
 // A group is "interior" when both of its frames exist and all their samples are present in both

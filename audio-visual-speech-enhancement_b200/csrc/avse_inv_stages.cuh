@@ -269,6 +269,14 @@ AVSE_HD void inv_stage_passB_side(int lane, int ph, const float* s_win2, const f
     for (int j = 0; j < 20; ++j) side[(j + 8 * f) * 8 + r] += c[j];
 }
 
+// Last store of the path: float32 PCM, or int16 like AudioSignal.save_to_wav_file (se:176-177):
+// np.clip(x, -32768, 32767).astype(int16), i.e. clip then truncate toward zero.
+AVSE_HD void store_pcm(float* p, float v) { *p = v; }
+AVSE_HD void store_pcm(short* p, float v) {
+    v = v < -32768.0f ? -32768.0f : (v > 32767.0f ? 32767.0f : v);
+    *p = (short)(int)v;      // C conversion truncates toward zero like numpy's astype
+}
+
 // librosa.istft window sum-square at padded position P for T_use frames (Appendix A.1): sum over the
 // (<= 4) frames t = P/160 - q that exist.  Interior value is exactly 1.5 for the periodic Hann at hop N/4.
 AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win2) {
@@ -285,16 +293,17 @@ AVSE_HD float inv_wss_recip(int P, int T_use, const float* s_win2) {
 
 // Emit the 4 finished hops of the group (rows J = 0..15) and rotate the overlap-add state.
 // out: trimmed PCM of this utterance (index o = P - 320), out_len = 160 (T_use - 1).
-AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, float* out,
+template <typename O>
+AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, O* out,
                                  float (&acc)[INV_SIDE_ROWS]) {
     if (write) {
         // hot case: every row has its 4 frames and lies inside the trimmed output -> straight-line stores, no cold code
         // in the instruction stream (the per-row edge branches showed up as instruction-fetch stalls in ncu)
         const bool interior = t0 >= 3 && t0 + 3 < T_use && t0 * HOP - HALF >= 0 && t0 * HOP + N2 * 15 + 31 - HALF < out_len;
         if (interior) {
-            float* o = out + (t0 * HOP - HALF + lane);
+            O* o = out + (t0 * HOP - HALF + lane);
 #pragma unroll
-            for (int J = 0; J < 16; ++J) o[N2 * J] = acc[J] * (1.0f / 1.5f);
+            for (int J = 0; J < 16; ++J) store_pcm(o + N2 * J, acc[J] * (1.0f / 1.5f));
         } else {
 #pragma unroll 1
             for (int J = 0; J < 16; ++J) {
@@ -303,7 +312,7 @@ AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool 
                 float a = acc[0];
 #pragma unroll
                 for (int q = 1; q < 16; ++q) a = J == q ? acc[q] : a;      // register select (rolled cold loop)
-                if (o >= 0 && o < out_len) out[o] = a * inv_wss_recip(P, T_use, s_win2);
+                if (o >= 0 && o < out_len) store_pcm(out + o, a * inv_wss_recip(P, T_use, s_win2));
             }
         }
     }
@@ -314,7 +323,8 @@ AVSE_HD void inv_stage_emit_main(int lane, int t0, int T_use, int out_len, bool 
 }
 
 // side buffer: lane = (row J = lane/2, half = lane%2): 4 samples each, then rotate rows.
-AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, float* out,
+template <typename O>
+AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool write, const float* s_win2, O* out,
                                  const float* side, float (&keep)[4], float (&carry)[4]) {
     const int J = lane >> 1, hf = lane & 1;
 #pragma unroll
@@ -327,13 +337,13 @@ AVSE_HD void inv_stage_emit_side(int lane, int t0, int T_use, int out_len, bool 
         const int P0 = t0 * HOP + N2 * J + 32 + 4 * hf;
         if (interior) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) out[P0 - HALF + e] = keep[e] * (1.0f / 1.5f);
+            for (int e = 0; e < 4; ++e) store_pcm(out + (P0 - HALF + e), keep[e] * (1.0f / 1.5f));
         } else {
 #pragma unroll 1
             for (int e = 0; e < 4; ++e) {
                 const int o = P0 + e - HALF;
                 const float k = e == 0 ? keep[0] : (e == 1 ? keep[1] : (e == 2 ? keep[2] : keep[3]));
-                if (o >= 0 && o < out_len) out[o] = k * inv_wss_recip(P0 + e, T_use, s_win2);
+                if (o >= 0 && o < out_len) store_pcm(out + o, k * inv_wss_recip(P0 + e, T_use, s_win2));
             }
         }
     }

@@ -82,7 +82,7 @@ struct InvParams {
 
 // EXT: explicit phase array (dp:99 signature) instead of the recomputed mixture STFT; a separate instantiation keeps each
 // kernel's code (instruction-cache footprint) small.
-template <bool EXT>
+template <bool EXT, typename O>
 __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __grid_constant__ InvParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
         tl.T = P.T;
         tl.T_use = P.T_use;
         const float* ycoef = A.work + (size_t)u * A.work_stride;
-        float* out = A.out_pcm + (size_t)u * A.out_stride;
+        O* out = static_cast<O*>(A.out_pcm) + (size_t)u * A.out_stride;
 
         float acc[INV_SIDE_ROWS];
 #pragma unroll
@@ -225,6 +225,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (!a.mel_db || (!a.mixed_pcm && !a.phase) || !a.out_pcm || !a.work) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
     if (a.B <= 0 || (!a.phase && a.L <= HALF)) return avse_fail(AVSE_E_ARG, "avse_inverse: need B > 0 and L > 320");
     if (a.layout != AVSE_LAYOUT_SLICES && a.layout != AVSE_LAYOUT_SPEC) return avse_fail(AVSE_E_ARG, "avse_inverse: bad layout");
+    if (a.out_format != AVSE_SAMPLE_F32 && a.out_format != AVSE_SAMPLE_I16) return avse_fail(AVSE_E_ARG, "avse_inverse: bad out_format");
     InvParams P;
     P.a = a;
     P.T = a.phase ? a.phase_frames : 1 + a.L / HOP;
@@ -251,8 +252,10 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_inverse: current device differs from the context's device");
     static thread_local int configured_dev = -1;
     if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<false, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
         configured_dev = dev;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -281,8 +284,14 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     long long blocks = 2LL * ctx->num_sms;
     const long long need = ((long long)a.B * P.chunks + INV_WARPS - 1) / INV_WARPS;
     if (blocks > need) blocks = need;
-    if (a.phase) avse_inverse_kernel<true><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
-    else avse_inverse_kernel<false><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    const bool o16 = a.out_format == AVSE_SAMPLE_I16;
+    if (a.phase) {
+        if (o16) avse_inverse_kernel<true, short><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+        else avse_inverse_kernel<true, float><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    } else {
+        if (o16) avse_inverse_kernel<false, short><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+        else avse_inverse_kernel<false, float><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

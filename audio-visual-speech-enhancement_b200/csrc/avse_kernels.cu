@@ -118,26 +118,43 @@ extern "C" int avse_get_filterbank(const avse_ctx* ctx, double* host_out) {
 // ---------------------------------------------------------------------------------------------
 // SNR factor (dp:130) -- one CTA per utterance, float64 accumulation
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) avse_snr_factor_kernel(const float* __restrict__ speech, const float* __restrict__ noise,
+template <typename S> struct Sample4;
+template <> struct Sample4<float> {
+    typedef float4 vec;
+    static __device__ __forceinline__ void load(const float* p, int i, float (&v)[4]) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct Sample4<short> {
+    typedef short4 vec;
+    static __device__ __forceinline__ void load(const short* p, int i, float (&v)[4]) {
+        const short4 t = __ldg(reinterpret_cast<const short4*>(p) + i); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restrict__ speech, const S* __restrict__ noise,
                                                               long long stride, const int* __restrict__ lengths, int L,
                                                               const float* __restrict__ snr_db, float* __restrict__ factor_out,
                                                               int* __restrict__ max_key, int* __restrict__ min_key) {
     const int u = blockIdx.x;
     const int n = lengths ? lengths[u] : L;
-    const float* s = speech + (size_t)u * stride;
-    const float* z = noise + (size_t)u * stride;
+    const S* s = speech + (size_t)u * stride;
+    const S* z = noise + (size_t)u * stride;
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    const int n4 = ((((size_t)s | (size_t)z) & 15) == 0) ? (n >> 2) : 0;
+    constexpr size_t AL = sizeof(typename Sample4<S>::vec) - 1;
+    const int n4 = ((((size_t)s | (size_t)z) & AL) == 0) ? (n >> 2) : 0;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(s) + i);
-        const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
-        a0 += (double)sv.x + (double)sv.y + (double)sv.z + (double)sv.w;
-        a1 += (double)sv.x * sv.x + (double)sv.y * sv.y + (double)sv.z * sv.z + (double)sv.w * sv.w;
-        b0 += (double)zv.x + (double)zv.y + (double)zv.z + (double)zv.w;
-        b1 += (double)zv.x * zv.x + (double)zv.y * zv.y + (double)zv.z * zv.z + (double)zv.w * zv.w;
+        float sv[4], zv[4];
+        Sample4<S>::load(s, i, sv);
+        Sample4<S>::load(z, i, zv);
+        a0 += (double)sv[0] + (double)sv[1] + (double)sv[2] + (double)sv[3];
+        a1 += (double)sv[0] * sv[0] + (double)sv[1] * sv[1] + (double)sv[2] * sv[2] + (double)sv[3] * sv[3];
+        b0 += (double)zv[0] + (double)zv[1] + (double)zv[2] + (double)zv[3];
+        b1 += (double)zv[0] * zv[0] + (double)zv[1] * zv[1] + (double)zv[2] * zv[2] + (double)zv[3] * zv[3];
     }
     for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
-        const double sv = s[i], zv = z[i];
+        const double sv = (double)s[i], zv = (double)z[i];
         a0 += sv; a1 += sv * sv; b0 += zv; b1 += zv * zv;
     }
     __shared__ double red[4][8];
@@ -164,11 +181,18 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const float* __res
     }
 }
 
-extern "C" int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride, const int* lengths,
-                               int B, int L, const float* snr_db, float* factor_out, int* max_key, int* min_key, void* stream) {
+extern "C" int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* noise, int sample_format, long long stride,
+                               const int* lengths, int B, int L, const float* snr_db, float* factor_out, int* max_key, int* min_key,
+                               void* stream) {
     if (!ctx || !speech || !noise || !factor_out) return avse_fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
     if (B <= 0 || L <= 0 || stride < L) return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
-    avse_snr_factor_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
+    if (sample_format == AVSE_SAMPLE_F32)
+        avse_snr_factor_kernel<float><<<B, 256, 0, (cudaStream_t)stream>>>((const float*)speech, (const float*)noise, stride, lengths, L,
+                                                                            snr_db, factor_out, max_key, min_key);
+    else if (sample_format == AVSE_SAMPLE_I16)
+        avse_snr_factor_kernel<short><<<B, 256, 0, (cudaStream_t)stream>>>((const short*)speech, (const short*)noise, stride, lengths, L,
+                                                                            snr_db, factor_out, max_key, min_key);
+    else return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sample_format");
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -276,8 +300,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
             factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
         }
         FwdTile tl;
-        tl.sp = A.speech + (size_t)u * A.in_stride;
-        tl.nz = have_noise ? A.noise + (size_t)u * A.in_stride : nullptr;
+        tl.sp = static_cast<const float*>(A.speech) + (size_t)u * A.in_stride;
+        tl.nz = have_noise ? static_cast<const float*>(A.noise) + (size_t)u * A.in_stride : nullptr;
         tl.L = A.L;
         tl.valid_s = vs;
         tl.valid_n = vn;
@@ -363,9 +387,6 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
 // up to 255 registers per thread so that the pass-1 window / twiddle values stay in registers for the whole
 // kernel.  See avse_fwd4_stages.cuh for the stage functions and the reasoning.
 // ---------------------------------------------------------------------------------------------
-#ifndef AVSE_F4_SWP
-#define AVSE_F4_SWP 1
-#endif
 #ifndef AVSE_F4_PREFETCH
 #define AVSE_F4_PREFETCH 2
 #endif
@@ -384,6 +405,7 @@ constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
 static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 4) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
 
+template <typename S>
 __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,7 +440,9 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     mn[lane] = -neg_inf(); mn[32 + lane] = -neg_inf(); mn[64 + lane] = -neg_inf();
     float factor = 0.0f;
     int vs = 0, vn = 0;
-    bool fresh = true;
+    const S* in_speech = reinterpret_cast<const S*>(A.speech);
+    const S* in_noise = reinterpret_cast<const S*>(A.noise);
+    constexpr int LINE = 128 / (int)sizeof(S);        // samples per 128-byte line
 
     auto flush_max = [&](int uu) {
 #pragma unroll
@@ -446,16 +470,15 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
             if (g2 >= P.G) { g2 -= P.G; ++u2; }
             const int lo = g2 == 0 ? 0 : g2 * (F4 * HOP) + HOP;      // first sample not covered by group g2 - 1
             const int hi = g2 * (F4 * HOP) + (NFFT + HOP);           // window end of group g2 (exclusive)
-            const int i0 = (lo & ~31) + 32 * lane;                   // one 128-byte line per lane
+            const int i0 = (lo & ~(LINE - 1)) + LINE * lane;         // one 128-byte line per lane
             if (i0 < hi && i0 < A.L && i0 < A.in_stride && lane < 22) {
                 const size_t o = (size_t)u2 * A.in_stride + i0;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.speech + o));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noise + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_speech + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_noise + o));
             }
         }
 #endif
     };
-#if AVSE_F4_SWP
     // Software-pipelined tile loop: the raw samples of tile it+1 are loaded into registers before the dB stage of
     // tile it, so their HBM/L2 latency is covered by the dB arithmetic and stores instead of stalling pass 1.
     auto load_utt = [&](int uu, int& ovs, int& ovn, float& of) {
@@ -466,9 +489,9 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         of = A.factor ? A.factor[uu] : 1.0f;
     };
     auto make_tile = [&](int uu, int gg, int tvs, int tvn, float tf) {
-        FwdTile t;
-        t.sp = A.speech + (size_t)uu * A.in_stride;
-        t.nz = A.noise + (size_t)uu * A.in_stride;
+        FwdTileT<S> t;
+        t.sp = in_speech + (size_t)uu * A.in_stride;
+        t.nz = in_noise + (size_t)uu * A.in_stride;
         t.L = A.L;
         t.valid_s = tvs;
         t.valid_n = tvn;
@@ -480,7 +503,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         return t;
     };
     load_utt(u, vs, vn, factor);
-    FwdTile tl = make_tile(u, g, vs, vn, factor);
+    FwdTileT<S> tl = make_tile(u, g, vs, vn, factor);
     bool interior = group4_interior(tl);
     float rs[RAW4], rn[RAW4], ts[16], tn[16];
     if (interior) {
@@ -520,7 +543,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         const bool last_of_utt = g2 == P.G;
         const bool have_next = it + 1 < n_tiles;
         if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, vs2, vn2, factor2); }
-        FwdTile tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
+        FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
         const bool interior2 = have_next && group4_interior(tnx);
         if (interior2) {
             p4_load_raw(tnx, lane, rs, rn);
@@ -547,81 +570,6 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         interior = interior2;
     }
 }
-#else
-#pragma unroll 1
-    for (int it = 0; it < n_tiles; ++it) {
-        if (fresh) {
-            fresh = false;
-            vs = A.len_speech ? A.len_speech[u] : A.L;
-            vn = A.len_noise ? A.len_noise[u] : vs;
-            vs = vs < A.L ? vs : A.L;
-            vn = vn < A.L ? vn : A.L;
-            factor = A.factor ? A.factor[u] : 1.0f;
-        }
-        FwdTile tl;
-        tl.sp = A.speech + (size_t)u * A.in_stride;
-        tl.nz = A.noise + (size_t)u * A.in_stride;
-        tl.L = A.L;
-        tl.valid_s = vs;
-        tl.valid_n = vn;
-        tl.vmin = vs < vn ? vs : vn;
-        tl.T = P.T;
-        tl.t0 = g * F4;
-        tl.factor = factor;
-        tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
-
-        prefetch_ahead(it, u, g);
-        // ---- pass 1 ----
-        if (group4_interior(tl)) {
-            {
-                float rs[RAW4], rn[RAW4];
-                p4_load_raw(tl, lane, rs, rn);
-                stage4_pass1_main(tl, lane, rs, rn, lc, frames);
-            }
-            stage4_pass1_tail(tl, lane, s_win, s_tw, frames);
-        } else {
-            stage4_pass1_edge(tl, lane, s_win, s_tw, frames);
-        }
-        __syncwarp();
-
-        // ---- pass 2 ----
-#pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-            cpx x[40];
-            p4_pass2_compute(lane, r, frames, x);
-            __syncwarp();
-            p4_pass2_store(lane, r, frames, x);
-        }
-        __syncwarp();
-
-        // ---- unpack + mel scan ----
-        stage4_scan(lane, factor, s_scanw, mask_lo, mask_hi, frames);
-        __syncwarp();
-
-        // ---- dB + stores ----
-        {
-            FwdOut out;
-            out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
-            out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
-            out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
-            out.layout = A.layout;
-            out.n_slices = A.n_slices;
-            out.ld_t = A.ld_t;
-#pragma unroll 1
-            for (int q = 0; q < 3; ++q) stage4_db(lane, q, factor, s_loc, frames, out, g * F4, P.T, mx, mn);
-        }
-        __syncwarp();
-
-        if (++g == P.G) {
-            flush_max(u);
-            g = 0;
-            ++u;
-            fresh = true;
-        }
-    }
-    if (!fresh) flush_max(u);
-}
-#endif
 
 __global__ void avse_reset_max_kernel(int* __restrict__ max_key, int* __restrict__ min_key, int n, int min_value);
 
@@ -656,11 +604,15 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
     // F4 kernel: pair batches (noise present), standard 2-tap filterbank, no complex STFT output
-    const bool use_f4 = ctx->f4_tables && a.noise != nullptr && a.stft_speech == nullptr && !ctx->force_f2;
+    if (a.sample_format != AVSE_SAMPLE_F32 && a.sample_format != AVSE_SAMPLE_I16) return avse_fail(AVSE_E_ARG, "avse_forward: bad sample_format");
+    const bool i16 = a.sample_format == AVSE_SAMPLE_I16;
+    const bool use_f4 = ctx->f4_tables && a.noise != nullptr && a.stft_speech == nullptr && (!ctx->force_f2 || i16);
+    if (i16 && !use_f4) return avse_fail(AVSE_E_ARG, "avse_forward: int16 samples are supported for pair batches (noise != NULL, no stft_speech) with the standard 2-tap filterbank; convert to float32 first");
     if (use_f4) {
         static thread_local int configured4_dev = -1;
         if (configured4_dev != dev) {
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
             configured4_dev = dev;
         }
         P.G = (P.T + F4 - 1) / F4;
@@ -671,7 +623,8 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
         const long long nwarps4 = blocks4 * F4_WARPS;
         P.total_tiles = (int)total4;
         P.per_warp = (int)((total4 + nwarps4 - 1) / nwarps4);
-        avse_forward4_kernel<<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        if (i16) avse_forward4_kernel<short><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else avse_forward4_kernel<float><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

@@ -17,6 +17,7 @@ from ._native import ForwardArgs, InverseArgs, check
 
 N_FFT, HOP, N_BINS, N_MELS, SPSS = 640, 160, 321, 80, 20
 LAYOUT_SLICES, LAYOUT_SPEC = 0, 1
+SAMPLE_F32, SAMPLE_I16 = 0, 1
 
 
 def _ptr(t):
@@ -99,10 +100,11 @@ class SpectralEngine(object):
         check(self._lib.avse_get_filterbank(self._ctx, fb.ctypes.data), "avse_get_filterbank")
         return fb
 
-    def _as_batch(self, x):
+    def _as_batch(self, x, keep_int16=False):
+        """[B, n] contiguous-row view; float32, or raw int16 WAV samples when the kernel decodes them itself."""
         if x.dim() == 1:
             x = x.unsqueeze(0)
-        if x.dtype != torch.float32:
+        if x.dtype != torch.float32 and not (keep_int16 and x.dtype == torch.int16):
             x = x.to(torch.float32)
         if x.stride(-1) != 1:
             x = x.contiguous()
@@ -115,14 +117,15 @@ class SpectralEngine(object):
     # ------------------------------------------------------------------ a3: SNR factor
     def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None):
         """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], DbKeys) with the keys reset."""
-        speech, noise = self._as_batch(speech), self._as_batch(noise)
+        i16 = speech.dtype == torch.int16 and noise.dtype == torch.int16
+        speech, noise = self._as_batch(speech, i16), self._as_batch(noise, i16)
         B, L = speech.shape
         assert noise.shape == speech.shape and _rs(noise) == _rs(speech)
         factor = torch.empty(B, dtype=torch.float32, device=self.device)
         if max_key is None:
             max_key = DbKeys(B, self.device)
         kmax, kmin = _keys(max_key)
-        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), _rs(speech), _ptr(lengths), B, L,
+        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), SAMPLE_I16 if i16 else SAMPLE_F32, _rs(speech), _ptr(lengths), B, L,
                                         _ptr(snr_db), _ptr(factor), _ptr(kmax), _ptr(kmin), self._stream()), "avse_snr_factor")
         return factor, max_key
 
@@ -130,12 +133,14 @@ class SpectralEngine(object):
     def forward_raw(self, speech, noise=None, L=None, len_speech=None, len_noise=None, factor=None, layout=LAYOUT_SLICES,
                     n_slices=None, want=("speech", "noise", "mixed"), mixed_pcm=True, max_key=None, stft=False, out=None):
         """Launch avse_forward.  Returns dict with un-floored outputs + max_key (see include/avse_b200.h)."""
-        speech = self._as_batch(speech)
+        # raw int16 samples go to the kernel as they are (decode fused into its loads) for pair batches
+        i16 = noise is not None and speech.dtype == torch.int16 and noise.dtype == torch.int16 and not stft
+        speech = self._as_batch(speech, i16)
         B = speech.shape[0]
         if L is None:
             L = speech.shape[1]
         if noise is not None:
-            noise = self._as_batch(noise)
+            noise = self._as_batch(noise, i16)
             assert _rs(noise) == _rs(speech) and noise.shape[0] == B
         T = self.n_frames(L)
         if n_slices is None:
@@ -172,6 +177,7 @@ class SpectralEngine(object):
         a.pcm_stride = _rs(res["mixed_pcm"])
         a.max_key = _ptr(kmax)
         a.min_key = _ptr(kmin)
+        a.sample_format = SAMPLE_I16 if i16 else SAMPLE_F32
         a.stft_speech = _ptr(res["stft"])
         check(self._lib.avse_forward(self._ctx, ctypes.byref(a), self._stream()), "avse_forward")
         res["T"], res["ld_t"], res["n_slices"], res["layout"] = T, ld_t, n_slices, layout
@@ -225,7 +231,8 @@ class SpectralEngine(object):
         (dp:125-128, see fit_noise).  Returns (mixed_slices, speech_slices, noise_slices, mixed_pcm)
         with shapes [B, n, 80, 20] x3 and [B, L]; n = min(n_video_slices, int(T/20)) (dp:50, dp:164).
         """
-        speech, noise = self._as_batch(speech), self._as_batch(noise)
+        i16 = speech.dtype == torch.int16 and noise.dtype == torch.int16
+        speech, noise = self._as_batch(speech, i16), self._as_batch(noise, i16)
         L = self.samples_per_slice * int(n_video_slices)
         T = self.n_frames(L)
         n = min(int(n_video_slices), T // SPSS)
@@ -265,8 +272,9 @@ class SpectralEngine(object):
         res = self.forward_raw(signals, None, L=L, len_speech=lengths, layout=LAYOUT_SLICES, n_slices=n, want=("speech",), mixed_pcm=False)
         return self.floor_(res["speech"], res["max_key"], 0)
 
-    def reconstruct(self, mixed_pcm, mel_slices, lengths=None, out=None, work=None):
-        """Batched reconstruct_speech_signal (dp:60-74): mixture PCM [B, L] + dB slices [B, n, 80, 20] -> PCM [B, 160*(min(20n, T)-1)]."""
+    def reconstruct(self, mixed_pcm, mel_slices, lengths=None, out=None, work=None, out_dtype=torch.float32):
+        """Batched reconstruct_speech_signal (dp:60-74): mixture PCM [B, L] + dB slices [B, n, 80, 20] -> PCM [B, 160*(min(20n, T)-1)].
+        out_dtype=torch.int16 fuses AudioSignal.save_to_wav_file's clip + cast (se:176-177) into the last store."""
         mixed_pcm = self._as_batch(mixed_pcm)
         mel = mel_slices if mel_slices.dtype == torch.float32 else mel_slices.to(torch.float32)
         if mel.dim() == 3:
@@ -277,7 +285,8 @@ class SpectralEngine(object):
         T_use = min(SPSS * n, self.n_frames(L))
         out_len = HOP * (T_use - 1)
         if out is None:
-            out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
+            out = torch.empty((B, out_len), dtype=out_dtype, device=self.device)
+        assert out.dtype in (torch.float32, torch.int16)
         per = ctypes.c_longlong(0)
         check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
         if work is None or work.numel() < B * per.value:
@@ -288,6 +297,7 @@ class SpectralEngine(object):
         a.mixed_pcm, a.pcm_stride, a.len_pcm = _ptr(mixed_pcm), _rs(mixed_pcm), _ptr(lengths)
         a.B, a.L = B, L
         a.out_pcm, a.out_stride = _ptr(out), _rs(out)
+        a.out_format = SAMPLE_I16 if out.dtype == torch.int16 else SAMPLE_F32
         a.work, a.work_stride = _ptr(work), per.value
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
@@ -390,7 +400,8 @@ class HostPipeline(object):
     Copies of one chunk overlap the kernels and copies of its neighbours, consecutive submit() calls keep the ring
     going (no barrier between batches), and nothing synchronises with the host until synchronize()."""
 
-    def __init__(self, engine, L, n_video_slices, chunk=125, n_streams=3):
+    def __init__(self, engine, L, n_video_slices, chunk=125, n_streams=3, sample_dtype=torch.float32):
+        assert sample_dtype in (torch.float32, torch.int16)   # int16: raw WAV samples, decoded inside the kernels
         self.eng = engine
         self.L = int(L)
         self.n_video_slices = int(n_video_slices)
@@ -401,8 +412,8 @@ class HostPipeline(object):
         self.slots = []
         for _ in range(n_streams):
             self.slots.append({
-                "s": torch.empty((self.chunk, self.L), dtype=torch.float32, device=dev),
-                "n": torch.empty((self.chunk, self.L), dtype=torch.float32, device=dev),
+                "s": torch.empty((self.chunk, self.L), dtype=sample_dtype, device=dev),
+                "n": torch.empty((self.chunk, self.L), dtype=sample_dtype, device=dev),
                 "snr": torch.zeros((self.chunk,), dtype=torch.float32, device=dev),
                 "out": {},
             })
@@ -424,7 +435,7 @@ class HostPipeline(object):
             st.synchronize()
 
     def submit(self, h_speech, h_noise, h_mixed, h_speech_out, h_noise_out, h_pcm, snr_db=None):
-        """Queue one batch.  h_speech / h_noise: pinned [B, L] float32 (noise fitted to the speech length, dp:125-128);
+        """Queue one batch.  h_speech / h_noise: pinned [B, L] of the pipeline's sample dtype (noise fitted to the speech length, dp:125-128);
         h_mixed / h_speech_out / h_noise_out: pinned [B, n_slices, 80, 20]; h_pcm: pinned [B, L]; snr_db: optional
         pinned [B] float32 (None: 0 dB, dp:130).  Returns the number of chunks queued."""
         B = h_speech.shape[0]

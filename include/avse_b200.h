@@ -34,6 +34,10 @@ extern "C" {
 #define AVSE_E_CONFIG (-2)
 #define AVSE_E_NOCUDA (-3)
 
+#define AVSE_SAMPLE_F32 0 /* float32 samples */
+#define AVSE_SAMPLE_I16 1 /* raw int16 WAV samples (AudioSignal.from_wav_file, dp:122-123): decode fused into the kernels' loads;
+                             encode = clip to [-32768, 32767] + truncate (AudioSignal.save_to_wav_file, se:176-177) fused into the stores */
+
 #define AVSE_LAYOUT_SLICES 0 /* [B][n_slices][80][20]  (np.stack of dp:52-57) */
 #define AVSE_LAYOUT_SPEC 1   /* [B][80][ld_t]          (dp:96 magnitude, time minor) */
 
@@ -55,15 +59,15 @@ int avse_get_filterbank(const avse_ctx* ctx, double* host_out);
  * Accumulates in float64.  snr_db == NULL means 0 dB for every utterance (the reference).
  * Also resets max_key[u][0..2] (the running dB maxima used by avse_forward / avse_floor_*) and, when
  * given, min_key[u][0..2] (the running minima of the stored values).
- * speech/noise: [B][stride] with stride >= L. */
-int avse_snr_factor(avse_ctx* ctx, const float* speech, const float* noise, long long stride,
+ * speech/noise: [B][stride] with stride >= L, float32 or int16 (sample_format = AVSE_SAMPLE_*). */
+int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* noise, int sample_format, long long stride,
                     const int* lengths, int B, int L, const float* snr_db,
                     float* factor_out, int* max_key, int* min_key, void* stream);
 
 typedef struct avse_forward_args {
     /* inputs */
-    const float* speech;     /* [B][in_stride] */
-    const float* noise;      /* [B][in_stride], already fitted to the speech length (dp:125-128); NULL: single signal */
+    const void* speech;      /* [B][in_stride], float32 or int16 (see sample_format) */
+    const void* noise;       /* [B][in_stride], already fitted to the speech length (dp:125-128); NULL: single signal */
     long long in_stride;     /* elements between consecutive utterances */
     const int* len_speech;   /* [B] samples present (zeros beyond: pad_with_zeros dp:40); NULL: L */
     const int* len_noise;    /* [B]; NULL: same as len_speech */
@@ -84,6 +88,8 @@ typedef struct avse_forward_args {
     float* stft_speech;      /* optional complex64 [B][T][321] (re, im interleaved): librosa.stft of `speech` (dp:79), frame-major */
     int* min_key;            /* optional [B][3] running minima of the STORED dB values (same key encoding): lets avse_floor_*
                                 skip every utterance whose minimum is already >= max - 80 (nothing to clip) */
+    int sample_format;       /* AVSE_SAMPLE_F32 (0) or AVSE_SAMPLE_I16: element type of speech / noise.  int16 is supported
+                                for pair batches (noise != NULL) without stft_speech */
 } avse_forward_args;
 
 /* preprocess_audio_pair's arithmetic (dp:130-137) / signal_to_spectrogram (dp:77-96) for a batch:
@@ -117,7 +123,7 @@ typedef struct avse_inverse_args {
     const int* len_pcm;      /* [B] samples present (zeros beyond); NULL: L */
     int B;
     int L;                   /* mixture length; T = 1 + L/160 frames; frames used = min(mel frames, T) (dp:68) */
-    float* out_pcm;          /* [B][out_stride] reconstructed PCM, 160 * (frames_used - 1) samples each (librosa.istft, dp:114) */
+    void* out_pcm;           /* [B][out_stride] reconstructed PCM, 160 * (frames_used - 1) samples each (librosa.istft, dp:114) */
     long long out_stride;
     float* work;             /* scratch [B][work_stride], work_stride >= avse_inverse_work_elems(frames_used) */
     long long work_stride;
@@ -125,6 +131,8 @@ typedef struct avse_inverse_args {
                                 mixed_pcm / L are ignored and frames used = min(mel frames, phase_frames) */
     long long phase_stride;  /* complex elements between utterances */
     int phase_frames;
+    int out_format;          /* AVSE_SAMPLE_F32 (0): out_pcm is float32; AVSE_SAMPLE_I16: out_pcm is int16 [B][out_stride],
+                                clipped to the int16 range and truncated like AudioSignal.save_to_wav_file (se:176-177) */
 } avse_inverse_args;
 
 /* reconstruct_speech_signal / reconstruct_signal_from_spectrogram (dp:60-74, dp:99-116) for a batch:
