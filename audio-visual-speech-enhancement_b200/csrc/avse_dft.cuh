@@ -18,8 +18,8 @@ namespace avse {
 #if defined(__CUDA_ARCH__)
 struct cpx { unsigned long long v; };
 AVSE_HD cpx cmake(float r, float i) { cpx c; asm("mov.b64 %0, {%1, %2};" : "=l"(c.v) : "f"(r), "f"(i)); return c; }
-AVSE_HD float cre(cpx a) { float r, i; asm("mov.b64 {%0, %1}, %2;" : "=f"(r), "=f"(i) : "l"(a.v)); return r; }
-AVSE_HD float cim(cpx a) { float r, i; asm("mov.b64 {%0, %1}, %2;" : "=f"(r), "=f"(i) : "l"(a.v)); return i; }
+AVSE_HD float cre(cpx a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }   // register-pair halves: no instruction
+AVSE_HD float cim(cpx a) { return __uint_as_float((unsigned)(a.v >> 32)); }
 AVSE_HD cpx cadd(cpx a, cpx b) { cpx c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c.v) : "l"(a.v), "l"(b.v)); return c; }
 AVSE_HD cpx csub(cpx a, cpx b) { cpx c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c.v) : "l"(a.v), "l"(b.v)); return c; }
 // element-wise products with a (pr, pi) pair held in a register pair

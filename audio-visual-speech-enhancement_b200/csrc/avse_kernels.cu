@@ -655,6 +655,13 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
 // blockIdx.z selects the signal (data0/1/2 with key column which0 + z).  Only 16-byte groups that actually hold a value
 // below the floor are written back, and an utterance whose stored minimum (min_key, tracked by avse_forward) is already
 // >= max - 80 is skipped without being read: the pass then costs one key load per CTA.
+static __device__ __forceinline__ void floor_store(float4* q, float4 v, float thr) {
+    if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < thr) {
+        v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+        *q = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restrict__ data0, float* __restrict__ data1,
                                                                  float* __restrict__ data2, long long stride, long long n_per_utt,
                                                                  const int* __restrict__ max_key, const int* __restrict__ min_key,
@@ -669,15 +676,12 @@ __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restri
     const long long step = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * step < n4; i += 4 * step) {          // four independent 16-byte loads in flight per thread
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = reinterpret_cast<float4*>(p)[i + k * step];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (fminf(fminf(v[k].x, v[k].y), fminf(v[k].z, v[k].w)) < thr) {
-                v[k].x = fmaxf(v[k].x, thr); v[k].y = fmaxf(v[k].y, thr); v[k].z = fmaxf(v[k].z, thr); v[k].w = fmaxf(v[k].w, thr);
-                reinterpret_cast<float4*>(p)[i + k * step] = v[k];
-            }
+        float4* q = reinterpret_cast<float4*>(p) + i;
+        const float4 v0 = q[0], v1 = q[step], v2 = q[2 * step], v3 = q[3 * step];
+        floor_store(q, v0, thr);
+        floor_store(q + step, v1, thr);
+        floor_store(q + 2 * step, v2, thr);
+        floor_store(q + 3 * step, v3, thr);
     }
     for (; i < n4; i += step) {
         float4 v = reinterpret_cast<float4*>(p)[i];

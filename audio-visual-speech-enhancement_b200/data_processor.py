@@ -36,6 +36,13 @@ def _mono_f32(audio_signal):
     return np.ascontiguousarray(data, dtype=np.float32)
 
 
+def _mono(audio_signal, keep_int16):
+    """Channel 0 (dp:78) as float32, or as the raw int16 WAV samples (from_wav_file, dp:122-123) when the kernels
+    decode them themselves (halves the host->device bytes)."""
+    data = audio_signal.get_data(channel_index=0)
+    return np.ascontiguousarray(data, dtype=np.int16 if keep_int16 else np.float32)
+
+
 def _to_dev(x, eng):
     return torch.from_numpy(x).to(eng.device, non_blocking=True)
 
@@ -148,14 +155,15 @@ def preprocess_audio_pairs(speech_signals, noise_signals, slice_duration_ms, n_v
         buckets.setdefault(int(nvs), []).append(i)
     for nvs, idxs in buckets.items():
         L = eng.samples_per_slice * nvs
-        sp = [_mono_f32(speech_signals[i]) for i in idxs]
+        i16 = all(speech_signals[i].get_data().dtype == np.int16 and noise_signals[i].get_data().dtype == np.int16 for i in idxs)
+        sp = [_mono(speech_signals[i], i16) for i in idxs]
         width = max(max(len(s) for s in sp), 1)
-        S = np.zeros((len(idxs), width), dtype=np.float32)
-        N = np.zeros((len(idxs), width), dtype=np.float32)
+        S = np.zeros((len(idxs), width), dtype=np.int16 if i16 else np.float32)
+        N = np.zeros((len(idxs), width), dtype=np.int16 if i16 else np.float32)
         lens = np.zeros(len(idxs), dtype=np.int32)
         for r, i in enumerate(idxs):
             S[r, :len(sp[r])] = sp[r]
-            N[r, :len(sp[r])] = _fit_noise_np(_mono_f32(noise_signals[i]), len(sp[r]))
+            N[r, :len(sp[r])] = _fit_noise_np(_mono(noise_signals[i], i16), len(sp[r]))
             lens[r] = len(sp[r])
         snr = None
         if snr_db is not None:

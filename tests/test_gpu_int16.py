@@ -97,3 +97,13 @@ def test_int16_single_signal_is_converted_by_the_host_layer(eng):
     a = eng.preprocess_signals(torch.from_numpy(x).cuda(), 5)
     b = eng.preprocess_signals(torch.from_numpy(x.astype(np.float32)).cuda(), 5)
     assert torch.equal(a, b)
+
+
+def test_data_processor_mirror_takes_wav_int16(eng):
+    dp = importlib.import_module("audio-visual-speech-enhancement_b200.data_processor")
+    s, z = _wav_pair(5, 16000, 7000)
+    got = dp.preprocess_audio_pair_signals(dp.AudioSignal(s.copy(), SR), dp.AudioSignal(z.copy(), SR), SLICE_MS, 5, FPS, snr_db=0)
+    ref = O.preprocess_audio_pair_signals(O.AudioSignal(s.copy(), SR), O.AudioSignal(z.copy(), SR), SLICE_MS, 5, FPS, snr_db=0)
+    for g, r in zip(got[:3], ref[:3]):
+        assert np.max(np.abs(g - r)) <= TOL_DB
+    assert np.max(np.abs(got[3].get_data() - ref[3].get_data())) <= TOL_PCM * np.max(np.abs(ref[3].get_data()))
