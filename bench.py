@@ -432,11 +432,41 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te[0])
+        d2h = 3 * B * N_VIDEO_SLICES * 80 * 20 * 4 + B * L * 4
         line["e2e"] = {"value": world * B * UTT_SECONDS / (e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e_ms,
-                       "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": 3 * B * N_VIDEO_SLICES * 80 * 20 * 4 + B * L * 4,
+                       "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": d2h,
                        "api": "engine.HostPipeline.submit (SNR factor + fused forward + floor over the C ABI) on pinned host buffers; %d chunks per step round-robin over %d streams so H2D, kernels and D2H overlap within and across steps; all copies inside the timed region" % (NCH, args.e2e_streams),
                        "gpu_launches": 3 * NCH * steps_e,
-                       "bound": "PCIe: D2H %.0f MB + H2D %.0f MB per step" % ((3 * B * N_VIDEO_SLICES * 80 * 20 * 4 + B * L * 4) / 1e6, 2 * B * L * 4 / 1e6)}
+                       "bound": "PCIe: D2H %.0f MB + H2D %.0f MB per step" % (d2h / 1e6, 2 * B * L * 4 / 1e6)}
+
+        # the same pipeline fed with raw int16 WAV samples (the reference's on-disk format, dp:122-123): half the H2D bytes
+        del pipe
+        scale = 32767.0 / max(float(speech.abs().max()), float(noise.abs().max()))
+        h_s16 = torch.empty((B, L), dtype=torch.int16, pin_memory=True)
+        h_n16 = torch.empty((B, L), dtype=torch.int16, pin_memory=True)
+        h_s16.copy_((speech * scale).round().to(torch.int16))
+        h_n16.copy_((noise * scale).round().to(torch.int16))
+        pipe16 = eng_mod.HostPipeline(eng, L, N_VIDEO_SLICES, chunk=B // NCH, n_streams=args.e2e_streams, sample_dtype=torch.int16)
+        pipe16.begin_after(main)
+        for _ in range(2):
+            pipe16.submit(h_s16, h_n16, h_out[0], h_out[1], h_out[2], h_pcm)
+        pipe16.join(main)
+        barrier()
+        t0.record()
+        pipe16.begin_after(main)
+        for _ in range(steps_e):
+            pipe16.submit(h_s16, h_n16, h_out[0], h_out[1], h_out[2], h_pcm)
+        pipe16.join(main)
+        t1.record()
+        barrier()
+        e16 = t0.elapsed_time(t1) / steps_e
+        te = torch.tensor([e16], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e16 = float(te[0])
+        line["e2e_int16_input"] = {"value": world * B * UTT_SECONDS / (e16 * 1e-3), "unit": "audio-s/s", "ms_per_step": e16,
+                                   "h2d_bytes_per_step": 2 * B * L * 2, "d2h_bytes_per_step": d2h,
+                                   "note": "same pipeline, host inputs as int16 WAV samples decoded inside the kernels"}
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
