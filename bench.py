@@ -273,6 +273,19 @@ def synth_batch(torch, B, device, seed):
     return x.contiguous(), n.contiguous()
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal affinity) so that the pinned host buffers of the
+    end-to-end pipeline are allocated on the GPU's own NUMA node; matters when several ranks share one host."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -288,6 +301,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     eng_mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
@@ -364,7 +378,7 @@ def main():
         "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(B, world), "roofline": roofline,
-        "gpu_launches": 3 * args.steps, "clocks": clocks,
+        "gpu_launches": 3 * args.steps, "clocks": clocks, "host_cpus_bound_to_gpu_numa_node": numa,
     }
 
     # ---------------- inverse path (config 4), reported beside the headline ----------------
@@ -470,6 +484,10 @@ def main():
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))     # the CPU baseline gets every host thread again
+        except Exception:
+            pass
         procs = host_cores()
         n = args.cpu_sample or B     # the whole per-GPU batch once: ~20-25 core-seconds of float64 numpy
         v, dt = cpu_throughput(n, procs)
