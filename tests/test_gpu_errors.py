@@ -1,0 +1,96 @@
+"""Error behaviour at the boundary: the C ABI returns a negative status for bad arguments (never throws, never
+launches), the Python binding turns it into an exception with the library's message, and the batch driver keeps the
+reference's "bad sample is skipped, the batch continues" semantics (dp:180-186, dp:196)."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import SR, FPS, SLICE_MS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mod():
+    return importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+
+
+@pytest.fixture(scope="module")
+def native():
+    return importlib.import_module("audio-visual-speech-enhancement_b200._native")
+
+
+@pytest.fixture(scope="module")
+def eng(mod):
+    return mod.SpectralEngine(SR, FPS, SLICE_MS, device="cuda:0")
+
+
+def test_c_abi_status_codes(eng, native):
+    lib = eng._lib
+    a = native.ForwardArgs()
+    assert lib.avse_forward(eng._ctx, ctypes.byref(a), None) == -1          # AVSE_E_ARG: NULL speech / max_key
+    assert b"required" in lib.avse_last_error()
+    assert lib.avse_forward(None, ctypes.byref(a), None) == -1
+    assert lib.avse_snr_factor(eng._ctx, None, None, 0, 0, None, 1, 10, None, None, None, None, None) == -1
+    h = ctypes.c_void_p()
+    assert lib.avse_create(16000, 0.0, 8000.0, 9999, ctypes.byref(h)) == -1 and not h.value   # bad device index
+    assert lib.avse_create(16000, 9000.0, 8000.0, 0, ctypes.byref(h)) == -2 and not h.value   # AVSE_E_CONFIG: fmin > fmax
+    per = ctypes.c_longlong(0)
+    assert lib.avse_inverse_work_elems(0, ctypes.byref(per)) == -1
+
+
+def test_python_layer_raises_with_the_library_message(eng, native):
+    s = torch.zeros((2, 300), device="cuda")            # L <= 320: reflect padding impossible (librosa would raise too)
+    with pytest.raises(native.AvseError, match="L > 320"):
+        eng.forward_raw(s, s.clone())
+    s = torch.zeros((1, 16000), device="cuda")
+    with pytest.raises(native.AvseError, match="n_slices"):
+        eng.forward_raw(s, s.clone(), n_slices=6)       # more slices than int(T / 20) (dp:50)
+    with pytest.raises(native.AvseError, match="int16"):
+        _single_int16(eng, native)                      # int16 samples without a noise signal: refused, not mis-read
+    # the engine is still usable after failed calls
+    ok = eng.preprocess_pairs(torch.randn((1, 16000), device="cuda"), torch.randn((1, 16000), device="cuda"), 5)
+    assert torch.isfinite(ok[0]).all()
+
+
+def _single_int16(eng, native):
+    a = native.ForwardArgs()
+    x = torch.zeros((1, 16000), dtype=torch.int16, device="cuda")
+    out = torch.empty((1, 5, 80, 20), device="cuda")
+    key = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    a.speech, a.in_stride, a.B, a.L, a.n_slices = x.data_ptr(), 16000, 1, 16000, 5
+    a.out_speech, a.out_stride, a.max_key, a.sample_format = out.data_ptr(), 8000, key.data_ptr(), 1
+    native.check(eng._lib.avse_forward(eng._ctx, ctypes.byref(a), None), "avse_forward")
+
+
+def test_unsupported_geometry_is_refused(mod):
+    with pytest.raises(NotImplementedError):
+        mod.SpectralEngine(SR, 30.0, SLICE_MS, device="cuda:0")     # n_fft 533: inconsistent in the reference itself
+
+
+def test_batch_driver_skips_failed_samples(eng, tmp_path):
+    dp = importlib.import_module("audio-visual-speech-enhancement_b200.data_processor")
+    from scipy.io import wavfile
+    from collections import namedtuple
+    Entry = namedtuple("Entry", ["speaker_id", "audio_path", "video_path"])
+    rng = np.random.RandomState(0)
+    entries, noises = [], []
+    for i in range(3):
+        sp, nz = tmp_path / ("s%d.wav" % i), tmp_path / ("n%d.wav" % i)
+        wavfile.write(str(sp), SR, (rng.randn(16000) * 3000).astype(np.int16))
+        wavfile.write(str(nz), SR, (rng.randn(9000) * 1000).astype(np.int16))
+        entries.append(Entry("spk", str(sp), "v%d.mp4" % i))
+        noises.append(str(nz))
+    entries[1] = Entry("spk", str(tmp_path / "missing.wav"), "v1.mp4")   # unreadable audio -> sample dropped, others kept
+
+    def video(path, slice_ms):
+        return np.zeros((4 if path == "v2.mp4" else 5, 128, 128, 5), np.uint8), FPS
+
+    samples = dp.preprocess_data(entries, noises, video)
+    assert [s.video_file_path for s in samples] == ["v0.mp4", "v2.mp4"]
+    assert samples[0].mixed_spectrograms.shape == (5, 80, 20)
+    assert samples[1].mixed_spectrograms.shape == (4, 80, 20)             # n_slices = min(video, audio), dp:164
+    assert samples[0].mixed_signal.get_number_of_samples() == 16000
