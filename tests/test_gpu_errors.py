@@ -94,3 +94,36 @@ def test_batch_driver_skips_failed_samples(eng, tmp_path):
     assert samples[0].mixed_spectrograms.shape == (5, 80, 20)
     assert samples[1].mixed_spectrograms.shape == (4, 80, 20)             # n_slices = min(video, audio), dp:164
     assert samples[0].mixed_signal.get_number_of_samples() == 16000
+
+
+def test_kernels_stay_inside_their_buffers(eng):
+    # compute-sanitizer is not available on this pool: guard bands instead.  Every output row is followed by a gap filled
+    # with a sentinel; after the forward, floor and inverse kernels the gaps (and an unused tail utterance) are untouched.
+    B, L, n = 5, 16000, 5
+    SENT = -12345.0
+    g = torch.Generator(device="cuda").manual_seed(11)
+    s = torch.randn((B, L), generator=g, device="cuda") * 0.1
+    z = torch.randn((B, L), generator=g, device="cuda") * 0.05
+    lens = torch.tensor([16000, 15999, 9000, 16000, 321 + 7], dtype=torch.int32, device="cuda")
+    gap = 64
+    bufs = {k: torch.full((B + 1, n * 1600 + gap), SENT, device="cuda") for k in ("speech", "noise", "mixed")}
+    pcm = torch.full((B + 1, L + gap), SENT, device="cuda")
+    out = {k: v[:B, :n * 1600].view(B, n, 80, 20) for k, v in bufs.items()}
+    out["mixed_pcm"] = pcm[:B, :L]
+    f, keys = eng.snr_factor(s, z, lengths=lens)
+    r = eng.forward_raw(s, z, L=L, len_speech=lens, len_noise=lens, factor=f, n_slices=n, max_key=keys, out=out)
+    eng.floor3_(r["speech"], r["noise"], r["mixed"], keys)
+    assert r["mixed"].data_ptr() == bufs["mixed"].data_ptr()
+    for k, v in bufs.items():
+        assert torch.all(v[:B, n * 1600:] == SENT) and torch.all(v[B] == SENT), k
+        assert torch.isfinite(v[:B, :n * 1600]).all() and not torch.any(v[:B, :n * 1600] == SENT), k
+    assert torch.all(pcm[:B, L:] == SENT) and torch.all(pcm[B] == SENT) and not torch.any(pcm[:B, :L] == SENT)
+    T_use = 100
+    rec_buf = torch.full((B + 1, 160 * (T_use - 1) + gap), SENT, device="cuda")
+    rec = eng.reconstruct(pcm[:B, :L], r["mixed"], lengths=lens, out=rec_buf[:B, :160 * (T_use - 1)])
+    assert rec.data_ptr() == rec_buf.data_ptr()
+    assert torch.all(rec_buf[:B, 160 * (T_use - 1):] == SENT) and torch.all(rec_buf[B] == SENT)
+    assert torch.isfinite(rec).all() and not torch.any(rec == SENT)
+    rec16_buf = torch.full((B + 1, 160 * (T_use - 1) + gap), 12321, dtype=torch.int16, device="cuda")
+    eng.reconstruct(pcm[:B, :L], r["mixed"], lengths=lens, out=rec16_buf[:B, :160 * (T_use - 1)])
+    assert torch.all(rec16_buf[:B, 160 * (T_use - 1):] == 12321) and torch.all(rec16_buf[B] == 12321)
