@@ -202,11 +202,11 @@ AVSE_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
 
 // One bin of the scan.  n' = Z_k - conj Z_{N-k} = i N' has the same magnitude as N', and the mixture follows from
 // M' = S' + factor N' = S' + factor (n'_im, -n'_re): bit-identical to forming N' first, with one packed op less.
-AVSE_HD void scan4_bin(const float* za, const float* zc, const vec4* tab, int j, bool emit, float factor, float nfactor,
+AVSE_HD void scan4_bin(const float* za, const float* zc, const vec2* tab, int j, bool emit, float factor, float nfactor,
                        float*& esn, float*& em, cpx& Asn, cpx& Bsn, float& Am, float& Bm) {
     const cpx a = cload(za + 2 * j);
     const cpx c = cload(zc - 2 * j);
-    const vec4 w = tab[j];                                                // (wa, wa, wb, wb)
+    const vec2 w = tab[j];                                                // (wa, wb): one 8-byte load (2 wavefronts; 16 bytes cost 4)
     if (emit) {
         cstore(esn, Asn);
         *em = Am;
@@ -223,20 +223,20 @@ AVSE_HD void scan4_bin(const float* za, const float* zc, const vec4* tab, int j,
     const float mn = fast_sqrt(fma_rn(cim(n), cim(n), cre(n) * cre(n)));
     const float mm = fast_sqrt(fma_rn(mi, mi, mr * mr));
     const cpx msn = cmake(ms, mn);
-    Asn = cfma_pp(msn, cmake(w.x, w.y), Asn);
-    Bsn = cfma_pp(msn, cmake(w.z, w.w), Bsn);
+    Asn = cfma_pp(msn, cmake(w.x, w.x), Asn);
+    Bsn = cfma_pp(msn, cmake(w.y, w.y), Bsn);
     Am = fma_rn(w.x, mm, Am);
-    Bm = fma_rn(w.z, mm, Bm);
+    Bm = fma_rn(w.y, mm, Bm);
 }
 
-// s_w4: [SCAN4_BINS] (wa, wa, wb, wb).  Blocks of 8 bins with compile-time mask bit positions (the mask is shifted
+// s_w: [SCAN4_BINS] (wa, wb).  Blocks of 8 bins with compile-time mask bit positions (the mask is shifted
 // once per block), so the emission test is a single predicate-setting logic op per bin.
-AVSE_HD void stage4_scan(int lane, float factor, const vec4* s_w4, unsigned mask_lo, unsigned mask_hi, float* frames) {
+AVSE_HD void stage4_scan(int lane, float factor, const vec2* s_w, unsigned mask_lo, unsigned mask_hi, float* frames) {
     const int f = lane >> 3, p = lane & 7;
     float* fr = frames + f * FRAME4_F;
     const float* za = fr + 2 * CHUNK4 * p;            // slot k      = za + 2 i
     const float* zc = fr + 2 * (NFFT - CHUNK4 * p);   // slot 640-k  = zc - 2 i
-    const vec4* tab = s_w4 + CHUNK4 * p;
+    const vec2* tab = s_w + CHUNK4 * p;
     float* esn = fr + 2 * CHUNK4 * p;                 // next (speech, noise) emission slot
     float* em = fr + 2 * (NFFT - CHUNK4 * p) + 1;     // next mixture emission float
     cpx Asn = cmake(0.0f, 0.0f), Bsn = cmake(0.0f, 0.0f);

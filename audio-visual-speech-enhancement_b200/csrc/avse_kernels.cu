@@ -397,12 +397,12 @@ constexpr int F4_WARPS = AVSE_F4_WARPS;
 constexpr int F4_THREADS = F4_WARPS * 32;
 constexpr int F4_SM_WIN = F4_WARPS * WARP4_SMEM_F;             // [640]
 constexpr int F4_SM_TW = F4_SM_WIN + NFFT;                     // [16][40] vec2
-constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec4 (wa, wa, wb, wb)
-constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 4;        // [80] ivec4
+constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec2 (wa, wb)
+constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 2;        // [80] ivec4
 constexpr int F4_SM_MIN = F4_SM_LOC + NMEL * 4;                // [warps][3][32] per-lane running minima
 constexpr int F4_SMEM_F = F4_SM_MIN + F4_WARPS * 96;
 constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
-static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 4) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
+static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
 
 template <typename S>
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NFFT; i += F4_THREADS) smem[F4_SM_WIN + i] = P.tb.window[i];
     for (int i = threadIdx.x; i < N1 * N2 * 2; i += F4_THREADS) smem[F4_SM_TW + i] = P.tb.tw1t[i];
-    for (int i = threadIdx.x; i < SCAN4_BINS * 4; i += F4_THREADS) smem[F4_SM_SCANW + i] = P.tb.scan4_w[2 * (i >> 2) + ((i >> 1) & 1)];
+    for (int i = threadIdx.x; i < SCAN4_BINS * 2; i += F4_THREADS) smem[F4_SM_SCANW + i] = P.tb.scan4_w[i];
     for (int i = threadIdx.x; i < NMEL * 4; i += F4_THREADS) reinterpret_cast<int*>(smem + F4_SM_LOC)[i] = P.tb.scan4_loc[i];
     float* frames = smem + warp * WARP4_SMEM_F;
     for (int i = lane; i < WARP4_SMEM_F; i += 32) frames[i] = 0.0f;   // pad slots stay finite (they meet exact-zero weights)
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
 
     const float* s_win = smem + F4_SM_WIN;
     const vec2* s_tw = reinterpret_cast<const vec2*>(smem + F4_SM_TW);
-    const vec4* s_scanw = reinterpret_cast<const vec4*>(smem + F4_SM_SCANW);
+    const vec2* s_scanw = reinterpret_cast<const vec2*>(smem + F4_SM_SCANW);
     const ivec4* s_loc = reinterpret_cast<const ivec4*>(smem + F4_SM_LOC);
 
     Lane4Const lc;

@@ -143,9 +143,7 @@ extern "C" int emul_forward4(const float* speech, const float* noise, int L, int
     memset(w.frames, 0, sizeof(w.frames));
     const int T = 1 + L / HOP, G = (T + F4 - 1) / F4;
     const vec2* s_tw = reinterpret_cast<const vec2*>(h.tw1t.data());
-    std::vector<float> w4(h.scan4_w.size() * 2);     // the kernel stages (wa, wb) as (wa, wa, wb, wb)
-    for (size_t i = 0; i < w4.size(); ++i) w4[i] = h.scan4_w[2 * (i >> 2) + ((i >> 1) & 1)];
-    const vec4* s_scanw = reinterpret_cast<const vec4*>(w4.data());
+    const vec2* s_scanw = reinterpret_cast<const vec2*>(h.scan4_w.data());
     std::vector<ivec4> loc(NMEL);
     for (int m = 0; m < NMEL; ++m) { loc[m].x = h.scan4_loc[4 * m]; loc[m].y = h.scan4_loc[4 * m + 1]; loc[m].z = h.scan4_loc[4 * m + 2]; loc[m].w = h.scan4_loc[4 * m + 3]; }
     for (int lane = 0; lane < 32; ++lane) lane4_const_init(lane, h.window.data(), s_tw, w.lc[lane]);
