@@ -113,3 +113,24 @@ def test_reconstruct_roundtrip_quality():
     x = a.get_data()[:47840]
     err = rec.get_data() - x
     assert np.sqrt(np.mean(err ** 2)) / np.sqrt(np.mean(x ** 2)) < 0.5  # mel round trip is lossy but close
+
+
+def test_against_transformers_librosa_compatible_front_end():
+    """Third independent pin of the a5 row (dp:77-96): transformers.audio_utils re-implements librosa's mel filterbank,
+    STFT framing (periodic Hann, centre + reflect padding) and amplitude_to_db (reference 1, amin 1e-5, top_db 80)."""
+    au = pytest.importorskip("transformers.audio_utils")
+    fb_t = au.mel_filter_bank(321, 80, 0.0, 8000.0, SR, norm="slaney", mel_scale="slaney")        # (321, 80), float64
+    assert np.max(np.abs(fb_t.T - O.mel_filterbank(SR, 640, 80, 0.0, 8000.0))) < 1e-14
+    x = (O.synth_speech(48000, SR, 3) + O.synth_noise(48000, 3)).astype(np.float64)
+    win = au.window_function(640, "hann", periodic=True)
+    mag = au.spectrogram(x, win, 640, 160, fft_length=640, power=1.0, center=True, pad_mode="reflect", dtype=np.float64)
+    D = O.stft(x, 640, 160)
+    assert mag.shape == (321, 301) and np.max(np.abs(mag - np.abs(D))) < 1e-5 * np.max(np.abs(D))   # their FFT runs in complex64
+    logmel = au.spectrogram(x, win, 640, 160, fft_length=640, power=1.0, center=True, pad_mode="reflect", mel_filters=fb_t,
+                            mel_floor=0.0, log_mel="dB", reference=1.0, min_value=1e-5, db_range=80.0, dtype=np.float64)
+    ref, _ = O.signal_to_spectrogram(O.AudioSignal(x, SR), 640, 160)
+    assert logmel.shape == ref.shape == (80, 301)
+    assert np.max(np.abs(logmel - ref)) < 1e-5                                                      # dB
+    rng = np.random.RandomState(0)
+    a = np.abs(rng.randn(80, 50)) * 10.0 ** rng.uniform(-9, 1, (80, 50))                            # spans the amin clamp and the 80 dB floor
+    assert np.max(np.abs(au.amplitude_to_db(a, 1.0, 1e-5, 80.0) - O.amplitude_to_db(a))) < 1e-12
