@@ -46,6 +46,7 @@ EXPORTS = [
     "avse_create", "avse_destroy", "avse_last_error", "avse_version", "avse_get_filterbank",
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
     "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3", "avse_gather_rows",
+    "avse_create_ex", "avse_get_geometry", "avse_inverse_work_elems_ctx",
 ]
 
 
@@ -89,6 +90,12 @@ def load(build=True):
     lib.avse_inverse.restype = i32
     lib.avse_inverse_work_elems.argtypes = [i32, _c.POINTER(ll)]
     lib.avse_inverse_work_elems.restype = i32
+    lib.avse_create_ex.argtypes = [i32, i32, i32, i32, i32, f64, f64, i32, _c.POINTER(vp)]
+    lib.avse_create_ex.restype = i32
+    lib.avse_get_geometry.argtypes = [vp, _c.POINTER(i32 * 6)]
+    lib.avse_get_geometry.restype = i32
+    lib.avse_inverse_work_elems_ctx.argtypes = [vp, i32, _c.POINTER(ll)]
+    lib.avse_inverse_work_elems_ctx.restype = i32
     lib.avse_gather_rows.argtypes = [vp, vp, vp, vp, ll, ll, vp, ll, vp, vp, vp, vp, vp]
     lib.avse_gather_rows.restype = i32
     _lib = lib

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include "../../include/avse_b200.h"
 #include "avse_tables.h"
+#include "avse_generic.h"
 #include "avse_fwd_stages.cuh"
 
 struct avse_ctx {
@@ -19,7 +21,17 @@ struct avse_ctx {
     const float* d_tri_sup = nullptr;
     const int* d_col_band = nullptr;
     const float* d_col_w = nullptr;
+    // geometry served by this context; generic == true: the fallback kernels of avse_generic.cu (any n_fft)
+    bool generic = false;
+    int n_fft = 640, hop = 160, n_bins = 321, n_mels = 80, spss = 20;
+    avse::GenericHost gen;
+    avse::GenericDev gd;
+    void* gbase = nullptr;        // device allocation holding the generic tables
 };
+
+int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream);
+int avse_generic_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream);
+int avse_generic_frames(const avse::GenericGeo& q, int L);
 
 int avse_fail(int code, const std::string& msg);
 int avse_cuda_fail(cudaError_t e, const char* where);

@@ -219,8 +219,18 @@ extern "C" int avse_inverse_work_elems(int n_frames_use, long long* per_utteranc
     return 0;
 }
 
+// Scratch floats per utterance for `ctx`'s geometry: the generic path keeps every windowed output frame ([T][n_inv]).
+extern "C" int avse_inverse_work_elems_ctx(const avse_ctx* ctx, int n_frames_use, long long* per_utterance) {
+    if (!ctx) return avse_fail(AVSE_E_ARG, "avse_inverse_work_elems_ctx: NULL context");
+    if (!ctx->generic) return avse_inverse_work_elems(n_frames_use, per_utterance);
+    if (n_frames_use <= 0 || per_utterance == nullptr) return avse_fail(AVSE_E_ARG, "avse_inverse_work_elems_ctx: bad argument");
+    *per_utterance = ((long long)n_frames_use * ctx->gen.geo.n_inv + 3) / 4 * 4;
+    return 0;
+}
+
 extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream) {
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL argument");
+    if (ctx->generic) return avse_generic_inverse(ctx, args, stream);
     const avse_inverse_args& a = *args;
     if (!a.mel_db || (!a.mixed_pcm && !a.phase) || !a.out_pcm || !a.work) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
     if (a.B <= 0 || (!a.phase && a.L <= HALF)) return avse_fail(AVSE_E_ARG, "avse_inverse: need B > 0 and L > 320");

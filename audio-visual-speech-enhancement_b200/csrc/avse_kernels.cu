@@ -99,11 +99,12 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
 
 extern "C" void avse_destroy(avse_ctx* ctx) {
     if (ctx == nullptr) return;
-    if (ctx->dbase) {
+    if (ctx->dbase || ctx->gbase) {
         int prev = 0;
         cudaGetDevice(&prev);
         cudaSetDevice(ctx->device);
-        cudaFree(ctx->dbase);
+        if (ctx->dbase) cudaFree(ctx->dbase);
+        if (ctx->gbase) cudaFree(ctx->gbase);
         cudaSetDevice(prev);
     }
     delete ctx;
@@ -111,7 +112,76 @@ extern "C" void avse_destroy(avse_ctx* ctx) {
 
 extern "C" int avse_get_filterbank(const avse_ctx* ctx, double* host_out) {
     if (ctx == nullptr || host_out == nullptr) return avse_fail(AVSE_E_ARG, "avse_get_filterbank: NULL argument");
-    memcpy(host_out, ctx->host.fb.data(), sizeof(double) * NMEL * NBINS);
+    if (ctx->generic) memcpy(host_out, ctx->gen.fb.data(), sizeof(double) * ctx->gen.fb.size());
+    else memcpy(host_out, ctx->host.fb.data(), sizeof(double) * NMEL * NBINS);
+    return 0;
+}
+
+extern "C" int avse_get_geometry(const avse_ctx* ctx, int* out6) {
+    if (ctx == nullptr || out6 == nullptr) return avse_fail(AVSE_E_ARG, "avse_get_geometry: NULL argument");
+    out6[0] = ctx->n_fft; out6[1] = ctx->hop; out6[2] = ctx->n_bins; out6[3] = ctx->n_mels; out6[4] = ctx->spss;
+    out6[5] = ctx->generic ? 1 : 0;
+    return 0;
+}
+
+// Any geometry the reference can derive (dp:44-45, dp:49): the specialised kernels for 640 / 160 / 80 / 20, the generic
+// fallback kernels (avse_generic.cu) otherwise.
+extern "C" int avse_create_ex(int sample_rate, int n_fft, int hop, int n_mels, int spss, double fmin, double fmax, int device,
+                              avse_ctx** out) {
+    const char* fg = getenv("AVSE_FORCE_GENERIC");     // testing: run the generic kernels at the specialised geometry too
+    if (n_fft == NFFT && hop == HOP && n_mels == NMEL && spss == SPSS && !(fg != nullptr && fg[0] == '1')) {
+        const int rc = avse_create(sample_rate, fmin, fmax, device, out);
+        if (rc != AVSE_E_CONFIG) return rc;     // a filterbank the banded kernels cannot hold falls through to the generic path
+    }
+    if (out == nullptr) return avse_fail(AVSE_E_ARG, "avse_create_ex: out is NULL");
+    *out = nullptr;
+    avse_ctx* c = new (std::nothrow) avse_ctx();
+    if (c == nullptr) return avse_fail(AVSE_E_ARG, "avse_create_ex: out of host memory");
+    if (!build_generic(c->gen, sample_rate, n_fft, hop, n_mels, spss, fmin, fmax)) {
+        std::string e = c->gen.error;
+        delete c;
+        return avse_fail(AVSE_E_CONFIG, "avse_create_ex: " + e);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { delete c; return avse_fail(AVSE_E_NOCUDA, "avse_create_ex: no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) { delete c; return avse_fail(AVSE_E_ARG, "avse_create_ex: bad device index"); }
+    c->device = device;
+    c->generic = true;
+    c->n_fft = n_fft; c->hop = hop; c->n_bins = c->gen.geo.bins; c->n_mels = n_mels; c->spss = spss;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const GenericHost& h = c->gen;
+    struct Sec { const void* src; size_t bytes; size_t off; };
+    std::vector<Sec> secs = {
+        {h.window.data(), h.window.size() * 4, 0},         {h.tw.data(), h.tw.size() * 8, 0},
+        {h.window_inv.data(), h.window_inv.size() * 4, 0}, {h.tw_inv.data(), h.tw_inv.size() * 8, 0},
+        {h.band_lo.data(), h.band_lo.size() * 4, 0},       {h.band_cnt.data(), h.band_cnt.size() * 4, 0},
+        {h.band_off.data(), h.band_off.size() * 4, 0},     {h.band_w.data(), h.band_w.size() * 4, 0},
+        {h.pinv.data(), h.pinv.size() * 4, 0},
+    };
+    size_t total = 0;
+    for (auto& sc : secs) { sc.off = total; total += (sc.bytes + 255) / 256 * 256; }
+    std::vector<char> stage(total, 0);
+    for (auto& sc : secs) memcpy(stage.data() + sc.off, sc.src, sc.bytes);
+    e = cudaMalloc(&c->gbase, total);
+    if (e != cudaSuccess) { delete c; cudaSetDevice(prev); return avse_cuda_fail(e, "cudaMalloc(generic tables)"); }
+    e = cudaMemcpy(c->gbase, stage.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(c->gbase); delete c; cudaSetDevice(prev); return avse_cuda_fail(e, "cudaMemcpy(generic tables)"); }
+    char* b = (char*)c->gbase;
+    c->gd.window = (const float*)(b + secs[0].off);
+    c->gd.tw = (const double*)(b + secs[1].off);
+    c->gd.window_inv = (const float*)(b + secs[2].off);
+    c->gd.tw_inv = (const double*)(b + secs[3].off);
+    c->gd.band_lo = (const int*)(b + secs[4].off);
+    c->gd.band_cnt = (const int*)(b + secs[5].off);
+    c->gd.band_off = (const int*)(b + secs[6].off);
+    c->gd.band_w = (const float*)(b + secs[7].off);
+    c->gd.pinv = (const float*)(b + secs[8].off);
+    cudaSetDevice(prev);
+    *out = c;
     return 0;
 }
 
@@ -575,6 +645,7 @@ __global__ void avse_reset_max_kernel(int* __restrict__ max_key, int* __restrict
 
 extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream) {
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_forward: NULL argument");
+    if (ctx->generic) return avse_generic_forward(ctx, args, stream);
     const avse_forward_args& a = *args;
     if (!a.speech || !a.max_key) return avse_fail(AVSE_E_ARG, "avse_forward: speech and max_key are required");
     if (a.B <= 0 || a.L <= HALF) return avse_fail(AVSE_E_ARG, "avse_forward: need B > 0 and L > 320 (reflect padding)");
@@ -728,29 +799,30 @@ extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, 
 
 __global__ void __launch_bounds__(256) avse_floor_gather_kernel(const float* __restrict__ spec, long long spec_stride, int ld_t,
                                                                 float* __restrict__ slices, long long slices_stride, int n_slices,
-                                                                const int* __restrict__ max_key, int which) {
+                                                                const int* __restrict__ max_key, int which, int n_mels, int spss) {
     const int u = blockIdx.y;
     const float thr = key_to_float(max_key[3 * u + which]) - TOP_DB;
     const float* src = spec + (size_t)u * spec_stride;
     float* dst = slices + (size_t)u * slices_stride;
-    const int n = n_slices * NMEL * AVSE_SPSS;
+    const int n = n_slices * n_mels * spss;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int j = i % AVSE_SPSS;
-        const int m = (i / AVSE_SPSS) % NMEL;
-        const int s = i / (AVSE_SPSS * NMEL);
-        dst[i] = fmaxf(src[(size_t)m * ld_t + s * AVSE_SPSS + j], thr);
+        const int j = i % spss;
+        const int m = (i / spss) % n_mels;
+        const int s = i / (spss * n_mels);
+        dst[i] = fmaxf(src[(size_t)m * ld_t + s * spss + j], thr);
     }
 }
 
 extern "C" int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spec_stride, int ld_t, float* slices,
                                  long long slices_stride, int n_slices, int B, const int* max_key, int which, void* stream) {
     if (!ctx || !spec || !slices || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_gather: NULL argument");
-    if (B <= 0 || n_slices <= 0 || ld_t < n_slices * AVSE_SPSS || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_gather: bad sizes");
-    const int n = n_slices * NMEL * AVSE_SPSS;
+    if (B <= 0 || n_slices <= 0 || ld_t < n_slices * ctx->spss || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_gather: bad sizes");
+    const int n = n_slices * ctx->n_mels * ctx->spss;
     int bx = (n + 255) / 256;
     if (bx > 64) bx = 64;
     dim3 grid((unsigned)bx, (unsigned)B);
-    avse_floor_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(spec, spec_stride, ld_t, slices, slices_stride, n_slices, max_key, which);
+    avse_floor_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(spec, spec_stride, ld_t, slices, slices_stride, n_slices, max_key, which,
+                                                                     ctx->n_mels, ctx->spss);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -31,6 +31,15 @@ def get_engine(sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, 
     return _engines[key]
 
 
+def _engine_for_fft(sample_rate, n_fft, hop_length, device=None):
+    """Engine for an explicit (n_fft, hop_length) pair (the arguments of dp:77 / dp:99)."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    key = (int(sample_rate), "fft", int(n_fft), int(hop_length), dev)
+    if key not in _engines:
+        _engines[key] = SpectralEngine(sample_rate, float(sample_rate) / n_fft, 200, device="cuda:%d" % dev, n_fft=n_fft, hop=hop_length)
+    return _engines[key]
+
+
 def _mono_f32(audio_signal):
     data = audio_signal.get_data(channel_index=0)  # dp:78
     return np.ascontiguousarray(data, dtype=np.float32)
@@ -52,9 +61,7 @@ def _to_dev(x, eng):
 # --------------------------------------------------------------------------------------------
 def signal_to_spectrogram(audio_signal, n_fft, hop_length, mel=True, db=True):
     """dp:77-96.  Returns (magnitude (80|321, T) float32, phase (321, T) complex64)."""
-    if (n_fft, hop_length) != (N_FFT, HOP):
-        raise NotImplementedError("only n_fft=640 / hop_length=160 (the reference's 16 kHz / 25 fps geometry)")
-    eng = get_engine(audio_signal.get_sample_rate(), audio_signal.get_sample_rate() / float(n_fft))
+    eng = _engine_for_fft(audio_signal.get_sample_rate(), n_fft, hop_length)
     x = _to_dev(_mono_f32(audio_signal), eng)
     db_mel, D = eng.spectrogram(x, stft=True)
     D = D[0].transpose(0, 1)  # (321, T)
@@ -98,7 +105,7 @@ def reconstruct_speech_signal(mixed_signal, speech_spectrograms, video_frame_rat
     """dp:60-74.  speech_spectrograms: (n, 80, 20) dB slices.  Returns AudioSignal (float32 data)."""
     eng = get_engine(mixed_signal.get_sample_rate(), video_frame_rate)
     spec = np.asarray(speech_spectrograms, dtype=np.float32)
-    if spec.ndim != 3 or spec.shape[1:] != (N_MELS, SPSS):
+    if spec.ndim != 3 or spec.shape[1:] != (eng.n_mels, eng.spss):
         raise ValueError("speech_spectrograms must have shape (n_slices, 80, 20)")
     pcm = _to_dev(_mono_f32(mixed_signal), eng)
     out = eng.reconstruct(pcm, _to_dev(np.ascontiguousarray(spec), eng))
@@ -107,9 +114,9 @@ def reconstruct_speech_signal(mixed_signal, speech_spectrograms, video_frame_rat
 
 def reconstruct_signal_from_spectrogram(magnitude, phase, sample_rate, n_fft, hop_length, mel=True, db=True):
     """dp:99-116 with an explicit phase array (321, T).  Returns AudioSignal."""
-    if (n_fft, hop_length) != (N_FFT, HOP) or not (mel and db):
-        raise NotImplementedError("only the reference's call form: n_fft=640, hop=160, mel=True, db=True")
-    eng = get_engine(sample_rate, sample_rate / float(n_fft))
+    if not (mel and db):
+        raise NotImplementedError("only the reference's call form: mel=True, db=True (dp:72-74)")
+    eng = _engine_for_fft(sample_rate, n_fft, hop_length)
     mag = np.ascontiguousarray(np.asarray(magnitude, dtype=np.float32))
     ph = np.ascontiguousarray(np.asarray(phase).astype(np.complex64).T)  # frame-major (T, 321)
     out = eng.reconstruct_with_phase(_to_dev(mag, eng).unsqueeze(0), _to_dev(ph, eng).unsqueeze(0))
@@ -267,7 +274,7 @@ class MelConverter(object):
         self.slice_duration_ms = slice_duration_ms
 
     def signal_to_mel_spectrogram(self, audio_signal):
-        return signal_to_spectrogram(audio_signal, N_FFT, HOP, mel=True, db=True)[0]
+        return signal_to_spectrogram(audio_signal, self.engine.n_fft, self.engine.hop, mel=True, db=True)[0]
 
     def signal_to_slices(self, audio_signal, n_video_slices):
         return preprocess_audio_signal(audio_signal, self.slice_duration_ms, n_video_slices, self.video_frame_rate)

@@ -62,25 +62,37 @@ def geometry(sample_rate, video_frame_rate, slice_duration_ms=200):
 class SpectralEngine(object):
     """One GPU's worth of the spectral front/back end."""
 
-    def __init__(self, sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, fmin=0.0, fmax=8000.0, device=None):
+    def __init__(self, sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, fmin=0.0, fmax=8000.0, device=None,
+                 n_fft=None, hop=None):
+        """Geometry from (sample_rate, video_frame_rate, slice_duration_ms) as the reference derives it (dp:36, dp:44-45,
+        dp:49); n_fft / hop may be given explicitly instead (signal_to_spectrogram's own arguments, dp:77)."""
         if not torch.cuda.is_available():
             raise RuntimeError("SpectralEngine needs a CUDA device: this framework has no CPU path")
-        sps, n_fft, hop, spss = geometry(sample_rate, video_frame_rate, slice_duration_ms)
-        if (n_fft, hop) != (N_FFT, HOP):
-            raise NotImplementedError(
-                "kernels are specialised for n_fft=640/hop=160 (sample_rate/fps = 640, the reference's 16 kHz / 25 fps); got n_fft=%d" % n_fft)
+        sps, n_fft_d, hop_d, spss = geometry(sample_rate, video_frame_rate, slice_duration_ms)
+        if n_fft is None:
+            n_fft, hop = n_fft_d, hop_d
+        else:
+            n_fft = int(n_fft)
+            hop = int(n_fft / 4) if hop is None else int(hop)
+            spss = int(sps / hop) if hop else 0
+        if hop < 1 or spss < 1:
+            raise ValueError("degenerate geometry: n_fft=%d hop=%d frames per slice=%d" % (n_fft, hop, spss))
         self.sample_rate = int(sample_rate)
         self.video_frame_rate = float(video_frame_rate)
         self.slice_duration_ms = slice_duration_ms
         self.samples_per_slice = sps
-        self.spss = spss
-        if spss != SPSS:
-            raise NotImplementedError("slice_duration_ms must give 20 spectrogram frames per slice (200 ms at hop 160)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._lib = _native.load()
         h = ctypes.c_void_p()
-        check(self._lib.avse_create(self.sample_rate, float(fmin), float(fmax), self.device.index or 0, ctypes.byref(h)), "avse_create")
+        # (640, 160, 80, 20) -- the reference's 16 kHz / 25 fps -- gets the specialised kernels; any other geometry the
+        # reference can derive (dp:44-45) runs the generic fallback kernels behind the same entry points
+        check(self._lib.avse_create_ex(self.sample_rate, n_fft, hop, N_MELS, spss, float(fmin), float(fmax), self.device.index or 0,
+                                       ctypes.byref(h)), "avse_create_ex")
         self._ctx = h
+        geo = (ctypes.c_int * 6)()
+        check(self._lib.avse_get_geometry(self._ctx, ctypes.byref(geo)), "avse_get_geometry")
+        self.n_fft, self.hop, self.n_bins, self.n_mels, self.spss = (int(v) for v in geo[:5])
+        self.specialised = geo[5] == 0      # False: the generic fallback kernels serve this geometry
 
     def __del__(self):
         try:
@@ -96,7 +108,7 @@ class SpectralEngine(object):
 
     def filterbank(self):
         """librosa.filters.mel(sr, 640, 80, fmin, fmax) as built by the library (float64 (80, 321))."""
-        fb = np.zeros((N_MELS, N_BINS), dtype=np.float64)
+        fb = np.zeros((self.n_mels, self.n_bins), dtype=np.float64)
         check(self._lib.avse_get_filterbank(self._ctx, fb.ctypes.data), "avse_get_filterbank")
         return fb
 
@@ -110,9 +122,9 @@ class SpectralEngine(object):
             x = x.contiguous()
         return x
 
-    @staticmethod
-    def n_frames(L):
-        return 1 + L // HOP
+    def n_frames(self, L):
+        """librosa.stft(center=True) frame count: 1 + (L + 2 (n_fft // 2) - n_fft) // hop (== 1 + L // hop for even n_fft)."""
+        return 1 + (L + 2 * (self.n_fft // 2) - self.n_fft) // self.hop
 
     # ------------------------------------------------------------------ a3: SNR factor
     def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None):
@@ -144,10 +156,10 @@ class SpectralEngine(object):
             assert _rs(noise) == _rs(speech) and noise.shape[0] == B
         T = self.n_frames(L)
         if n_slices is None:
-            n_slices = T // SPSS
+            n_slices = T // self.spss
         res = {} if out is None else out
         ld_t = (T + 3) // 4 * 4
-        shape = (B, n_slices, N_MELS, SPSS) if layout == LAYOUT_SLICES else (B, N_MELS, ld_t)
+        shape = (B, n_slices, self.n_mels, self.spss) if layout == LAYOUT_SLICES else (B, self.n_mels, ld_t)
         for name in ("speech", "noise", "mixed"):
             if name in want and (name == "speech" or noise is not None):
                 if name not in res:
@@ -164,7 +176,7 @@ class SpectralEngine(object):
             check(self._lib.avse_reset_max(self._ctx, _ptr(max_key.max), _ptr(max_key.min), 3 * B, self._stream()), "avse_reset_max")
         kmax, kmin = _keys(max_key)
         res["max_key"] = max_key
-        res["stft"] = torch.empty((B, T, N_BINS), dtype=torch.complex64, device=self.device) if stft else None
+        res["stft"] = torch.empty((B, T, self.n_bins), dtype=torch.complex64, device=self.device) if stft else None
         ref = res["speech"]
         a = ForwardArgs()
         a.speech, a.noise, a.in_stride = _ptr(speech), _ptr(noise), _rs(speech)
@@ -204,7 +216,7 @@ class SpectralEngine(object):
     def floor_gather(self, spec, max_key, which, n_slices):
         """dp:49-57: SPEC [B,80,ld_t] (un-floored) -> floored slices [B,n_slices,80,20]."""
         B, _, ld_t = spec.shape
-        out = torch.empty((B, n_slices, N_MELS, SPSS), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, n_slices, self.n_mels, self.spss), dtype=torch.float32, device=self.device)
         check(self._lib.avse_floor_gather(self._ctx, _ptr(spec), _rs(spec), ld_t, _ptr(out), _rs(out), n_slices, B,
                                           _ptr(_keys(max_key)[0]), which, self._stream()), "avse_floor_gather")
         return out
@@ -235,7 +247,7 @@ class SpectralEngine(object):
         speech, noise = self._as_batch(speech, i16), self._as_batch(noise, i16)
         L = self.samples_per_slice * int(n_video_slices)
         T = self.n_frames(L)
-        n = min(int(n_video_slices), T // SPSS)
+        n = min(int(n_video_slices), T // self.spss)
         if lengths is None and speech.shape[1] != L:
             lengths = torch.full((speech.shape[0],), speech.shape[1], dtype=torch.int32, device=self.device)
         fl = None
@@ -268,7 +280,7 @@ class SpectralEngine(object):
         if lengths is None and signals.shape[1] < L:
             lengths = torch.full((signals.shape[0],), signals.shape[1], dtype=torch.int32, device=self.device)
         T = self.n_frames(L)
-        n = T // SPSS
+        n = T // self.spss
         res = self.forward_raw(signals, None, L=L, len_speech=lengths, layout=LAYOUT_SLICES, n_slices=n, want=("speech",), mixed_pcm=False)
         return self.floor_(res["speech"], res["max_key"], 0)
 
@@ -282,13 +294,13 @@ class SpectralEngine(object):
         mel = mel.contiguous()
         B, L = mixed_pcm.shape
         n = mel.shape[1]
-        T_use = min(SPSS * n, self.n_frames(L))
-        out_len = HOP * (T_use - 1)
+        T_use = min(self.spss * n, self.n_frames(L))
+        out_len = self.hop * (T_use - 1)
         if out is None:
             out = torch.empty((B, out_len), dtype=out_dtype, device=self.device)
         assert out.dtype in (torch.float32, torch.int16)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
         if work is None or work.numel() < B * per.value:
             work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
@@ -310,9 +322,9 @@ class SpectralEngine(object):
         B, _, T_mel = mel.shape
         T_ph = phase.shape[1]
         T_use = min(T_mel, T_ph)
-        out = torch.empty((B, HOP * (T_use - 1)), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, self.hop * (T_use - 1)), dtype=torch.float32, device=self.device)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
         work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, T_mel, T_mel
@@ -321,7 +333,7 @@ class SpectralEngine(object):
         a.B, a.L = B, 0
         a.out_pcm, a.out_stride = _ptr(out), _rs(out)
         a.work, a.work_stride = _ptr(work), per.value
-        a.phase, a.phase_stride, a.phase_frames = ph.data_ptr(), T_ph * N_BINS, T_ph
+        a.phase, a.phase_stride, a.phase_frames = ph.data_ptr(), T_ph * self.n_bins, T_ph
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
 
@@ -334,9 +346,9 @@ class SpectralEngine(object):
         mel = mel.contiguous()
         B, L = mixed_pcm.shape
         T_use = min(mel.shape[2], self.n_frames(L))
-        out = torch.empty((B, HOP * (T_use - 1)), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, self.hop * (T_use - 1)), dtype=torch.float32, device=self.device)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems(T_use, ctypes.byref(per)), "avse_inverse_work_elems")
+        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
         work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, mel.shape[2], mel.shape[2]
@@ -405,7 +417,7 @@ class HostPipeline(object):
         self.eng = engine
         self.L = int(L)
         self.n_video_slices = int(n_video_slices)
-        self.n_slices = min(self.n_video_slices, engine.n_frames(self.L) // SPSS)
+        self.n_slices = min(self.n_video_slices, engine.n_frames(self.L) // engine.spss)
         self.chunk = int(chunk)
         dev = engine.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]

@@ -14,8 +14,9 @@
  *    allocates nothing (the context owns only small constant tables).
  *  - Return value: 0 ok; < 0 bad arguments (AVSE_E_*); > 0 a cudaError_t.  Nothing throws.
  *    avse_last_error() returns a thread-local description of the last failure.
- *  - Geometry is the reference's hard-coded one (dp:44-45, dp:83-89): n_fft 640, hop 160,
- *    321 bins, 80 mel bands, 20 spectrogram frames per 200 ms slice.
+ *  - Geometry: the reference's hard-coded one (dp:44-45, dp:83-89: n_fft 640, hop 160, 321 bins, 80 mel bands,
+ *    20 spectrogram frames per 200 ms slice at 16 kHz / 25 fps) is the specialised hot path; the shapes in the
+ *    comments below ([80][20], [321], 160 ...) read as [n_mels][spss], [bins], hop ... for avse_create_ex contexts.
  */
 #ifndef AVSE_B200_H
 #define AVSE_B200_H
@@ -47,11 +48,23 @@ typedef struct avse_ctx avse_ctx;
  * fmin, fmax) in banded form, tridiagonal factors of F F^T) in float64 on the host and uploads
  * them to `device`.  Replaces the per-call rebuilds at dp:83-89, dp:104-112. */
 int avse_create(int sample_rate, double fmin, double fmax, int device, avse_ctx** out);
+
+/* Any geometry the reference derives from (sample rate, video frame rate, slice duration): n_fft = int(sr / fps) (dp:44),
+ * hop = int(n_fft / 4) (dp:45), spss = int(samples_per_slice / hop) (dp:49), n_mels (dp:86).  (640, 160, 80, 20) gives the
+ * specialised kernels (same as avse_create); anything else -- 320 @ 50 fps, 666 @ 24 fps, odd sizes like 533 @ 30 fps,
+ * 1764 @ 44.1 kHz -- runs the generic kernels (two-level DFT with run-time factors, dense filterbank / pinv tables): same
+ * entry points, same argument structs, correct but several times slower.  For odd n_fft the inverse uses librosa.istft's
+ * inferred size 2 * (bins - 1), as the reference does (dp:114).  Limits: n_fft <= 4096, n_mels <= 256. */
+int avse_create_ex(int sample_rate, int n_fft, int hop, int n_mels, int spss, double fmin, double fmax, int device,
+                   avse_ctx** out);
+
+/* out6 = { n_fft, hop, bins, n_mels, spss, generic (1: fallback kernels, 0: specialised) } of the context. */
+int avse_get_geometry(const avse_ctx* ctx, int* out6);
 void avse_destroy(avse_ctx* ctx);
 const char* avse_last_error(void);
 const char* avse_version(void);
 
-/* Host copy of the dense filterbank, float64 [80][321] (== librosa.filters.mel, dp:83-89). */
+/* Host copy of the dense filterbank, float64 [n_mels][bins] ([80][321] for avse_create; == librosa.filters.mel, dp:83-89). */
 int avse_get_filterbank(const avse_ctx* ctx, double* host_out);
 
 /* AudioMixer.snr_factor (dp:130): factor[u] = sqrt(var(speech_u) / var(noise_u)) * 10^(-snr_db[u]/20),
@@ -140,8 +153,10 @@ typedef struct avse_inverse_args {
  * on the fly) -> irfft + Hann + overlap-add / window sum-square, centre trim.  Two kernels on `stream`. */
 int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream);
 
-/* Scratch floats per utterance needed by avse_inverse for `n_frames_use` reconstructed frames. */
+/* Scratch floats per utterance needed by avse_inverse for `n_frames_use` reconstructed frames (specialised geometry). */
 int avse_inverse_work_elems(int n_frames_use, long long* per_utterance);
+/* The same for the geometry of `ctx` (use this one with avse_create_ex contexts). */
+int avse_inverse_work_elems_ctx(const avse_ctx* ctx, int n_frames_use, long long* per_utterance);
 
 /* Sets n running-max keys to "minus infinity" (and, when min_key != NULL, n running-min keys to "plus infinity") (needed before avse_forward when avse_snr_factor,
  * which also resets them, is not part of the sequence, e.g. single-signal spectrograms). */

@@ -66,9 +66,14 @@ def _single_int16(eng, native):
     native.check(eng._lib.avse_forward(eng._ctx, ctypes.byref(a), None), "avse_forward")
 
 
-def test_unsupported_geometry_is_refused(mod):
-    with pytest.raises(NotImplementedError):
-        mod.SpectralEngine(SR, 30.0, SLICE_MS, device="cuda:0")     # n_fft 533: inconsistent in the reference itself
+def test_unsupported_geometry_is_refused(mod, native):
+    # every n_fft the reference derives is served (generic kernels); only sizes beyond the tables' limits are refused
+    eng30 = mod.SpectralEngine(SR, 30.0, SLICE_MS, device="cuda:0")     # n_fft 533 (odd), hop 133, 24 frames per slice
+    assert (eng30.n_fft, eng30.hop, eng30.spss, eng30.n_bins) == (533, 133, 24, 267) and not eng30.specialised
+    with pytest.raises(native.AvseError, match="n_fft"):
+        mod.SpectralEngine(48000, 10.0, SLICE_MS, device="cuda:0")      # n_fft 4800 > 4096
+    with pytest.raises(ValueError):
+        mod.SpectralEngine(SR, 9000.0, SLICE_MS, device="cuda:0")       # n_fft 1, hop 0
 
 
 def test_batch_driver_skips_failed_samples(eng, tmp_path):
