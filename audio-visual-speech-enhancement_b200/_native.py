@@ -47,6 +47,7 @@ EXPORTS = [
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
     "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3", "avse_gather_rows",
     "avse_create_ex", "avse_get_geometry", "avse_inverse_work_elems_ctx",
+    "avse_video_stats", "avse_video_normalize", "avse_mse",
 ]
 
 
@@ -96,6 +97,12 @@ def load(build=True):
     lib.avse_get_geometry.restype = i32
     lib.avse_inverse_work_elems_ctx.argtypes = [vp, i32, _c.POINTER(ll)]
     lib.avse_inverse_work_elems_ctx.restype = i32
+    lib.avse_video_stats.argtypes = [vp, vp, ll, i32, i32, vp, vp, vp, vp]
+    lib.avse_video_stats.restype = i32
+    lib.avse_video_normalize.argtypes = [vp, vp, ll, i32, i32, vp, vp, vp]
+    lib.avse_video_normalize.restype = i32
+    lib.avse_mse.argtypes = [vp, vp, vp, ll, vp, vp, vp]
+    lib.avse_mse.restype = i32
     lib.avse_gather_rows.argtypes = [vp, vp, vp, vp, ll, ll, vp, ll, vp, vp, vp, vp, vp]
     lib.avse_gather_rows.restype = i32
     _lib = lib

@@ -403,6 +403,55 @@ class SpectralEngine(object):
         return tuple(outs[:2]) + (permutation,) + tuple(outs[2:])
 
 
+class VideoNormalizer(object):
+    """data_processor.VideoNormalizer (dp:201-212) on the device: per-pixel mean / std over (slices, frames) of the
+    mouth-crop tensor [N, H, W, F] and the in-place normalisation."""
+
+    def __init__(self, engine, video_samples):
+        v = self._as_dev(engine, video_samples)
+        N, H, W, F = v.shape
+        self.eng = engine
+        self.shape = (H, W)
+        self.mean_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
+        self.std_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
+        scratch = torch.empty(2 * H * W, dtype=torch.float64, device=engine.device)
+        check(engine._lib.avse_video_stats(engine._ctx, _ptr(v), N, H * W, F, _ptr(scratch), _ptr(self.mean_image), _ptr(self.std_image),
+                                           engine._stream()), "avse_video_stats")
+
+    @staticmethod
+    def _as_dev(engine, video_samples):
+        v = video_samples if torch.is_tensor(video_samples) else torch.from_numpy(np.ascontiguousarray(video_samples, dtype=np.float32))
+        v = v.to(engine.device, dtype=torch.float32).contiguous()
+        assert v.dim() == 4, "video_samples: slices x height x width x frames_per_slice"
+        return v
+
+    def normalize(self, video_samples):
+        """In place like the reference: a CUDA float32 tensor is modified directly, a numpy array is overwritten."""
+        on_dev = torch.is_tensor(video_samples) and video_samples.is_cuda and video_samples.dtype == torch.float32 and video_samples.is_contiguous()
+        v = video_samples if on_dev else self._as_dev(self.eng, video_samples)
+        N, H, W, F = v.shape
+        assert (H, W) == self.shape
+        check(self.eng._lib.avse_video_normalize(self.eng._ctx, _ptr(v), N, H * W, F, _ptr(self.mean_image), _ptr(self.std_image),
+                                                 self.eng._stream()), "avse_video_normalize")
+        if not on_dev:
+            if torch.is_tensor(video_samples):
+                video_samples.copy_(v)
+            else:
+                video_samples[...] = v.cpu().numpy()
+        return video_samples
+
+
+def mse(engine, a, b):
+    """Mean squared error over every element (the loss of network.evaluate on log-mel slices, network.py:214-220)."""
+    a = a.to(engine.device, dtype=torch.float32).contiguous()
+    b = b.to(engine.device, dtype=torch.float32).contiguous()
+    assert a.shape == b.shape
+    scratch = torch.empty(1, dtype=torch.float64, device=engine.device)
+    out = torch.empty(1, dtype=torch.float32, device=engine.device)
+    check(engine._lib.avse_mse(engine._ctx, _ptr(a), _ptr(b), a.numel(), _ptr(scratch), _ptr(out), engine._stream()), "avse_mse")
+    return out
+
+
 class HostPipeline(object):
     """preprocess_audio_pair (dp:119-139) for a HOST-resident batch: pinned host waveforms in, pinned host slices out.
 

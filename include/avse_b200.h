@@ -174,6 +174,20 @@ int avse_gather_rows(avse_ctx* ctx, const float* src0, const float* src1, const 
                      long long row_elems, const long long* index, long long n_out, float* dst0, float* dst1, float* dst2,
                      int* bad_index_flag, void* stream);
 
+/* VideoNormalizer.__init__ (dp:201-205): per-pixel mean and population std over (slices, frames) of the mouth-crop tensor
+ * video [n_slices][hw][frames] float32 (hw = height * width, e.g. 128 * 128; frames = 5).  scratch: 2 * hw doubles
+ * (device).  mean_out / std_out: [hw] float32.  Float64 accumulation. */
+int avse_video_stats(avse_ctx* ctx, const float* video, long long n_slices, int hw, int frames, double* scratch,
+                     float* mean_out, float* std_out, void* stream);
+
+/* VideoNormalizer.normalize (dp:207-212): video[s][p][f] = (video[s][p][f] - mean[p]) / std[p], in place, no epsilon. */
+int avse_video_normalize(avse_ctx* ctx, float* video, long long n_slices, int hw, int frames, const float* mean,
+                         const float* stdv, void* stream);
+
+/* Mean squared error over n elements (the loss network.evaluate reports on log-mel slices, network.py:214-220).
+ * scratch: 1 double (device); out: 1 float (device). */
+int avse_mse(avse_ctx* ctx, const float* a, const float* b, long long n, double* scratch, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
