@@ -9,7 +9,7 @@ sharded by utterance, no data-path collective); rank 0 prints ONE JSON line.
 
   value     whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the host-facing API: pinned host buffers, H2D + D2H in the timed region
-  roofline  dominant kernel (avse_forward_kernel): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  roofline  dominant kernel (avse_forward4_kernel): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the float64 CPU restatement of the reference path (oracle/), timed on host cores
 """
 from __future__ import annotations
@@ -369,10 +369,10 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "forward_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "avse_forward_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "avse_forward4_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
-                "note": "FP32-issue-bound fused FFT kernel; see DESIGN.md and profiles/"}
+                "note": "fused FFT kernel bound by FP32 issue + the shared-memory data pipe, not by HBM; see DESIGN.md section 5 and profiles/"}
 
     line = {
         "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
