@@ -159,10 +159,10 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
     constexpr int LAST_N = (NBINS - 1) - 15 * POST_CHUNK;
 #pragma unroll 3
     for (int i = 0; i < POST_CHUNK; ++i) {
-        if (i >= LAST_N && last) {
-            if (i == LAST_N) cstore(za + 2 * i, cmake(0.0f, 0.0f));   // Nyquist bin: lin = 0
-            continue;
-        }
+        // chunk 15 holds only bins 315..320: the tail iterations compute on harmless in-range slots and keep their stores
+        // predicated off (a branch here diverges in every iteration of the hot loop); the Nyquist bin (lin = 0) stores 0
+        const bool tail = last && i >= LAST_N;
+        const bool nyq = last && i == LAST_N;
         const ivec4 t = tab[i];
         const cpx y0 = cload(yb + 4 * t.x), y1 = cload(yb + 4 * t.y);
         // (lin_A, lin_B) = w0 (c_A, c_B)[b0] + w1 (c_A, c_B)[b1]
@@ -170,8 +170,8 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
         float par, pai, pbr, pbi;
         if (EXT) {
             const int k = POST_CHUNK * p + i;
-            const vec2 qa = phA != nullptr ? phA[k] : vec2{1.0f, 0.0f};
-            const vec2 qb = phB != nullptr ? phB[k] : vec2{1.0f, 0.0f};
+            const vec2 qa = (phA != nullptr && !tail) ? phA[k] : vec2{1.0f, 0.0f};
+            const vec2 qb = (phB != nullptr && !tail) ? phB[k] : vec2{1.0f, 0.0f};
             par = qa.x; pai = qa.y; pbr = qb.x; pbi = qb.y;
         } else {
             const cpx a = cload(za + 2 * i);
@@ -186,8 +186,11 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
         }
         const float yar = cre(lin) * par, yai = cre(lin) * pai;
         const float ybr = cim(lin) * pbr, ybi = cim(lin) * pbi;
-        cstore(za + 2 * i, cmake(yar - ybi, -(yai + ybr)));   // conj(Y_A + i Y_B)
-        cstore(zc - 2 * i, cmake(yar + ybi, yai - ybr));      // conj(conj(Y_A) + i conj(Y_B))
+        if (nyq) cstore(za + 2 * i, cmake(0.0f, 0.0f));
+        if (!tail) {
+            cstore(za + 2 * i, cmake(yar - ybi, -(yai + ybr)));   // conj(Y_A + i Y_B)
+            cstore(zc - 2 * i, cmake(yar + ybi, yai - ybr));      // conj(conj(Y_A) + i conj(Y_B))
+        }
     }
 }
 
