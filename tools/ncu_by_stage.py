@@ -14,6 +14,9 @@ import subprocess
 import sys
 import tempfile
 
+# NCU_KERNEL=<regex> selects one kernel of a multi-kernel report
+KFILTER = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+
 rep, so, kname = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
 F = float(sys.argv[4]) if len(sys.argv) > 4 else 301000.0
 tmp = tempfile.mkdtemp()
@@ -52,7 +55,7 @@ for l in lines:
         insts.append((int(m.group(1), 16), cf, cl, m.group(2)))
     if l.startswith("//---") or ".section" in l:
         if insts: break
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KFILTER, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; ix = {n: i for i, n in enumerate(h)}
 data = [r for r in rows[2:] if len(r) >= len(h)]

@@ -2,6 +2,9 @@
 """List the shared-memory instructions of a kernel with the most excessive (bank-conflict) wavefronts, with source lines.
 usage: python tools/ncu_smem_excess.py <rep.ncu-rep> <lib.so> <kernel-mangled-name> [frames]"""
 import csv, glob, io, os, re, subprocess, sys, tempfile
+
+# NCU_KERNEL=<regex> selects one kernel of a multi-kernel report
+KFILTER = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
 rep, so, kname = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
 F = float(sys.argv[4]) if len(sys.argv) > 4 else 301000.0
 tmp = tempfile.mkdtemp()
@@ -18,7 +21,7 @@ for l in lines:
     if m: cf, cl = os.path.basename(m.group(1)), int(m.group(2)); continue
     m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*);", l)
     if m: loc[int(m.group(1), 16)] = (cf, cl)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KFILTER, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; ix = {n: i for i, n in enumerate(h)}
 data = [r for r in rows[2:] if len(r) >= len(h)]

@@ -4,12 +4,16 @@
 import collections
 import csv
 import io
+import os
 import subprocess
 import sys
 
+# NCU_KERNEL=<regex> selects one kernel of a multi-kernel report
+KFILTER = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+
 rep = sys.argv[1]
 F = float(sys.argv[2]) if len(sys.argv) > 2 else 301000.0
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + KFILTER, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
 m = dict(zip(hdr, vals))
@@ -35,7 +39,7 @@ for k in keys:
 for k in hdr:
     if "issue_stalled" in k and "per_issue_active" in k and "not_issued" not in k.lower():
         print("%-75s %s" % (k.replace("smsp__average_warps_issue_stalled_", "stall ").replace("_per_issue_active.ratio", ""), m[k]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KFILTER, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 ix = {n: i for i, n in enumerate(h)}
