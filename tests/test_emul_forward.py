@@ -229,3 +229,36 @@ def test_f4_ragged_and_zero_padded_lengths(emul, n_valid, nvs):
         want = np.stack([ref[:, 20 * i:20 * i + 20] for i in range(ns)])
         assert np.max(np.abs(got[k] - want)) <= TOL_DB, k
         assert abs(got["max"][("speech", "noise", "mixed").index(k)] - ref.max()) <= TOL_DB
+
+
+def test_f4_stage_code_fuzz_against_oracle(emul):
+    """Property test (hypothesis): random valid lengths (edge / interior group mixes, zero padding), slice counts, input
+    scales (unit ... int16) and SNR factors -- the F4 stage code stays within the 1e-3 dB gate of the float64 oracle and
+    reproduces the mixture PCM; the running max equals the oracle's max over ALL frames (dp:94)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @hyp.settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(nvs=st.integers(1, 4), frac=st.floats(0.11, 1.0), log_scale=st.floats(-2.0, 4.5), fac=st.floats(0.05, 8.0),
+               seed=st.integers(0, 10 ** 6))
+    def check(nvs, frac, log_scale, fac, seed):
+        L = 3200 * nvs
+        nv = max(330, min(L, int(frac * L)))
+        rng = np.random.RandomState(seed)
+        scale = 10.0 ** log_scale
+        s = np.zeros(L, np.float32)
+        nf = np.zeros(L, np.float32)
+        s[:nv] = (O.synth_speech(nv, SR, seed) * scale).astype(np.float32)
+        nf[:nv] = (0.05 * scale * rng.randn(nv)).astype(np.float32)
+        ns = min(nvs, (1 + L // 160) // 20)
+        got = _run_emul4(emul, s, nf, L, np.float32(fac), ns, valid=nv)
+        f = float(np.float32(fac))
+        mix = s.astype(np.float64) + f * nf.astype(np.float64)
+        assert np.max(np.abs(got["mixed_pcm"] - mix)) <= TOL_PCM * max(np.max(np.abs(mix)), 1e-30)
+        for k, x in (("speech", s.astype(np.float64)), ("noise", f * nf.astype(np.float64)), ("mixed", mix)):
+            ref, _ = O.signal_to_spectrogram(O.AudioSignal(x, SR), 640, 160)
+            want = np.stack([ref[:, 20 * i:20 * i + 20] for i in range(ns)])
+            assert np.max(np.abs(got[k] - want)) <= TOL_DB, (k, nvs, nv, scale, fac)
+            assert abs(got["max"][("speech", "noise", "mixed").index(k)] - ref.max()) <= TOL_DB
+
+    check()
