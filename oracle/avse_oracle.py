@@ -13,7 +13,8 @@ vectors or fixtures for this path.  This file therefore *restates* the published
 algorithms of those calls in float64 numpy, function for function with the
 reference call sites (cited as ``dp:LINE`` = /root/reference/data_processor.py),
 and is pinned instead by independent cross-checks in tests/test_oracle.py
-(torch.stft / torch.istft / torchaudio Slaney filterbank / algebraic identities).
+(torch.stft / torch.istft / torchaudio Slaney filterbank / transformers.audio_utils'
+librosa-compatible filterbank, amplitude_to_db and log-mel pipeline / algebraic identities).
 
 Everything is float64 unless stated otherwise.
 """
