@@ -167,25 +167,25 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
         const cpx y0 = cload(yb + 4 * t.x), y1 = cload(yb + 4 * t.y);
         // (lin_A, lin_B) = w0 (c_A, c_B)[b0] + w1 (c_A, c_B)[b1]
         const cpx lin = cfma_s(y1, bits_to_float(t.w), cmul_s(y0, bits_to_float(t.z)));
-        float par, pai, pbr, pbi;
+        float yar, yai, ybr, ybi;      // Y_A = lin_A * phase_A, Y_B = lin_B * phase_B
         if (EXT) {
             const int k = POST_CHUNK * p + i;
             const vec2 qa = (phA != nullptr && !tail) ? phA[k] : vec2{1.0f, 0.0f};
             const vec2 qb = (phB != nullptr && !tail) ? phB[k] : vec2{1.0f, 0.0f};
-            par = qa.x; pai = qa.y; pbr = qb.x; pbi = qb.y;
+            yar = cre(lin) * qa.x; yai = cre(lin) * qa.y;
+            ybr = cim(lin) * qb.x; ybi = cim(lin) * qb.y;
         } else {
             const cpx a = cload(za + 2 * i);
             const cpx c = cload(zc - 2 * i);
-            const cpx xa = cfma_pp(c, cmake(1.0f, -1.0f), a);             // 2 X_A
-            const cpx xb = cmake(cim(a) + cim(c), cre(c) - cre(a));       // 2 X_B
-            const float na = cre(xa) * cre(xa) + cim(xa) * cim(xa), nb = cre(xb) * cre(xb) + cim(xb) * cim(xb);
-            const float ia = inv_rsqrt(na), ib = inv_rsqrt(nb);
+            const cpx xa = cfma_pp(c, cmake(1.0f, -1.0f), a);             // 2 X_A = Z_k + conj Z_{N-k}
+            const cpx xn = cfma_pp(c, cmake(-1.0f, 1.0f), a);             // 2 i X_B = Z_k - conj Z_{N-k}:  2 X_B = (xn.im, -xn.re)
+            const float na = cre(xa) * cre(xa) + cim(xa) * cim(xa), nb = cre(xn) * cre(xn) + cim(xn) * cim(xn);
+            // lin * X / |X| with the scale lin / |X| formed once per frame; 1 + 0j where X == 0 (librosa.magphase, dp:80)
+            const float sa = cre(lin) * inv_rsqrt(na), sb = cim(lin) * inv_rsqrt(nb);
             const bool okA = na > 0.0f && liveA, okB = nb > 0.0f && liveB;
-            par = okA ? cre(xa) * ia : 1.0f; pai = okA ? cim(xa) * ia : 0.0f;
-            pbr = okB ? cre(xb) * ib : 1.0f; pbi = okB ? cim(xb) * ib : 0.0f;
+            yar = okA ? cre(xa) * sa : cre(lin); yai = okA ? cim(xa) * sa : 0.0f;
+            ybr = okB ? cim(xn) * sb : cim(lin); ybi = okB ? -cre(xn) * sb : 0.0f;
         }
-        const float yar = cre(lin) * par, yai = cre(lin) * pai;
-        const float ybr = cim(lin) * pbr, ybi = cim(lin) * pbi;
         if (nyq) cstore(za + 2 * i, cmake(0.0f, 0.0f));
         if (!tail) {
             cstore(za + 2 * i, cmake(yar - ybi, -(yai + ybr)));   // conj(Y_A + i Y_B)
