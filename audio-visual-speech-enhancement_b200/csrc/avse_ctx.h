@@ -27,6 +27,7 @@ struct avse_ctx {
     avse::GenericHost gen;
     avse::GenericDev gd;
     void* gbase = nullptr;        // device allocation holding the generic tables
+    size_t gen_fwd_smem_set = 0, gen_inv_smem_set = 0;   // dynamic shared-memory opt-in already requested through this context
 };
 
 int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* stream);

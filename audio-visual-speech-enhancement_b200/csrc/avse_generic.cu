@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(256) avse_generic_inverse_ola_kernel(const __g
     }
 }
 
+constexpr size_t kGenMaxSmem = 227 * 1024;   // opt-in ceiling of sm_100 (n_fft <= 4096 needs <= 157 KB)
+
 size_t gen_fwd_smem(const GenericGeo& q) { return (size_t)q.n_fft * 32 + (size_t)q.bins * 12 + 32; }
 size_t gen_inv_smem(const GenericGeo& q) {
     const size_t nx = q.n_fft > q.n_inv ? q.n_fft : q.n_inv;
@@ -328,8 +330,11 @@ int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* str
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
     const size_t smem = gen_fwd_smem(q);
-    CUDA_TRY(cudaFuncSetAttribute(avse_generic_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(avse_generic_forward_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > ctx->gen_fwd_smem_set) {   // the opt-in is per function: only ever raise it (contexts of different geometry coexist)
+        CUDA_TRY(cudaFuncSetAttribute(avse_generic_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenMaxSmem));
+        CUDA_TRY(cudaFuncSetAttribute(avse_generic_forward_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenMaxSmem));
+        ctx->gen_fwd_smem_set = kGenMaxSmem;
+    }
     dim3 grid((unsigned)P.T, (unsigned)a.B);
     if (a.sample_format == AVSE_SAMPLE_I16) avse_generic_forward_kernel<short><<<grid, GEN_THREADS, smem, (cudaStream_t)stream>>>(P);
     else avse_generic_forward_kernel<float><<<grid, GEN_THREADS, smem, (cudaStream_t)stream>>>(P);
@@ -364,7 +369,10 @@ int avse_generic_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* str
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_inverse: current device differs from the context's device");
     const size_t smem = gen_inv_smem(q);
-    CUDA_TRY(cudaFuncSetAttribute(avse_generic_inverse_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > ctx->gen_inv_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(avse_generic_inverse_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenMaxSmem));
+        ctx->gen_inv_smem_set = kGenMaxSmem;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     avse_generic_inverse_frame_kernel<<<dim3((unsigned)P.T_use, (unsigned)a.B), GEN_THREADS, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
