@@ -43,7 +43,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1000, help="utterances per GPU per step")
+    ap.add_argument("--seconds", type=float, default=3.0, help="utterance duration (BASELINE configs[4] long form: 60)")
+    ap.add_argument("--snr-sweep", action="store_true", help="per-utterance SNR cycling through -10, -5, 0, 5, 10 dB (configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0: auto)")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU baseline (0: every host thread)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks per step in the host pipeline")
     ap.add_argument("--e2e-streams", type=int, default=3)
@@ -65,18 +68,44 @@ def _cpu_one(seed):
     return time.perf_counter() - t0
 
 
+SNR_SWEEP = (-10.0, -5.0, 0.0, 5.0, 10.0)
+SWEEP = False
+
+
+def set_workload(seconds, sweep):
+    """Utterance duration / SNR policy of this run (module globals: the forked CPU workers inherit them)."""
+    global UTT_SECONDS, L, N_VIDEO_SLICES, SWEEP
+    UTT_SECONDS = float(seconds)
+    N_VIDEO_SLICES = int(UTT_SECONDS * FPS / 5)           # dp:24-25: 5 video frames per 200 ms slice
+    L = 3200 * N_VIDEO_SLICES                             # dp:36-37
+    SWEEP = bool(sweep)
+
+
 def _cpu_prepare(n):
     import numpy as np
     from oracle import avse_oracle as O
-    return [(O.synth_speech(L, SR, i).astype(np.float32), O.synth_noise(L, i).astype(np.float32)) for i in range(n)]
+    return [(O.synth_speech(L, SR, i).astype(np.float32), O.synth_noise(L, i).astype(np.float32),
+             SNR_SWEEP[i % 5] if SWEEP else 0.0) for i in range(n)]
 
 
 def _cpu_work(pair):
     from oracle import avse_oracle as O
     s = O.AudioSignal(pair[0], SR)
     n = O.AudioSignal(pair[1], SR)
-    out = O.preprocess_audio_pair_signals(s, n, SLICE_MS, N_VIDEO_SLICES, FPS, snr_db=0)
+    out = O.preprocess_audio_pair_signals(s, n, SLICE_MS, N_VIDEO_SLICES, FPS, snr_db=pair[2])
     return out[0].shape[0]
+
+
+def _cpu_fwd_keep(pair):
+    from oracle import avse_oracle as O
+    out = O.preprocess_audio_pair_signals(O.AudioSignal(pair[0], SR), O.AudioSignal(pair[1], SR), SLICE_MS, N_VIDEO_SLICES, FPS,
+                                          snr_db=pair[2])
+    return out[3].get_data(), out[1]
+
+
+def _cpu_inv_work(item):
+    from oracle import avse_oracle as O
+    return O.reconstruct_speech_signal(O.AudioSignal(item[0], SR), item[1], FPS).get_number_of_samples()
 
 
 _CPU_LIMIT = None
@@ -124,11 +153,25 @@ def cpu_throughput(n_utts, procs):
     return n_utts * UTT_SECONDS / dt, dt
 
 
+def cpu_inverse_throughput(n_utts, procs):
+    """audio-s/s of the oracle's reconstruct_speech_signal (dp:60-74) over n_utts utterances (inputs prepared untimed)."""
+    import multiprocessing as mp
+    if n_utts not in _CPU_PAIRS:
+        _CPU_PAIRS[n_utts] = _cpu_prepare(n_utts)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs, initializer=_cpu_init) as pool:
+        items = pool.map(_cpu_fwd_keep, _CPU_PAIRS[n_utts])
+        t0 = time.perf_counter()
+        pool.map(_cpu_inv_work, items, chunksize=max(1, n_utts // (4 * procs)))
+        dt = time.perf_counter() - t0
+    return n_utts * UTT_SECONDS / dt, dt
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = host_cores()             # every host thread available (the reference itself hard-codes Pool(16), dp:194)
+    procs = args.cpu_procs or host_cores()   # every host thread available (the reference itself hard-codes Pool(16), dp:194)
     n = args.cpu_sample or args.batch   # one step = the GPU arm's per-GPU batch (1,000 x 3 s: ~20-25 core-seconds)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -147,14 +190,18 @@ def run_reference_arm(args):
                          "sample": "%d x 3 s pairs per step, oracle/avse_oracle.py preprocess_audio_pair_signals (float64 numpy), "
                                    "multiprocessing Pool(%d) = all host threads (the reference hard-codes Pool(16), dp:194)" % (n, procs)},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "inverse": None if args.no_inverse else {"value": cpu_inverse_throughput(min(n, 256), procs)[0], "unit": "audio-s/s",
+                                                  "what": "oracle reconstruct_speech_signal (dp:60-74), same pool"},
         "note": "reference's librosa/mediaio are not installable here; this is the float64 numpy restatement (oracle/) of dp:119-139",
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(batch, gpus):
+    tag = "BASELINE configs[1]" if (UTT_SECONDS == 3.0 and not SWEEP) else ("BASELINE configs[4] (long form)" if UTT_SECONDS >= 30 else "custom")
     return {
-        "workload": "BASELINE configs[1]: %d x 3 s 16 kHz utterances + white noise @ 0 dB per GPU; mix + 3x log-mel (n_fft 640, hop 160, 80 mel) + top_db floor + 15 AV-aligned (80,20) slices + mixed PCM" % batch,
+        "workload": "%s: %d x %g s 16 kHz utterances + white noise @ %s per GPU; mix + 3x log-mel (n_fft 640, hop 160, 80 mel) + top_db floor + %d AV-aligned (80,20) slices + mixed PCM" % (
+            tag, batch, UTT_SECONDS, "SNR sweep -10..+10 dB" if SWEEP else "0 dB", N_VIDEO_SLICES),
         "utterances_per_gpu": batch, "seconds_per_utterance": UTT_SECONDS, "sharding": "by utterance, no collective",
         "n_gpus": gpus,
         "l2": "per-step working set %.0f MB (inputs %.0f MB + outputs %.0f MB) > 126 MB L2; no explicit flush" % (
@@ -288,6 +335,7 @@ def bind_to_gpu_numa_node(index):
 
 def main():
     args = parse_args()
+    set_workload(args.seconds, args.snr_sweep)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -311,12 +359,13 @@ def main():
     speech, noise = synth_batch(torch, B, device, seed=rank)
     T = eng.n_frames(L)
     out = {}
+    snr = torch.tensor([SNR_SWEEP[i % 5] for i in range(B)], dtype=torch.float32, device=device) if SWEEP else None
 
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     def step(i=None):
-        factor, max_key = eng.snr_factor(speech, noise, max_key=out.get("max_key"))
+        factor, max_key = eng.snr_factor(speech, noise, snr_db=snr, max_key=out.get("max_key"))
         if i is not None:
             ev_k0[i].record()
         res = eng.forward_raw(speech, noise, L=L, factor=factor, n_slices=N_VIDEO_SLICES, max_key=max_key, out=out)
@@ -403,7 +452,7 @@ def main():
         inv_ms = float(tinv[0])
         t_use = min(20 * N_VIDEO_SLICES, T)
         inv_bytes = B * t_use * INV_BYTES_PER_FRAME
-        line["inverse"] = {"workload": "BASELINE configs[3]: %d enhanced mel-spectrograms (15,80,20) + mixture PCM -> waveforms per GPU" % B,
+        line["inverse"] = {"workload": "BASELINE configs[3]: %d enhanced mel-spectrograms (%d,80,20) + mixture PCM -> waveforms per GPU" % (B, N_VIDEO_SLICES),
                            "value": world * B * UTT_SECONDS / (inv_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": inv_ms,
                            "roofline": {"bound": "hbm", "kernel": "avse_inverse_kernel", "achieved": inv_bytes / (inv_ms * 1e-3) / 1e9,
                                         "peak": peak, "unit": "GB/s", "frac": inv_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
@@ -488,7 +537,7 @@ def main():
             os.sched_setaffinity(0, range(os.cpu_count() or 1))     # the CPU baseline gets every host thread again
         except Exception:
             pass
-        procs = host_cores()
+        procs = args.cpu_procs or host_cores()
         n = args.cpu_sample or B     # the whole per-GPU batch once: ~20-25 core-seconds of float64 numpy
         v, dt = cpu_throughput(n, procs)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port",
