@@ -1,5 +1,6 @@
 // CUDA kernels (sm_100a) + C ABI of the forward spectral path.  See include/avse_b200.h.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -202,19 +203,29 @@ template <> struct Sample4<short> {
     }
 };
 
-template <typename S>
+// One thread-block CLUSTER per utterance: the P CTAs of a cluster each reduce a contiguous part of the utterance and
+// rank 0 gathers their partial sums through distributed shared memory -- no scratch buffer, no second launch.  P = 1 for
+// the 3 s utterances of configs 1-3 (1 000 CTAs already fill the GPU); long-form audio (config 5: 64 x 60 s per GPU)
+// gets P = 8 so that all 148 SMs pull on HBM instead of 64.
+template <typename S, bool CLUSTER>
 __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restrict__ speech, const S* __restrict__ noise,
                                                               long long stride, const int* __restrict__ lengths, int L,
                                                               const float* __restrict__ snr_db, float* __restrict__ factor_out,
                                                               int* __restrict__ max_key, int* __restrict__ min_key) {
-    const int u = blockIdx.x;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int P = CLUSTER ? (int)cluster.num_blocks() : 1;
+    const int part = CLUSTER ? (int)cluster.block_rank() : 0;
+    const int u = blockIdx.x / P;
     const int n = lengths ? lengths[u] : L;
     const S* s = speech + (size_t)u * stride;
     const S* z = noise + (size_t)u * stride;
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     constexpr size_t AL = sizeof(typename Sample4<S>::vec) - 1;
     const int n4 = ((((size_t)s | (size_t)z) & AL) == 0) ? (n >> 2) : 0;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int per4 = (n4 + P - 1) / P;                       // this CTA's share of the vector part
+    const int lo4 = part * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+    for (int i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) {
         float sv[4], zv[4];
         Sample4<S>::load(s, i, sv);
         Sample4<S>::load(z, i, zv);
@@ -223,11 +234,13 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restric
         b0 += (double)zv[0] + (double)zv[1] + (double)zv[2] + (double)zv[3];
         b1 += (double)zv[0] * zv[0] + (double)zv[1] * zv[1] + (double)zv[2] * zv[2] + (double)zv[3] * zv[3];
     }
-    for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
-        const double sv = (double)s[i], zv = (double)z[i];
-        a0 += sv; a1 += sv * sv; b0 += zv; b1 += zv * zv;
-    }
+    if (part == P - 1)                                       // scalar tail (and the whole signal when it is unaligned)
+        for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+            const double sv = (double)s[i], zv = (double)z[i];
+            a0 += sv; a1 += sv * sv; b0 += zv; b1 += zv * zv;
+        }
     __shared__ double red[4][8];
+    __shared__ double partial[4];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
@@ -238,17 +251,50 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restric
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { red[0][w] = a0; red[1][w] = a1; red[2][w] = b0; red[3][w] = b1; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-        for (int i = 0; i < 8; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; t3 += red[3][i]; }
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        partial[threadIdx.x] = t;
+    }
+    if (CLUSTER) cluster.sync();                             // every CTA's partial sums are visible cluster-wide
+    else __syncthreads();
+    if (part == 0 && threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < P; ++r) {
+            const double* q = CLUSTER ? cluster.map_shared_rank(partial, r) : partial;   // distributed shared memory
+            t[0] += q[0]; t[1] += q[1]; t[2] += q[2]; t[3] += q[3];
+        }
         const double inv = 1.0 / (double)n;
-        const double ms = t0 * inv, mn = t2 * inv;
-        const double vs = t1 * inv - ms * ms, vn = t3 * inv - mn * mn;
+        const double ms = t[0] * inv, mn = t[2] * inv;
+        const double vs = t[1] * inv - ms * ms, vn = t[3] * inv - mn * mn;
         const double db = snr_db ? (double)snr_db[u] : 0.0;
         factor_out[u] = (float)(sqrt(vs / vn) * pow(10.0, -db / 20.0));
         if (max_key) { max_key[3 * u] = (int)0x80000000; max_key[3 * u + 1] = (int)0x80000000; max_key[3 * u + 2] = (int)0x80000000; }
         if (min_key) { min_key[3 * u] = 0x7fffffff; min_key[3 * u + 1] = 0x7fffffff; min_key[3 * u + 2] = 0x7fffffff; }
     }
+    if (CLUSTER) cluster.sync();                             // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+template <typename S>
+static cudaError_t launch_snr_factor(int B, int P, cudaStream_t st, const S* speech, const S* noise, long long stride, const int* lengths,
+                                     int L, const float* snr_db, float* factor_out, int* max_key, int* min_key) {
+    if (P == 1) {       // plain launch: cluster launches carry extra scheduling constraints
+        avse_snr_factor_kernel<S, false><<<B, 256, 0, st>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * P));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, avse_snr_factor_kernel<S, true>, speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
 }
 
 extern "C" int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* noise, int sample_format, long long stride,
@@ -256,13 +302,18 @@ extern "C" int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* no
                                void* stream) {
     if (!ctx || !speech || !noise || !factor_out) return avse_fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
     if (B <= 0 || L <= 0 || stride < L) return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
+    // cluster size: enough CTAs to occupy every SM a few times over, each with >= 64 K samples, at most 8 (portable limit)
+    int P = 1;
+    while (P < 8 && (long long)B * P < 4LL * ctx->num_sms && L / (2 * P) >= 65536) P *= 2;
+    cudaError_t e;
     if (sample_format == AVSE_SAMPLE_F32)
-        avse_snr_factor_kernel<float><<<B, 256, 0, (cudaStream_t)stream>>>((const float*)speech, (const float*)noise, stride, lengths, L,
-                                                                            snr_db, factor_out, max_key, min_key);
+        e = launch_snr_factor<float>(B, P, (cudaStream_t)stream, (const float*)speech, (const float*)noise, stride, lengths, L, snr_db,
+                                     factor_out, max_key, min_key);
     else if (sample_format == AVSE_SAMPLE_I16)
-        avse_snr_factor_kernel<short><<<B, 256, 0, (cudaStream_t)stream>>>((const short*)speech, (const short*)noise, stride, lengths, L,
-                                                                            snr_db, factor_out, max_key, min_key);
+        e = launch_snr_factor<short>(B, P, (cudaStream_t)stream, (const short*)speech, (const short*)noise, stride, lengths, L, snr_db,
+                                     factor_out, max_key, min_key);
     else return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sample_format");
+    if (e != cudaSuccess) return avse_cuda_fail(e, "avse_snr_factor launch");
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
