@@ -121,3 +121,17 @@ print("generic-at-640 ok")
     env = dict(os.environ, AVSE_FORCE_GENERIC="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "generic-at-640 ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_generic_int16_in_and_out(mod):
+    eng = mod.SpectralEngine(16000, 50.0, 200, device="cuda:0")
+    rng = np.random.RandomState(3)
+    s16 = (rng.randn(2, 19200) * 3000).astype(np.int16)
+    n16 = (rng.randn(2, 19200) * 900).astype(np.int16)
+    a = eng.preprocess_pairs(_d(s16), _d(n16), 6)
+    b = eng.preprocess_pairs(_d(s16.astype(np.float32)), _d(n16.astype(np.float32)), 6)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)                       # int16 -> float is exact
+    f32 = eng.reconstruct(a[3], a[0] + 6.0)
+    i16 = eng.reconstruct(a[3], a[0] + 6.0, out_dtype=torch.int16)
+    assert torch.equal(i16, torch.clamp(f32, -32768.0, 32767.0).to(torch.int32).to(torch.int16))
