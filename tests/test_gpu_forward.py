@@ -231,3 +231,42 @@ def test_host_pipeline_equals_device_batch(eng):
     for got, ref in ((outs[0], ref0), (outs[1], ref1)):
         for a, b in zip(got, ref):
             assert torch.equal(a, b.cpu())
+
+
+def test_gpu_fuzz_ragged_batch_against_oracle(eng):
+    """40 utterances with random lengths (tile ranges of different warps start and end anywhere: edge groups, prefetch and
+    software-pipelined loads across utterance boundaries), scales from 1e-2 to int16 range and SNRs in [-10, 10] dB: every
+    one must match its own float64 oracle; then the inverse on the GPU's own outputs."""
+    rng = np.random.RandomState(2024)
+    B, nvs = 40, 10
+    Lmax = 3200 * nvs
+    lens = rng.randint(400, Lmax + 1, size=B).astype(np.int32)
+    lens[:3] = [Lmax, 321 + 9, Lmax - 1]
+    scales = 10.0 ** rng.uniform(-2.0, 4.4, size=B)
+    snrs = rng.uniform(-10.0, 10.0, size=B).astype(np.float32)
+    S = np.zeros((B, Lmax), np.float32)
+    Z = np.zeros((B, Lmax), np.float32)
+    for i in range(B):
+        n = int(lens[i])
+        S[i, :n] = (O.synth_speech(n, SR, 700 + i) * scales[i]).astype(np.float32)
+        Z[i, :n] = (O.synth_noise(n, 700 + i) * scales[i]).astype(np.float32)
+    mixed, speech, noise, pcm = eng.preprocess_pairs(_dev(S), _dev(Z), nvs, lengths=_dev(lens), snr_db=_dev(snrs))
+    rec = eng.reconstruct(pcm, speech, lengths=None)
+    worst = 0.0
+    for i in range(B):
+        n = int(lens[i])
+        sp = O.AudioSignal(S[i, :n].astype(np.float64), SR)
+        nz = O.AudioSignal(Z[i, :n].astype(np.float64), SR)
+        r_mixed, r_speech, r_noise, r_sig = O.preprocess_audio_pair_signals(sp, nz, 200, nvs, FPS, snr_db=float(snrs[i]))
+        for name, got, ref in (("mixed", mixed, r_mixed), ("speech", speech, r_speech), ("noise", noise, r_noise)):
+            err = np.max(np.abs(got[i].cpu().numpy() - ref))
+            worst = max(worst, err)
+            assert err <= TOL_DB, (i, name, n, scales[i], snrs[i], err)
+        rp = r_sig.get_data()
+        scale = np.max(np.abs(rp))
+        assert np.max(np.abs(pcm[i].cpu().numpy() - rp)) <= TOL_PCM * scale, i
+        if i % 4 == 0:
+            sig = O.AudioSignal(pcm[i].double().cpu().numpy(), SR)
+            want = O.reconstruct_speech_signal(sig, speech[i].double().cpu().numpy(), FPS).get_data()
+            assert np.max(np.abs(rec[i].cpu().numpy() - want)) <= TOL_PCM * scale, (i, "recon")
+    assert worst > 0.0
