@@ -26,6 +26,8 @@ class ForwardArgs(_c.Structure):
         ("stft_speech", _c.c_void_p),
         ("min_key", _c.c_void_p),
         ("sample_format", _c.c_int),
+        ("equalizer", _c.c_void_p),
+        ("noise_period", _c.c_void_p),
     ]
 
 
@@ -73,7 +75,7 @@ def load(build=True):
     lib.avse_version.restype = _c.c_char_p
     lib.avse_get_filterbank.argtypes = [vp, vp]
     lib.avse_get_filterbank.restype = i32
-    lib.avse_snr_factor.argtypes = [vp, vp, vp, i32, ll, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.avse_snr_factor.argtypes = [vp, vp, vp, i32, ll, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.avse_snr_factor.restype = i32
     lib.avse_forward.argtypes = [vp, _c.POINTER(ForwardArgs), vp]
     lib.avse_forward.restype = i32

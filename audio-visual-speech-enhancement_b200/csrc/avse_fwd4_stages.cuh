@@ -48,10 +48,21 @@ AVSE_HD void lane4_const_init(int lane, const float* s_win, const vec2* s_tw, La
     for (int j = 0; j < 16; ++j) { lc.win[j] = s_win[N2 * j + lane]; lc.tw[j] = s_tw[j * N2 + lane]; }
 }
 
-// A group is "interior" when its four frames exist and need neither reflection nor zero padding.
+// A group is "interior" when its four frames exist and need neither reflection nor zero padding, and -- for a
+// periodically tiled noise (dp:125-128, period_n > 0) -- when the group's 1 120 samples do not straddle a period
+// boundary.  nz_shift is then the offset that maps the group's sample indices into the stored period:
+// noise[i] = nz[i + nz_shift] for every i of the group.
 template <typename S>
-AVSE_HD bool group4_interior(const FwdTileT<S>& tl) {
-    return tl.nz != nullptr && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.vmin && tl.t0 + 3 < tl.T;
+AVSE_HD bool group4_interior(const FwdTileT<S>& tl, int& nz_shift) {
+    nz_shift = 0;
+    const int a = tl.t0 * HOP - HALF;                       // first sample of the group
+    if (!(tl.nz != nullptr && a >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.vmin && tl.t0 + 3 < tl.T)) return false;
+    if (tl.period_n > 0) {
+        const int q = a / tl.period_n;
+        if ((a + (F4 - 1) * HOP + NFFT - 1) / tl.period_n != q) return false;
+        nz_shift = -q * tl.period_n;
+    }
+    return true;
 }
 
 // DFT-16 over n1, twiddle, store column as rows [k1][n2] of one frame buffer (dst = frame + 2 n2).
@@ -64,19 +75,22 @@ AVSE_HD void p4_column(cpx (&x)[16], const vec2 (&tw)[16], float* dst) {
 
 // The 28 strided samples per signal that the lane's column needs for the four frames (interior groups).
 template <typename S>
-AVSE_HD void p4_load_raw(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
+AVSE_HD void p4_load_raw(const FwdTileT<S>& tl, int nz_shift, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
     const int o = tl.t0 * HOP - HALF + lane;
     const S* ps = tl.sp + o;
-    const S* pn = tl.nz + o;
+    const S* pn = tl.nz + (o + nz_shift);
 #pragma unroll
     for (int j = 0; j < RAW4; ++j) { rs[j] = (float)ps[N2 * j]; rn[j] = (float)pn[N2 * j]; }
 }
 
 // Rounds 0..3 of an interior group: frame f, column n2 = lane.  Also stores the mixture PCM (dp:133) of the
 // group's own four hops (strides 8..23 of the batch) for the residues n2 < 32.
+// The raw noise samples are scaled by the level equaliser tl.gain here, once per group (see FwdTileT).
 template <typename S>
-AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs)[RAW4], const float (&rn)[RAW4],
+AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs)[RAW4], float (&rn)[RAW4],
                                const Lane4Const& lc, float* frames) {
+#pragma unroll
+    for (int j = 0; j < RAW4; ++j) rn[j] *= tl.gain;
     if (tl.mixed_pcm != nullptr) {
         float* pm = tl.mixed_pcm + tl.t0 * HOP + lane;
 #pragma unroll
@@ -94,19 +108,21 @@ AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs
 // Round 4 of an interior group: lane = (f = lane / 8, r = lane % 8), column n2 = 32 + r of frame f.
 // Window / twiddles come from the CTA's shared tables (8 distinct addresses per load: one wavefront).
 template <typename S>
-AVSE_HD void p4_load_tail_raw(const FwdTileT<S>& tl, int lane, float (&rs)[16], float (&rn)[16]) {
+AVSE_HD void p4_load_tail_raw(const FwdTileT<S>& tl, int nz_shift, int lane, float (&rs)[16], float (&rn)[16]) {
     const int f = lane >> 3, n2 = 32 + (lane & 7);
     const int o = (tl.t0 + f) * HOP - HALF + n2;
     const S* ps = tl.sp + o;
-    const S* pn = tl.nz + o;
+    const S* pn = tl.nz + (o + nz_shift);
 #pragma unroll
     for (int j = 0; j < 16; ++j) { rs[j] = (float)ps[N2 * j]; rn[j] = (float)pn[N2 * j]; }
 }
 
 template <typename S>
-AVSE_HD void stage4_pass1_tail_compute(const FwdTileT<S>& tl, int lane, const float (&rs)[16], const float (&rn)[16], const float* s_win,
+AVSE_HD void stage4_pass1_tail_compute(const FwdTileT<S>& tl, int lane, const float (&rs)[16], float (&rn)[16], const float* s_win,
                                        const vec2* s_tw, float* frames) {
     const int f = lane >> 3, n2 = 32 + (lane & 7);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rn[j] *= tl.gain;
     vec2 tw[16];
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw[k1 * N2 + n2];
@@ -123,9 +139,9 @@ AVSE_HD void stage4_pass1_tail_compute(const FwdTileT<S>& tl, int lane, const fl
 }
 
 template <typename S>
-AVSE_HD void stage4_pass1_tail(const FwdTileT<S>& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+AVSE_HD void stage4_pass1_tail(const FwdTileT<S>& tl, int nz_shift, int lane, const float* s_win, const vec2* s_tw, float* frames) {
     float rs[16], rn[16];
-    p4_load_tail_raw(tl, lane, rs, rn);
+    p4_load_tail_raw(tl, nz_shift, lane, rs, rn);
     stage4_pass1_tail_compute(tl, lane, rs, rn, s_win, s_tw, frames);
 }
 
@@ -144,7 +160,7 @@ AVSE_HD void stage4_pass1_edge(const FwdTileT<S>& tl, int lane, const float* s_w
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             rs[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
-            rn[j] = load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n);
+            rn[j] = tl.gain * load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n, tl.period_n);
         }
         if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
 #pragma unroll

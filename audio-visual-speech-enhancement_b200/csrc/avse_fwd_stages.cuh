@@ -87,31 +87,41 @@ struct FwdTables {
 template <typename S>
 struct FwdTileT {
     const S* sp;         // speech samples of this utterance
-    const S* nz;         // noise samples (already fitted to the speech length), may be nullptr
+    const S* nz;         // noise samples, may be nullptr; period_n > 0: only the first period_n are read (see below)
     int L;               // signal length after pad/truncate (dp:37-42); reflect domain
     int valid_s;         // samples present in sp (zeros beyond, dp:40)
     int valid_n;         // samples present in nz
     int vmin;            // min(valid_s, valid_n) (0 when nz == nullptr): interior test
     int T;               // STFT frames: 1 + L / hop
     int t0;              // first frame of the group (multiple of FPG)
-    float factor;        // SNR factor (dp:130); 0 when nz == nullptr
+    // The SNR factor f (dp:130) is applied in two parts, f = gain * factor: the noise is multiplied by `gain`
+    // (= sqrt(var_s / var_n), the level equaliser) as it is LOADED, so that the two channels of the packed FFT
+    // z = s + i (gain n) carry equal power whatever the raw levels of the two files (float vs int16 scale ...):
+    // fp32 rounding of the louder channel would otherwise leak into the quieter one through the unpack
+    // S' = Z_k + conj Z_{N-k}.  The residual `factor` (= 10^(-snr/20), exactly 1 at the reference's 0 dB) is applied
+    // after the unpack by STFT linearity.
+    float gain;          // applied to the noise samples at load; 0 when nz == nullptr
+    float factor;        // residual applied to the (gain-scaled) noise spectrum / mel sums; 0 when nz == nullptr
+    int period_n;        // dp:125-128: noise[i] = nz[i mod period_n] (the reference doubles the noise until it covers the
+                         // speech, then truncates: a periodic tiling); 0: nz covers [0, valid_n) itself
     float* mixed_pcm;    // [L] or nullptr: s + f*n (dp:133), zero-padded / truncated to L
 };
 using FwdTile = FwdTileT<float>;
 
 template <typename S>
-AVSE_HD float load_sample_edge(const S* p, int i, int L, int valid) {
+AVSE_HD float load_sample_edge(const S* p, int i, int L, int valid, int period = 0) {
     // np.pad(y, n_fft//2, mode='reflect') on the length-L (zero padded) signal
     i = i < 0 ? -i : i;
     i = i >= L ? 2 * (L - 1) - i : i;
     i = i < 0 ? 0 : i;
-    return (p != nullptr && i < valid) ? (float)p[i] : 0.0f;
+    if (p == nullptr || i >= valid) return 0.0f;
+    return (float)p[period > 0 ? i % period : i];
 }
 
 // A group is "interior" when both of its frames exist and all their samples are present in both
 // signals without reflection or zero padding.
 AVSE_HD bool group_interior(const FwdTile& tl) {
-    return tl.nz != nullptr && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 1) * HOP + HALF <= tl.vmin && tl.t0 + 1 < tl.T;
+    return tl.nz != nullptr && tl.period_n == 0 && tl.t0 * HOP - HALF >= 0 && (tl.t0 + 1) * HOP + HALF <= tl.vmin && tl.t0 + 1 < tl.T;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -145,7 +155,7 @@ AVSE_HD void stage_pass1_interior(const FwdTile& tl, int lane, const float* s_wi
         const float* pn = tl.nz + o;
         cpx x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = cmake(ps[N2 * j], pn[N2 * j]);
+        for (int j = 0; j < 16; ++j) x[j] = cmake(ps[N2 * j], tl.gain * pn[N2 * j]);
         if (tl.mixed_pcm != nullptr) {
             // this frame's own hop: original samples [160 t, 160 t + 160) = strides n1 = 8..11
             float* pm = tl.mixed_pcm + o + HALF;
@@ -172,7 +182,8 @@ AVSE_HD void stage_pass1_edge(const FwdTile& tl, int lane, const float* s_win2, 
         cpx x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            x[j] = cmake(load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s), load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n));
+            x[j] = cmake(load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s),
+                         tl.gain * load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n, tl.period_n));
         if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

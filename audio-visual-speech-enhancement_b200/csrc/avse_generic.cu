@@ -34,12 +34,14 @@ struct GenInvParams {
 };
 
 template <typename S>
-__device__ __forceinline__ float gen_sample(const S* p, int i, int L, int valid) {
-    // np.pad(y, n_fft // 2, mode='reflect') on the length-L (zero padded, dp:40) signal
+__device__ __forceinline__ float gen_sample(const S* p, int i, int L, int valid, int period = 0) {
+    // np.pad(y, n_fft // 2, mode='reflect') on the length-L (zero padded, dp:40) signal; period > 0: the signal is the
+    // periodic tiling p[i mod period] of a shorter noise file (dp:125-128)
     i = i < 0 ? -i : i;
     i = i >= L ? 2 * (L - 1) - i : i;
     i = i < 0 ? 0 : i;
-    return (p != nullptr && i < valid) ? (float)p[i] : 0.0f;
+    if (p == nullptr || i >= valid) return 0.0f;
+    return (float)p[period > 0 ? i % period : i];
 }
 
 // out[k1 + n1 k2] = sum_n in[n] W^{n k},  n = n2 a + c2.  `out` may alias `in`; tmp is scratch (shared memory).
@@ -102,15 +104,19 @@ __global__ void __launch_bounds__(GEN_THREADS) avse_generic_forward_kernel(const
     float* mags = reinterpret_cast<float*>(Y + N);        // [3][bins]
     int* keys = reinterpret_cast<int*>(mags + 3 * bins);  // [3] max, [3] min
     const double2* W = reinterpret_cast<const double2*>(P.d.tw);
-    const int t = blockIdx.x, u = blockIdx.y;
+    const int u = blockIdx.x / P.T, t = blockIdx.x - u * P.T;     // linear (utterance, frame) index: B is not capped at 65 535
     const int tid = threadIdx.x;
     const bool have_noise = A.noise != nullptr;
 
     int vs = A.len_speech ? A.len_speech[u] : A.L;
     int vn = A.len_noise ? A.len_noise[u] : vs;
-    vs = vs < A.L ? vs : A.L;
-    vn = vn < A.L ? vn : A.L;
+    vs = vs < 0 ? 0 : (vs < A.L ? vs : A.L);
+    vn = vn < 0 ? 0 : (vn < A.L ? vn : A.L);
+    // the whole SNR factor is applied after the transform: this path computes in float64, where the level equaliser of the
+    // float32 kernels (avse_forward_args::equalizer) is not needed
     const float factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
+    int period = (have_noise && A.noise_period) ? A.noise_period[u] : 0;
+    if (period <= 0 || period >= vn) period = 0;
     const S* sp = reinterpret_cast<const S*>(A.speech) + (size_t)u * A.in_stride;
     const S* nz = have_noise ? reinterpret_cast<const S*>(A.noise) + (size_t)u * A.in_stride : nullptr;
 
@@ -118,13 +124,13 @@ __global__ void __launch_bounds__(GEN_THREADS) avse_generic_forward_kernel(const
     const int base = t * q.hop - N / 2;
     for (int n = tid; n < N; n += GEN_THREADS) {
         const double w = P.d.window[n];
-        X[n] = make_double2(gen_sample(sp, base + n, A.L, vs) * w, gen_sample(nz, base + n, A.L, vn) * w);
+        X[n] = make_double2(gen_sample(sp, base + n, A.L, vs) * w, gen_sample(nz, base + n, A.L, vn, period) * w);
     }
     if (A.mixed_pcm != nullptr && have_noise) {     // this frame's own hop of s + f n (dp:133), zero padded / truncated to L
         float* pm = A.mixed_pcm + (size_t)u * A.pcm_stride;
         const int hi = (t + 1) * q.hop < A.L ? (t + 1) * q.hop : A.L;
         for (int i = t * q.hop + tid; i < hi; i += GEN_THREADS)
-            pm[i] = (i < vs ? (float)sp[i] : 0.0f) + factor * (i < vn ? (float)nz[i] : 0.0f);
+            pm[i] = (i < vs ? (float)sp[i] : 0.0f) + factor * (i < vn ? (float)nz[period > 0 ? i % period : i] : 0.0f);
     }
     __syncthreads();
     gen_dft(X, Y, X, W, N, q.n1, q.n2);
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(GEN_THREADS) avse_generic_inverse_frame_kernel
     float* lin = amp + M;                            // [bins]
     const double2* W = reinterpret_cast<const double2*>(P.d.tw);
     const double2* Wi = reinterpret_cast<const double2*>(P.d.tw_inv);
-    const int t = blockIdx.x, u = blockIdx.y;
+    const int u = blockIdx.x / P.T_use, t = blockIdx.x - u * P.T_use;
     const int tid = threadIdx.x;
 
     // db_to_amplitude (dp:101)
@@ -268,11 +274,11 @@ __device__ __forceinline__ void gen_store(short* p, float v) {
 template <typename O>
 __global__ void __launch_bounds__(256) avse_generic_inverse_ola_kernel(const __grid_constant__ GenInvParams P) {
     const GenericGeo& q = P.geo;
-    const int u = blockIdx.y;
+    const int u = blockIdx.x;
     const int Ni = q.n_inv, hop = q.hop;
     const float* w = P.a.work + (size_t)u * P.a.work_stride;
     O* out = static_cast<O*>(P.a.out_pcm) + (size_t)u * P.a.out_stride;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P.out_len; o += gridDim.x * blockDim.x) {
+    for (int o = blockIdx.y * blockDim.x + threadIdx.x; o < P.out_len; o += gridDim.y * blockDim.x) {
         const int pp = o + Ni / 2;
         int t_hi = pp / hop;
         if (t_hi > P.T_use - 1) t_hi = P.T_use - 1;
@@ -316,7 +322,7 @@ int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* str
     P.geo = q;
     P.d = ctx->gd;
     P.T = avse_generic_frames(q, a.L);
-    if (P.T < 1 || P.T > 65535 * 16) return avse_fail(AVSE_E_ARG, "avse_forward: bad frame count");
+    if (P.T < 1 || (long long)P.T * a.B > 0x7fffffffLL) return avse_fail(AVSE_E_ARG, "avse_forward: B * frames exceeds 2^31; split the batch");
     if (a.layout == AVSE_LAYOUT_SLICES) {
         if (a.n_slices < 0 || (long long)a.n_slices * q.spss > P.T) return avse_fail(AVSE_E_ARG, "avse_forward: n_slices exceeds int(T / spss) (dp:50)");
         if (a.out_stride < (long long)a.n_slices * q.n_mels * q.spss) return avse_fail(AVSE_E_ARG, "avse_forward: out_stride too small");
@@ -325,7 +331,6 @@ int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* str
         if (a.out_stride < (long long)q.n_mels * a.ld_t) return avse_fail(AVSE_E_ARG, "avse_forward: out_stride too small");
     }
     if (a.mixed_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_forward: pcm_stride < L");
-    if (a.B > 65535) return avse_fail(AVSE_E_ARG, "avse_forward: B > 65535; split the batch");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_forward: current device differs from the context's device");
@@ -335,7 +340,7 @@ int avse_generic_forward(avse_ctx* ctx, const avse_forward_args* args, void* str
         CUDA_TRY(cudaFuncSetAttribute(avse_generic_forward_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenMaxSmem));
         ctx->gen_fwd_smem_set = kGenMaxSmem;
     }
-    dim3 grid((unsigned)P.T, (unsigned)a.B);
+    dim3 grid((unsigned)((long long)P.T * a.B));
     if (a.sample_format == AVSE_SAMPLE_I16) avse_generic_forward_kernel<short><<<grid, GEN_THREADS, smem, (cudaStream_t)stream>>>(P);
     else avse_generic_forward_kernel<float><<<grid, GEN_THREADS, smem, (cudaStream_t)stream>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -364,7 +369,7 @@ int avse_generic_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* str
     if (a.out_stride < P.out_len) return avse_fail(AVSE_E_ARG, "avse_inverse: out_stride < hop (T_use - 1)");
     if (a.phase && a.phase_stride < (long long)P.T_use * q.bins) return avse_fail(AVSE_E_ARG, "avse_inverse: phase_stride too small");
     if (!a.phase && !a.len_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_inverse: pcm_stride < L needs len_pcm");
-    if (a.B > 65535) return avse_fail(AVSE_E_ARG, "avse_inverse: B > 65535; split the batch");
+    if ((long long)P.T_use * a.B > 0x7fffffffLL) return avse_fail(AVSE_E_ARG, "avse_inverse: B * frames exceeds 2^31; split the batch");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != ctx->device) return avse_fail(AVSE_E_ARG, "avse_inverse: current device differs from the context's device");
@@ -374,12 +379,12 @@ int avse_generic_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* str
         ctx->gen_inv_smem_set = kGenMaxSmem;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    avse_generic_inverse_frame_kernel<<<dim3((unsigned)P.T_use, (unsigned)a.B), GEN_THREADS, smem, st>>>(P);
+    avse_generic_inverse_frame_kernel<<<dim3((unsigned)((long long)P.T_use * a.B)), GEN_THREADS, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     long long bx = (P.out_len + 255) / 256;
     if (bx > 1024) bx = 1024;
-    if (a.out_format == AVSE_SAMPLE_I16) avse_generic_inverse_ola_kernel<short><<<dim3((unsigned)bx, (unsigned)a.B), 256, 0, st>>>(P);
-    else avse_generic_inverse_ola_kernel<float><<<dim3((unsigned)bx, (unsigned)a.B), 256, 0, st>>>(P);
+    if (a.out_format == AVSE_SAMPLE_I16) avse_generic_inverse_ola_kernel<short><<<dim3((unsigned)a.B, (unsigned)bx), 256, 0, st>>>(P);
+    else avse_generic_inverse_ola_kernel<float><<<dim3((unsigned)a.B, (unsigned)bx), 256, 0, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -209,15 +209,24 @@ template <> struct Sample4<short> {
 // gets P = 8 so that all 148 SMs pull on HBM instead of 64.
 template <typename S, bool CLUSTER>
 __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restrict__ speech, const S* __restrict__ noise,
-                                                              long long stride, const int* __restrict__ lengths, int L,
+                                                              long long stride, const int* __restrict__ lengths,
+                                                              const int* __restrict__ noise_period, int L,
                                                               const float* __restrict__ snr_db, float* __restrict__ factor_out,
-                                                              int* __restrict__ max_key, int* __restrict__ min_key) {
+                                                              float* __restrict__ equalizer_out, int* __restrict__ max_key,
+                                                              int* __restrict__ min_key) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int P = CLUSTER ? (int)cluster.num_blocks() : 1;
     const int part = CLUSTER ? (int)cluster.block_rank() : 0;
     const int u = blockIdx.x / P;
-    const int n = lengths ? lengths[u] : L;
+    int n = lengths ? lengths[u] : L;
+    n = n < 0 ? 0 : (n > L ? L : n);                          // never read past the row (stride >= L is checked by the launcher)
+    // dp:125-128: a noise file shorter than the speech is doubled until it covers it and then truncated, i.e. tiled
+    // periodically: noise[i] = nz[i mod Pn].  Its sums over [0, n) follow from one pass over the stored period:
+    // sample i < Pn occurs q + (i < rem) times, n = q Pn + rem.
+    int Pn = noise_period ? noise_period[u] : n;
+    Pn = (Pn <= 0 || Pn > n) ? n : Pn;
+    const int q = Pn > 0 ? n / Pn : 0, rem = Pn > 0 ? n - q * Pn : 0;
     const S* s = speech + (size_t)u * stride;
     const S* z = noise + (size_t)u * stride;
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -225,20 +234,38 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restric
     const int n4 = ((((size_t)s | (size_t)z) & AL) == 0) ? (n >> 2) : 0;
     const int per4 = (n4 + P - 1) / P;                       // this CTA's share of the vector part
     const int lo4 = part * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
-    for (int i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) {
-        float sv[4], zv[4];
-        Sample4<S>::load(s, i, sv);
-        Sample4<S>::load(z, i, zv);
-        a0 += (double)sv[0] + (double)sv[1] + (double)sv[2] + (double)sv[3];
-        a1 += (double)sv[0] * sv[0] + (double)sv[1] * sv[1] + (double)sv[2] * sv[2] + (double)sv[3] * sv[3];
-        b0 += (double)zv[0] + (double)zv[1] + (double)zv[2] + (double)zv[3];
-        b1 += (double)zv[0] * zv[0] + (double)zv[1] * zv[1] + (double)zv[2] * zv[2] + (double)zv[3] * zv[3];
-    }
-    if (part == P - 1)                                       // scalar tail (and the whole signal when it is unaligned)
-        for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
-            const double sv = (double)s[i], zv = (double)z[i];
-            a0 += sv; a1 += sv * sv; b0 += zv; b1 += zv * zv;
+    if (Pn == n) {
+        for (int i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) {
+            float sv[4], zv[4];
+            Sample4<S>::load(s, i, sv);
+            Sample4<S>::load(z, i, zv);
+            a0 += (double)sv[0] + (double)sv[1] + (double)sv[2] + (double)sv[3];
+            a1 += (double)sv[0] * sv[0] + (double)sv[1] * sv[1] + (double)sv[2] * sv[2] + (double)sv[3] * sv[3];
+            b0 += (double)zv[0] + (double)zv[1] + (double)zv[2] + (double)zv[3];
+            b1 += (double)zv[0] * zv[0] + (double)zv[1] * zv[1] + (double)zv[2] * zv[2] + (double)zv[3] * zv[3];
         }
+        if (part == P - 1)                                   // scalar tail (and the whole signal when it is unaligned)
+            for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+                const double sv = (double)s[i], zv = (double)z[i];
+                a0 += sv; a1 += sv * sv; b0 += zv; b1 += zv * zv;
+            }
+    } else {
+        // tiled noise (rare: the noise file is shorter than the utterance): speech over [0, n), noise over its period
+        for (int i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) {
+            float sv[4];
+            Sample4<S>::load(s, i, sv);
+            a0 += (double)sv[0] + (double)sv[1] + (double)sv[2] + (double)sv[3];
+            a1 += (double)sv[0] * sv[0] + (double)sv[1] * sv[1] + (double)sv[2] * sv[2] + (double)sv[3] * sv[3];
+        }
+        if (part == P - 1)
+            for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) { const double sv = (double)s[i]; a0 += sv; a1 += sv * sv; }
+        const int perp = (Pn + P - 1) / P;
+        const int lop = part * perp, hip = lop + perp < Pn ? lop + perp : Pn;
+        for (int i = lop + threadIdx.x; i < hip; i += blockDim.x) {
+            const double zv = (double)z[i], w = (double)(q + (i < rem ? 1 : 0));
+            b0 += w * zv; b1 += w * zv * zv;
+        }
+    }
     __shared__ double red[4][8];
     __shared__ double partial[4];
 #pragma unroll
@@ -261,14 +288,23 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restric
     if (part == 0 && threadIdx.x == 0) {
         double t[4] = {0.0, 0.0, 0.0, 0.0};
         for (int r = 0; r < P; ++r) {
-            const double* q = CLUSTER ? cluster.map_shared_rank(partial, r) : partial;   // distributed shared memory
-            t[0] += q[0]; t[1] += q[1]; t[2] += q[2]; t[3] += q[3];
+            const double* qq = CLUSTER ? cluster.map_shared_rank(partial, r) : partial;   // distributed shared memory
+            t[0] += qq[0]; t[1] += qq[1]; t[2] += qq[2]; t[3] += qq[3];
         }
-        const double inv = 1.0 / (double)n;
-        const double ms = t[0] * inv, mn = t[2] * inv;
-        const double vs = t[1] * inv - ms * ms, vn = t[3] * inv - mn * mn;
-        const double db = snr_db ? (double)snr_db[u] : 0.0;
-        factor_out[u] = (float)(sqrt(vs / vn) * pow(10.0, -db / 20.0));
+        // n == 0 (empty files): the reference mixes two empty arrays and pads with zeros (dp:39-40); nothing is scaled,
+        // so any finite factor gives its result: use 0.  var(noise) == 0 with n > 0 gives inf / nan exactly like numpy.
+        float g = 0.0f, f = 0.0f;
+        if (n > 0) {
+            const double inv = 1.0 / (double)n;
+            const double ms = t[0] * inv, mn = t[2] * inv;
+            const double vs = t[1] * inv - ms * ms, vn = t[3] * inv - mn * mn;
+            const double db = snr_db ? (double)snr_db[u] : 0.0;
+            const double eq = sqrt(vs / vn);
+            g = (float)eq;
+            f = (float)(eq * pow(10.0, -db / 20.0));
+        }
+        factor_out[u] = f;
+        if (equalizer_out) equalizer_out[u] = g;
         if (max_key) { max_key[3 * u] = (int)0x80000000; max_key[3 * u + 1] = (int)0x80000000; max_key[3 * u + 2] = (int)0x80000000; }
         if (min_key) { min_key[3 * u] = 0x7fffffff; min_key[3 * u + 1] = 0x7fffffff; min_key[3 * u + 2] = 0x7fffffff; }
     }
@@ -277,9 +313,11 @@ __global__ void __launch_bounds__(256) avse_snr_factor_kernel(const S* __restric
 
 template <typename S>
 static cudaError_t launch_snr_factor(int B, int P, cudaStream_t st, const S* speech, const S* noise, long long stride, const int* lengths,
-                                     int L, const float* snr_db, float* factor_out, int* max_key, int* min_key) {
+                                     const int* noise_period, int L, const float* snr_db, float* factor_out, float* equalizer_out,
+                                     int* max_key, int* min_key) {
     if (P == 1) {       // plain launch: cluster launches carry extra scheduling constraints
-        avse_snr_factor_kernel<S, false><<<B, 256, 0, st>>>(speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
+        avse_snr_factor_kernel<S, false><<<B, 256, 0, st>>>(speech, noise, stride, lengths, noise_period, L, snr_db, factor_out,
+                                                            equalizer_out, max_key, min_key);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -294,12 +332,13 @@ static cudaError_t launch_snr_factor(int B, int P, cudaStream_t st, const S* spe
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, avse_snr_factor_kernel<S, true>, speech, noise, stride, lengths, L, snr_db, factor_out, max_key, min_key);
+    return cudaLaunchKernelEx(&cfg, avse_snr_factor_kernel<S, true>, speech, noise, stride, lengths, noise_period, L, snr_db, factor_out,
+                              equalizer_out, max_key, min_key);
 }
 
 extern "C" int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* noise, int sample_format, long long stride,
-                               const int* lengths, int B, int L, const float* snr_db, float* factor_out, int* max_key, int* min_key,
-                               void* stream) {
+                               const int* lengths, const int* noise_period, int B, int L, const float* snr_db, float* factor_out,
+                               float* equalizer_out, int* max_key, int* min_key, void* stream) {
     if (!ctx || !speech || !noise || !factor_out) return avse_fail(AVSE_E_ARG, "avse_snr_factor: NULL argument");
     if (B <= 0 || L <= 0 || stride < L) return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sizes");
     // cluster size: enough CTAs to occupy every SM a few times over, each with >= 64 K samples, at most 8 (portable limit)
@@ -307,11 +346,11 @@ extern "C" int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* no
     while (P < 8 && (long long)B * P < 4LL * ctx->num_sms && L / (2 * P) >= 65536) P *= 2;
     cudaError_t e;
     if (sample_format == AVSE_SAMPLE_F32)
-        e = launch_snr_factor<float>(B, P, (cudaStream_t)stream, (const float*)speech, (const float*)noise, stride, lengths, L, snr_db,
-                                     factor_out, max_key, min_key);
+        e = launch_snr_factor<float>(B, P, (cudaStream_t)stream, (const float*)speech, (const float*)noise, stride, lengths, noise_period, L,
+                                     snr_db, factor_out, equalizer_out, max_key, min_key);
     else if (sample_format == AVSE_SAMPLE_I16)
-        e = launch_snr_factor<short>(B, P, (cudaStream_t)stream, (const short*)speech, (const short*)noise, stride, lengths, L, snr_db,
-                                     factor_out, max_key, min_key);
+        e = launch_snr_factor<short>(B, P, (cudaStream_t)stream, (const short*)speech, (const short*)noise, stride, lengths, noise_period, L,
+                                     snr_db, factor_out, equalizer_out, max_key, min_key);
     else return avse_fail(AVSE_E_ARG, "avse_snr_factor: bad sample_format");
     if (e != cudaSuccess) return avse_cuda_fail(e, "avse_snr_factor launch");
     CUDA_TRY(cudaGetLastError());
@@ -347,6 +386,17 @@ constexpr int FWD_SMEM_F = FWD_SMEM_F_GEN > FWD_SMEM_F_SCAN ? FWD_SMEM_F_GEN : F
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_F * 4;
 static_assert((FWD_SM_MODE % 4) == 0 && (FWD_SM_TW % 2) == 0 && (FWD_SM_SCANLOC % 4) == 0, "table alignment");
 static_assert(FWD_CTAS * (FWD_SMEM_BYTES + 1024) <= 233472, "the resident CTAs must fit in shared memory");
+
+// f = gain * resid (see FwdTileT): gain = the level equaliser applied to the noise at load, resid = what is left for
+// the linear stages.  Without an equaliser array the whole factor is applied at load.
+struct MixGain { float gain, resid; };
+static __device__ __forceinline__ MixGain mix_gain(const avse_forward_args& A, int u) {
+    const float f = A.factor ? A.factor[u] : 1.0f;
+    MixGain m;
+    if (A.equalizer) { m.gain = A.equalizer[u]; m.resid = m.gain != 0.0f ? f / m.gain : 0.0f; }
+    else { m.gain = f; m.resid = 1.0f; }
+    return m;
+}
 
 struct FwdParams {
     avse_forward_args a;
@@ -395,8 +445,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
     int g = tile - u * P.G;
 
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
-    float factor = 0.0f;
-    int vs = 0, vn = 0;
+    float factor = 0.0f, gain = 0.0f;
+    int vs = 0, vn = 0, period = 0;
     bool fresh = true;
 
     auto flush_max = [&](int uu) {
@@ -416,9 +466,13 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
             fresh = false;
             vs = A.len_speech ? A.len_speech[u] : A.L;
             vn = A.len_noise ? A.len_noise[u] : vs;
-            vs = vs < A.L ? vs : A.L;
-            vn = vn < A.L ? vn : A.L;
-            factor = have_noise ? (A.factor ? A.factor[u] : 1.0f) : 0.0f;
+            vs = vs < 0 ? 0 : (vs < A.L ? vs : A.L);
+            vn = vn < 0 ? 0 : (vn < A.L ? vn : A.L);
+            const MixGain mg = mix_gain(A, u);
+            factor = have_noise ? mg.resid : 0.0f;
+            gain = have_noise ? mg.gain : 0.0f;
+            period = (have_noise && A.noise_period) ? A.noise_period[u] : 0;
+            if (period <= 0 || period >= vn) period = 0;      // the stored noise already covers [0, vn)
         }
         FwdTile tl;
         tl.sp = static_cast<const float*>(A.speech) + (size_t)u * A.in_stride;
@@ -430,6 +484,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
         tl.T = P.T;
         tl.t0 = g * FPG;
         tl.factor = factor;
+        tl.gain = gain;
+        tl.period_n = period;
         tl.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)u * A.pcm_stride : nullptr;
 
         // ---- pass 1 ----
@@ -559,8 +615,9 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
     float* mn = smem + F4_SM_MIN + warp * 96;
     mn[lane] = -neg_inf(); mn[32 + lane] = -neg_inf(); mn[64 + lane] = -neg_inf();
-    float factor = 0.0f;
-    int vs = 0, vn = 0;
+    // per-utterance scalars that ride along the tile loop, packed to keep the loop-carried register count down
+    struct Utt { int vs, vn, period; float gain, factor; };
+    Utt ut = {0, 0, 0, 0.0f, 0.0f};
     const S* in_speech = reinterpret_cast<const S*>(A.speech);
     const S* in_noise = reinterpret_cast<const S*>(A.noise);
     constexpr int LINE = 128 / (int)sizeof(S);        // samples per 128-byte line
@@ -602,34 +659,41 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     };
     // Software-pipelined tile loop: the raw samples of tile it+1 are loaded into registers before the dB stage of
     // tile it, so their HBM/L2 latency is covered by the dB arithmetic and stores instead of stalling pass 1.
-    auto load_utt = [&](int uu, int& ovs, int& ovn, float& of) {
-        ovs = A.len_speech ? A.len_speech[uu] : A.L;
-        ovn = A.len_noise ? A.len_noise[uu] : ovs;
-        ovs = ovs < A.L ? ovs : A.L;
-        ovn = ovn < A.L ? ovn : A.L;
-        of = A.factor ? A.factor[uu] : 1.0f;
+    auto load_utt = [&](int uu, Utt& o) {
+        o.vs = A.len_speech ? A.len_speech[uu] : A.L;
+        o.vn = A.len_noise ? A.len_noise[uu] : o.vs;
+        o.vs = o.vs < 0 ? 0 : (o.vs < A.L ? o.vs : A.L);
+        o.vn = o.vn < 0 ? 0 : (o.vn < A.L ? o.vn : A.L);
+        const MixGain mg = mix_gain(A, uu);
+        o.gain = mg.gain;
+        o.factor = mg.resid;
+        o.period = A.noise_period ? A.noise_period[uu] : 0;
+        if (o.period <= 0 || o.period >= o.vn) o.period = 0;      // the stored noise already covers [0, vn)
     };
-    auto make_tile = [&](int uu, int gg, int tvs, int tvn, float tf) {
+    auto make_tile = [&](int uu, int gg, const Utt& o) {
         FwdTileT<S> t;
         t.sp = in_speech + (size_t)uu * A.in_stride;
         t.nz = in_noise + (size_t)uu * A.in_stride;
         t.L = A.L;
-        t.valid_s = tvs;
-        t.valid_n = tvn;
-        t.vmin = tvs < tvn ? tvs : tvn;
+        t.valid_s = o.vs;
+        t.valid_n = o.vn;
+        t.vmin = o.vs < o.vn ? o.vs : o.vn;
         t.T = P.T;
         t.t0 = gg * F4;
-        t.factor = tf;
+        t.gain = o.gain;
+        t.factor = o.factor;
+        t.period_n = o.period;
         t.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)uu * A.pcm_stride : nullptr;
         return t;
     };
-    load_utt(u, vs, vn, factor);
-    FwdTileT<S> tl = make_tile(u, g, vs, vn, factor);
-    bool interior = group4_interior(tl);
+    load_utt(u, ut);
+    FwdTileT<S> tl = make_tile(u, g, ut);
+    int nz_shift = 0;
+    bool interior = group4_interior(tl, nz_shift);
     float rs[RAW4], rn[RAW4], ts[16], tn[16];
     if (interior) {
-        p4_load_raw(tl, lane, rs, rn);
-        p4_load_tail_raw(tl, lane, ts, tn);
+        p4_load_raw(tl, nz_shift, lane, rs, rn);
+        p4_load_tail_raw(tl, nz_shift, lane, ts, tn);
     }
 #pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
@@ -659,16 +723,16 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
 
         // ---- next tile: issue its loads now ----
         int u2 = u, g2 = g + 1;
-        int vs2 = vs, vn2 = vn;
-        float factor2 = tl.factor;
+        Utt ut2 = ut;
         const bool last_of_utt = g2 == P.G;
         const bool have_next = it + 1 < n_tiles;
-        if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, vs2, vn2, factor2); }
-        FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
-        const bool interior2 = have_next && group4_interior(tnx);
+        if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, ut2); }
+        FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, ut2);
+        int nz_shift2 = 0;
+        const bool interior2 = have_next && group4_interior(tnx, nz_shift2);
         if (interior2) {
-            p4_load_raw(tnx, lane, rs, rn);
-            p4_load_tail_raw(tnx, lane, ts, tn);
+            p4_load_raw(tnx, nz_shift2, lane, rs, rn);
+            p4_load_tail_raw(tnx, nz_shift2, lane, ts, tn);
         }
 
         // ---- dB + stores ----
@@ -686,7 +750,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         __syncwarp();
 
         if (last_of_utt || !have_next) flush_max(u);
-        u = u2; g = g2; vs = vs2; vn = vn2;
+        u = u2; g = g2; ut = ut2;
         tl = tnx;
         interior = interior2;
     }
@@ -788,15 +852,15 @@ __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restri
                                                                  float* __restrict__ data2, long long stride, long long n_per_utt,
                                                                  const int* __restrict__ max_key, const int* __restrict__ min_key,
                                                                  int which0) {
-    const int u = blockIdx.y;
+    const int u = blockIdx.x;                 // utterance on grid.x: B is not capped at 65 535
     const int z = blockIdx.z;
     float* data = z == 0 ? data0 : (z == 1 ? data1 : data2);
     const float thr = key_to_float(max_key[3 * u + which0 + z]) - TOP_DB;
     if (min_key != nullptr && key_to_float(min_key[3 * u + which0 + z]) >= thr) return;
     float* p = data + (size_t)u * stride;
     const long long n4 = n_per_utt >> 2;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.y * blockDim.x;
+    long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
     for (; i + 3 * step < n4; i += 4 * step) {          // four independent 16-byte loads in flight per thread
         float4* q = reinterpret_cast<float4*>(p) + i;
         const float4 v0 = q[0], v1 = q[step], v2 = q[2 * step], v3 = q[3 * step];
@@ -812,7 +876,7 @@ __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restri
             reinterpret_cast<float4*>(p)[i] = v;
         }
     }
-    for (long long j = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_per_utt; j += step)
+    for (long long j = 4 * n4 + (long long)blockIdx.y * blockDim.x + threadIdx.x; j < n_per_utt; j += step)
         p[j] = fmaxf(p[j], thr);
 }
 
@@ -827,10 +891,9 @@ extern "C" int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, f
                                    int B, const int* max_key, const int* min_key, void* stream) {
     if (!ctx || !speech || !noise || !mixed || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: NULL argument");
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: bad sizes");
-    if (B > 65535) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: B > 65535; split the batch");
     if ((((size_t)speech | (size_t)noise | (size_t)mixed) & 15) || (stride & 3))
         return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: data must be 16-byte aligned with stride % 4 == 0");
-    dim3 grid(floor_grid_x(n_per_utt), (unsigned)B, 3);
+    dim3 grid((unsigned)B, floor_grid_x(n_per_utt), 3);
     avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, min_key, 0);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -840,9 +903,8 @@ extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, 
                                   const int* min_key, int which, void* stream) {
     if (!ctx || !data || !max_key) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: NULL argument");
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: bad sizes");
-    if (B > 65535) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: B > 65535; split the batch");
     if (((size_t)data & 15) || (stride & 3)) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: data must be 16-byte aligned with stride % 4 == 0");
-    dim3 grid(floor_grid_x(n_per_utt), (unsigned)B);
+    dim3 grid((unsigned)B, floor_grid_x(n_per_utt));
     avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, min_key, which);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -851,12 +913,12 @@ extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, 
 __global__ void __launch_bounds__(256) avse_floor_gather_kernel(const float* __restrict__ spec, long long spec_stride, int ld_t,
                                                                 float* __restrict__ slices, long long slices_stride, int n_slices,
                                                                 const int* __restrict__ max_key, int which, int n_mels, int spss) {
-    const int u = blockIdx.y;
+    const int u = blockIdx.x;
     const float thr = key_to_float(max_key[3 * u + which]) - TOP_DB;
     const float* src = spec + (size_t)u * spec_stride;
     float* dst = slices + (size_t)u * slices_stride;
     const int n = n_slices * n_mels * spss;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const int j = i % spss;
         const int m = (i / spss) % n_mels;
         const int s = i / (spss * n_mels);
@@ -871,7 +933,7 @@ extern "C" int avse_floor_gather(avse_ctx* ctx, const float* spec, long long spe
     const int n = n_slices * ctx->n_mels * ctx->spss;
     int bx = (n + 255) / 256;
     if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)B);
+    dim3 grid((unsigned)B, (unsigned)bx);
     avse_floor_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(spec, spec_stride, ld_t, slices, slices_stride, n_slices, max_key, which,
                                                                      ctx->n_mels, ctx->spss);
     CUDA_TRY(cudaGetLastError());

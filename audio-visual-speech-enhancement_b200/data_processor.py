@@ -6,8 +6,13 @@ library through `engine.SpectralEngine`.  Batched entry points (`preprocess_audi
 `preprocess_data`) replace the reference's `multiprocess.Pool(16)` fan-out (dp:189-198): CUDA
 work is batched in the parent process, one launch over many utterances.
 
-Out of scope here: the video front end (dp:12-32) and VideoNormalizer
-(dp:201-212).  `preprocess_sample` takes the video slices from a caller-supplied callable.
+Module surface == the reference module's: preprocess_video_sample, preprocess_audio_signal,
+reconstruct_speech_signal, signal_to_spectrogram, reconstruct_signal_from_spectrogram, preprocess_audio_pair, Sample,
+preprocess_sample, try_preprocess_sample, preprocess_data, VideoNormalizer -- so that the reference's
+`speech_enhancer.py` runs unmodified with `sys.modules["data_processor"]` pointing here
+(tests/test_dropin_speech_enhancer.py).  The video front end (dp:12-32: video decode + mouth crop through the third-party
+`facedetection` / `mediaio.video_io`) is out of scope as arithmetic: `preprocess_video_sample` calls those packages when
+they are importable, and `preprocess_data` accepts any other callable with the same contract.
 """
 from __future__ import annotations
 
@@ -22,9 +27,17 @@ from .mediaio_compat import AudioSignal, AudioMixer
 _engines = {}
 
 
+def _device_index(device):
+    """GPU index of `device`; None or a bare "cuda" mean the current device."""
+    if device is None:
+        return torch.cuda.current_device()
+    idx = torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
 def get_engine(sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, device=None):
     """One cached SpectralEngine per (sample_rate, fps, slice_ms, device)."""
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    dev = _device_index(device)
     key = (int(sample_rate), float(video_frame_rate), slice_duration_ms, dev)
     if key not in _engines:
         _engines[key] = SpectralEngine(sample_rate, video_frame_rate, slice_duration_ms, device="cuda:%d" % dev)
@@ -33,7 +46,7 @@ def get_engine(sample_rate=16000, video_frame_rate=25.0, slice_duration_ms=200, 
 
 def _engine_for_fft(sample_rate, n_fft, hop_length, device=None):
     """Engine for an explicit (n_fft, hop_length) pair (the arguments of dp:77 / dp:99)."""
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    dev = _device_index(device)
     key = (int(sample_rate), "fft", int(n_fft), int(hop_length), dev)
     if key not in _engines:
         _engines[key] = SpectralEngine(sample_rate, float(sample_rate) / n_fft, 200, device="cuda:%d" % dev, n_fft=n_fft, hop=hop_length)
@@ -127,7 +140,8 @@ def reconstruct_signal_from_spectrogram(magnitude, phase, sample_rate, n_fft, ho
 # dp:119-139
 # --------------------------------------------------------------------------------------------
 def _fit_noise_np(noise, n_speech):
-    """dp:125-128: double until long enough, truncate == periodic tiling."""
+    """dp:125-128 as an explicit host copy: double until long enough, truncate == periodic tiling.  The product path
+    does not use it (the kernels address noise[i mod Ln] themselves); kept for callers and tests."""
     n = noise.shape[0]
     if n < n_speech:
         noise = noise[np.arange(n_speech) % n]
@@ -139,6 +153,8 @@ def preprocess_audio_pair_signals(speech_signal, noise_signal, slice_duration_ms
     reference; returns (mixed_slices, speech_slices, noise_slices, mixed_signal)."""
     out = preprocess_audio_pairs([speech_signal], [noise_signal], slice_duration_ms, [n_video_slices], video_frame_rate,
                                  snr_db=[snr_db])
+    if isinstance(out[0], Exception):
+        raise out[0]
     return out[0]
 
 
@@ -150,10 +166,57 @@ def preprocess_audio_pair(speech_file_path, noise_file_path, slice_duration_ms, 
     return preprocess_audio_pair_signals(speech_signal, noise_signal, slice_duration_ms, n_video_slices, video_frame_rate)
 
 
+def _pair_bucket(eng, sr, speech_signals, noise_signals, idxs, nvs, snr_db):
+    """One launch over the utterances `idxs` (equal n_video_slices).  Returns {i: 4-tuple or Exception}."""
+    L = eng.samples_per_slice * nvs
+    i16 = all(speech_signals[i].get_data().dtype == np.int16 and noise_signals[i].get_data().dtype == np.int16 for i in idxs)
+    sp = [_mono(speech_signals[i], i16) for i in idxs]
+    nz = [_mono(noise_signals[i], i16) for i in idxs]
+    for r, i in enumerate(idxs):
+        if len(nz[r]) == 0 and len(sp[r]) > 0:
+            raise ValueError("empty noise signal")          # the reference's doubling loop (dp:125-126) would never end
+    width = max(max(len(s) for s in sp), 1)
+    dt = np.int16 if i16 else np.float32
+    S = np.zeros((len(idxs), width), dtype=dt)
+    N = np.zeros((len(idxs), width), dtype=dt)
+    lens = np.zeros(len(idxs), dtype=np.int32)
+    nlens = np.zeros(len(idxs), dtype=np.int32)
+    for r in range(len(idxs)):
+        m = min(len(nz[r]), len(sp[r]))                     # dp:128 truncate; a shorter noise is tiled in-kernel (dp:125-126)
+        S[r, :len(sp[r])] = sp[r]
+        N[r, :m] = nz[r][:m]
+        lens[r] = len(sp[r])
+        nlens[r] = len(nz[r]) if len(nz[r]) < len(sp[r]) else len(sp[r])
+    snr = None
+    if snr_db is not None:
+        snr = _to_dev(np.asarray([snr_db[i] for i in idxs], dtype=np.float32), eng)
+    info = {}
+    mixed, speech, noise, pcm = eng.preprocess_pairs(_to_dev(S, eng), _to_dev(N, eng), nvs, lengths=_to_dev(lens, eng), snr_db=snr,
+                                                     noise_lengths=_to_dev(nlens, eng), info=info)
+    factor = info["factor"].cpu().numpy()
+    mixed, speech, noise, pcm = mixed.cpu().numpy(), speech.cpu().numpy(), noise.cpu().numpy(), pcm.cpu().numpy()
+    res = {}
+    for r, i in enumerate(idxs):
+        if not np.isfinite(factor[r]):
+            # silent noise file: numpy gives an inf / nan factor and librosa.stft refuses the non-finite mixture, so the
+            # reference drops this sample in try_preprocess_sample (dp:180-186)
+            res[i] = ValueError("SNR factor is not finite (noise variance is zero)")
+            continue
+        # observable mutation of the reference: speech padded/truncated in place (dp:136 -> dp:39-42)
+        if speech_signals[i].get_number_of_samples() < L:
+            speech_signals[i].pad_with_zeros(L)
+        else:
+            speech_signals[i].truncate(L)
+        res[i] = (mixed[r], speech[r], noise[r], AudioSignal(pcm[r], sr))
+    return res
+
+
 def preprocess_audio_pairs(speech_signals, noise_signals, slice_duration_ms, n_video_slices, video_frame_rate, snr_db=None):
     """Batched dp:119-139: lists of AudioSignal -> list of (mixed, speech, noise slices, mixed AudioSignal).
 
-    Utterances are bucketed by n_video_slices (equal signal_length) and each bucket is one launch."""
+    Utterances are bucketed by n_video_slices (equal signal_length) and each bucket is one launch.  Failure isolation is
+    per SAMPLE like the reference's try_preprocess_sample (dp:180-186): if a bucket fails as a whole it is retried
+    utterance by utterance, and the entry of a failing utterance is its Exception instead of a tuple."""
     sr = speech_signals[0].get_sample_rate()
     eng = get_engine(sr, video_frame_rate, slice_duration_ms)
     results = [None] * len(speech_signals)
@@ -161,29 +224,20 @@ def preprocess_audio_pairs(speech_signals, noise_signals, slice_duration_ms, n_v
     for i, nvs in enumerate(n_video_slices):
         buckets.setdefault(int(nvs), []).append(i)
     for nvs, idxs in buckets.items():
-        L = eng.samples_per_slice * nvs
-        i16 = all(speech_signals[i].get_data().dtype == np.int16 and noise_signals[i].get_data().dtype == np.int16 for i in idxs)
-        sp = [_mono(speech_signals[i], i16) for i in idxs]
-        width = max(max(len(s) for s in sp), 1)
-        S = np.zeros((len(idxs), width), dtype=np.int16 if i16 else np.float32)
-        N = np.zeros((len(idxs), width), dtype=np.int16 if i16 else np.float32)
-        lens = np.zeros(len(idxs), dtype=np.int32)
-        for r, i in enumerate(idxs):
-            S[r, :len(sp[r])] = sp[r]
-            N[r, :len(sp[r])] = _fit_noise_np(_mono(noise_signals[i], i16), len(sp[r]))
-            lens[r] = len(sp[r])
-        snr = None
-        if snr_db is not None:
-            snr = _to_dev(np.asarray([snr_db[i] for i in idxs], dtype=np.float32), eng)
-        mixed, speech, noise, pcm = eng.preprocess_pairs(_to_dev(S, eng), _to_dev(N, eng), nvs, lengths=_to_dev(lens, eng), snr_db=snr)
-        mixed, speech, noise, pcm = mixed.cpu().numpy(), speech.cpu().numpy(), noise.cpu().numpy(), pcm.cpu().numpy()
-        for r, i in enumerate(idxs):
-            # observable mutation of the reference: speech padded/truncated in place (dp:136 -> dp:39-42)
-            if speech_signals[i].get_number_of_samples() < L:
-                speech_signals[i].pad_with_zeros(L)
-            else:
-                speech_signals[i].truncate(L)
-            results[i] = (mixed[r], speech[r], noise[r], AudioSignal(pcm[r], sr))
+        try:
+            done = _pair_bucket(eng, sr, speech_signals, noise_signals, idxs, nvs, snr_db)
+        except Exception as batch_error:
+            done = {}
+            for i in idxs:
+                if len(idxs) == 1:
+                    done[i] = batch_error
+                    break
+                try:
+                    done.update(_pair_bucket(eng, sr, speech_signals, noise_signals, [i], nvs, snr_db))
+                except Exception as e:
+                    done[i] = e
+        for i in idxs:
+            results[i] = done[i]
     return results
 
 
@@ -222,13 +276,53 @@ def assemble_sample(speech_entry, noise_file_path, video_samples, video_frame_ra
     )
 
 
-def preprocess_data(speech_entries, noise_file_paths, video_preprocessor, slice_duration_ms=200):
-    """dp:189-198 with the Pool(16) fan-out replaced by one batched GPU pass.
+def preprocess_video_sample(video_file_path, slice_duration_ms, mouth_height=128, mouth_width=128):
+    """dp:12-32 contract: (slices (n, height, width, frames_per_slice) float32, frame rate).  The decode and the mouth crop
+    belong to the third-party `mediaio.video_io` / `facedetection` packages (dp:7, dp:9; out of scope, SURVEY section 2);
+    they are imported here, on first use, so that this module loads without them."""
+    from facedetection.face_detection import FaceDetector
+    from mediaio.video_io import VideoFileReader
+    print("preprocessing %s" % video_file_path)
+    detector = FaceDetector()
+    with VideoFileReader(video_file_path) as reader:
+        frames = reader.read_all_frames(convert_to_gray_scale=True)
+        n_frames, fps = reader.get_frame_count(), reader.get_frame_rate()
+    crops = np.empty((mouth_height, mouth_width, n_frames), dtype=np.float32)
+    for t in range(n_frames):
+        crops[:, :, t] = detector.crop_mouth(frames[t], bounding_box_shape=(mouth_width, mouth_height))
+    per_slice = int((float(slice_duration_ms) / 1000) * fps)           # dp:24
+    n_slices = int(float(n_frames) / per_slice)                        # dp:25
+    slices = crops[:, :, :n_slices * per_slice].reshape(mouth_height, mouth_width, n_slices, per_slice)
+    return np.ascontiguousarray(np.moveaxis(slices, 2, 0)), fps
 
-    video_preprocessor(video_path, slice_duration_ms) -> (video_samples, fps) stands in for the
-    out-of-scope preprocess_video_sample (dp:12-32).  Samples whose video or audio loading fails are
-    dropped, like try_preprocess_sample (dp:180-186)."""
+
+def preprocess_sample(speech_entry, noise_file_path, slice_duration_ms=200):
+    """dp:156-177 for one sample (same signature)."""
+    print("preprocessing sample: %s, %s, %s..." % (speech_entry.video_path, speech_entry.audio_path, noise_file_path))
+    video_samples, video_frame_rate = preprocess_video_sample(speech_entry.video_path, slice_duration_ms)
+    pair = preprocess_audio_pair(speech_entry.audio_path, noise_file_path, slice_duration_ms, video_samples.shape[0], video_frame_rate)
+    return assemble_sample(speech_entry, noise_file_path, video_samples, video_frame_rate, pair)
+
+
+def try_preprocess_sample(sample_paths):
+    """dp:180-186."""
+    try:
+        return preprocess_sample(*sample_paths)
+    except Exception as e:
+        print("failed to preprocess %s (%s)" % (sample_paths, e))
+        return None
+
+
+def preprocess_data(speech_entries, noise_file_paths, video_preprocessor=None, slice_duration_ms=200):
+    """dp:189-198 (callable exactly like the reference: `preprocess_data(speech_entries, noise_file_paths)`, se:25) with the
+    Pool(16) fan-out replaced by one batched GPU pass per (frame rate, slice count) bucket.
+
+    video_preprocessor(video_path, slice_duration_ms) -> (video_samples, fps): defaults to this module's
+    preprocess_video_sample (dp:12-32).  A sample whose video, audio or arithmetic fails is dropped and the others are
+    kept, like try_preprocess_sample (dp:180-186); the order of the surviving samples is the input order (Pool.map)."""
     print("preprocessing data...")
+    if video_preprocessor is None:
+        video_preprocessor = preprocess_video_sample
     staged = []
     for entry, noise_path in zip(speech_entries, noise_file_paths):
         try:
@@ -238,29 +332,58 @@ def preprocess_data(speech_entries, noise_file_paths, video_preprocessor, slice_
             staged.append((entry, noise_path, video_samples, fps, speech, noise))
         except Exception as e:  # dp:184-186
             print("failed to preprocess %s (%s)" % ((entry, noise_path), e))
-    samples = []
-    by_fps = {}
-    for item in staged:
-        by_fps.setdefault(float(item[3]), []).append(item)
-    for fps, items in by_fps.items():
+    by_key = {}
+    for pos, item in enumerate(staged):
+        by_key.setdefault((float(item[3]), item[4].get_sample_rate()), []).append(pos)
+    done = [None] * len(staged)
+    for (fps, _sr), positions in by_key.items():
+        items = [staged[p] for p in positions]
         try:
             res = preprocess_audio_pairs([it[4] for it in items], [it[5] for it in items], slice_duration_ms,
                                          [it[2].shape[0] for it in items], fps)
         except Exception as e:
-            print("failed to preprocess batch at %s fps (%s)" % (fps, e))
-            continue
-        for it, r in zip(items, res):
-            samples.append(assemble_sample(it[0], it[1], it[2], it[3], r))
-    return samples
+            res = [e] * len(items)
+        for p, it, r in zip(positions, items, res):
+            if isinstance(r, Exception):
+                print("failed to preprocess %s (%s)" % ((it[0], it[1]), r))
+            else:
+                done[p] = assemble_sample(it[0], it[1], it[2], it[3], r)
+    return [d for d in done if d is not None]
 
 
-def make_sample_set(samples, permutation=None):
-    """speech_enhancer.py:241-262 (next row f1): concatenate slices over samples, one shared permutation."""
+class VideoNormalizer(object):
+    """dp:201-212 with the reference's constructor and in-place `normalize`: per-pixel mean / population std over
+    (slices, frames) and (x - mean) / std, computed by avse_video_stats / avse_video_normalize on the GPU.  The state is
+    two numpy images, so the object pickles like the reference's (se:55-56, se:66-67)."""
+
+    def __init__(self, video_samples):
+        # video_samples: slices x height x width x frames_per_slice
+        from .engine import VideoNormalizer as _DeviceNormalizer
+        dev = _DeviceNormalizer(get_engine(), video_samples)
+        self.__mean_image = dev.mean_image.cpu().numpy()
+        self.__std_image = dev.std_image.cpu().numpy()
+
+    def normalize(self, video_samples):
+        from .engine import VideoNormalizer as _DeviceNormalizer
+        dev = _DeviceNormalizer.from_images(get_engine(), self.__mean_image, self.__std_image)
+        dev.normalize(video_samples)
+
+
+def make_sample_set(samples, max_samples=None, permutation=None):
+    """speech_enhancer.py:241-262 (next row f1), same signature: a random subset of `max_samples` samples, the slices of
+    all of them concatenated, ONE shared permutation.  The two spectrogram arrays are concatenated and permuted on the
+    GPU (avse_gather_rows); the video slices are only indexed (they never enter the spectral path).
+    permutation: optional explicit permutation of the concatenated rows (tests); None: np.random.permutation like se:255."""
+    import random as _random
+    n_samples = len(samples) if max_samples is None else min(len(samples), max_samples)
+    samples = _random.sample(list(samples), n_samples)
     video = np.concatenate([s.video_samples for s in samples], axis=0)
-    mixed = np.concatenate([s.mixed_spectrograms for s in samples], axis=0)
-    speech = np.concatenate([s.speech_spectrograms for s in samples], axis=0)
     perm = np.random.permutation(video.shape[0]) if permutation is None else np.asarray(permutation)
-    return video[perm], mixed[perm], speech[perm]
+    eng = get_engine()
+    mixed = _to_dev(np.ascontiguousarray(np.concatenate([s.mixed_spectrograms for s in samples], axis=0), dtype=np.float32), eng)
+    speech = _to_dev(np.ascontiguousarray(np.concatenate([s.speech_spectrograms for s in samples], axis=0), dtype=np.float32), eng)
+    m, sp, _ = eng.make_sample_set(mixed.unsqueeze(0), speech.unsqueeze(0), permutation=_to_dev(perm.astype(np.int64), eng))
+    return video[perm], m.cpu().numpy(), sp.cpu().numpy()
 
 
 class MelConverter(object):

@@ -20,8 +20,21 @@ LAYOUT_SLICES, LAYOUT_SPEC = 0, 1
 SAMPLE_F32, SAMPLE_I16 = 0, 1
 
 
+import functools
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def _on_device(fn):
+    """Run an engine method with the engine's GPU as the current device: the launchers refuse a context whose device is
+    not current, and torch allocates on the current device."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 def _rs(t):
@@ -32,15 +45,19 @@ def _rs(t):
 
 
 class DbKeys(object):
-    """Per-utterance running dB extrema of (speech, noise, mixed) as order-preserving int32 keys, device resident:
-    `max` [B, 3] over all frames (librosa's top_db reference, dp:94) and `min` [B, 3] over the stored values
-    (lets the floor pass skip utterances that need no clipping)."""
-    __slots__ = ("buf", "max", "min")
+    """Per-utterance side data that the statistics pass (avse_snr_factor) hands to the forward pass, device resident:
+    the running dB extrema of (speech, noise, mixed) as order-preserving int32 keys -- `max` [B, 3] over all frames
+    (librosa's top_db reference, dp:94), `min` [B, 3] over the stored values (lets the floor pass skip utterances that
+    need no clipping) -- and `equalizer` [B] = sqrt(var_s / var_n), the level-equalising part of the SNR factor
+    (avse_forward_args::equalizer; None until snr_factor has filled it)."""
+    __slots__ = ("buf", "max", "min", "equalizer", "_eq_buf")
 
     def __init__(self, B, device):
         self.buf = torch.empty((2, B, 3), dtype=torch.int32, device=device)
         self.max = self.buf[0]
         self.min = self.buf[1]
+        self._eq_buf = torch.empty((B,), dtype=torch.float32, device=device)
+        self.equalizer = None
 
 
 def _keys(k):
@@ -82,11 +99,15 @@ class SpectralEngine(object):
         self.slice_duration_ms = slice_duration_ms
         self.samples_per_slice = sps
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("SpectralEngine needs a CUDA device: this framework has no CPU path")
+        if self.device.index is None:        # a bare "cuda" means the current device, not GPU 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _native.load()
         h = ctypes.c_void_p()
         # (640, 160, 80, 20) -- the reference's 16 kHz / 25 fps -- gets the specialised kernels; any other geometry the
         # reference can derive (dp:44-45) runs the generic fallback kernels behind the same entry points
-        check(self._lib.avse_create_ex(self.sample_rate, n_fft, hop, N_MELS, spss, float(fmin), float(fmax), self.device.index or 0,
+        check(self._lib.avse_create_ex(self.sample_rate, n_fft, hop, N_MELS, spss, float(fmin), float(fmax), self.device.index,
                                        ctypes.byref(h)), "avse_create_ex")
         self._ctx = h
         geo = (ctypes.c_int * 6)()
@@ -127,24 +148,36 @@ class SpectralEngine(object):
         return 1 + (L + 2 * (self.n_fft // 2) - self.n_fft) // self.hop
 
     # ------------------------------------------------------------------ a3: SNR factor
-    def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None):
-        """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], DbKeys) with the keys reset."""
+    @_on_device
+    def snr_factor(self, speech, noise, lengths=None, snr_db=None, max_key=None, noise_lengths=None):
+        """AudioMixer.snr_factor (dp:130) for a batch; returns (factor[B], DbKeys) with the keys reset and the level
+        equaliser filled in.  noise_lengths [B] int32: own length of each noise file; a noise shorter than its speech is
+        tiled periodically inside the kernel (dp:125-128) instead of being materialised."""
         i16 = speech.dtype == torch.int16 and noise.dtype == torch.int16
         speech, noise = self._as_batch(speech, i16), self._as_batch(noise, i16)
         B, L = speech.shape
-        assert noise.shape == speech.shape and _rs(noise) == _rs(speech)
+        assert noise.shape[0] == B and _rs(noise) == _rs(speech)
+        assert noise_lengths is not None or noise.shape[1] >= L, "a noise batch narrower than the speech needs noise_lengths"
         factor = torch.empty(B, dtype=torch.float32, device=self.device)
         if max_key is None:
             max_key = DbKeys(B, self.device)
         kmax, kmin = _keys(max_key)
-        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), SAMPLE_I16 if i16 else SAMPLE_F32, _rs(speech), _ptr(lengths), B, L,
-                                        _ptr(snr_db), _ptr(factor), _ptr(kmax), _ptr(kmin), self._stream()), "avse_snr_factor")
+        eq = None
+        if isinstance(max_key, DbKeys):
+            eq = max_key.equalizer = max_key._eq_buf
+        check(self._lib.avse_snr_factor(self._ctx, _ptr(speech), _ptr(noise), SAMPLE_I16 if i16 else SAMPLE_F32, _rs(speech), _ptr(lengths),
+                                        _ptr(noise_lengths), B, L, _ptr(snr_db), _ptr(factor), _ptr(eq), _ptr(kmax), _ptr(kmin),
+                                        self._stream()), "avse_snr_factor")
         return factor, max_key
 
     # ------------------------------------------------------------------ a1/a4/a5: forward
+    @_on_device
     def forward_raw(self, speech, noise=None, L=None, len_speech=None, len_noise=None, factor=None, layout=LAYOUT_SLICES,
-                    n_slices=None, want=("speech", "noise", "mixed"), mixed_pcm=True, max_key=None, stft=False, out=None):
-        """Launch avse_forward.  Returns dict with un-floored outputs + max_key (see include/avse_b200.h)."""
+                    n_slices=None, want=("speech", "noise", "mixed"), mixed_pcm=True, max_key=None, stft=False, out=None,
+                    noise_lengths=None):
+        """Launch avse_forward.  Returns dict with un-floored outputs + max_key (see include/avse_b200.h).
+        When `max_key` is the DbKeys that snr_factor returned, its level equaliser rides along (numerical conditioning of
+        the packed FFT; the result is s + factor * n either way)."""
         # raw int16 samples go to the kernel as they are (decode fused into its loads) for pair batches
         i16 = noise is not None and speech.dtype == torch.int16 and noise.dtype == torch.int16 and not stft
         speech = self._as_batch(speech, i16)
@@ -191,10 +224,13 @@ class SpectralEngine(object):
         a.min_key = _ptr(kmin)
         a.sample_format = SAMPLE_I16 if i16 else SAMPLE_F32
         a.stft_speech = _ptr(res["stft"])
+        a.equalizer = _ptr(max_key.equalizer) if (isinstance(max_key, DbKeys) and factor is not None and noise is not None) else 0
+        a.noise_period = _ptr(noise_lengths) if noise is not None else 0
         check(self._lib.avse_forward(self._ctx, ctypes.byref(a), self._stream()), "avse_forward")
         res["T"], res["ld_t"], res["n_slices"], res["layout"] = T, ld_t, n_slices, layout
         return res
 
+    @_on_device
     def floor_(self, data, max_key, which):
         """amplitude_to_db's top_db floor (dp:94), in place, per utterance."""
         B = data.shape[0]
@@ -204,6 +240,7 @@ class SpectralEngine(object):
               "avse_floor_inplace")
         return data
 
+    @_on_device
     def floor3_(self, speech, noise, mixed, max_key):
         """The top_db floor for the three outputs of a pair batch in one launch."""
         B = speech.shape[0]
@@ -213,6 +250,7 @@ class SpectralEngine(object):
         check(self._lib.avse_floor_inplace3(self._ctx, _ptr(speech), _ptr(noise), _ptr(mixed), _rs(speech), n, B, _ptr(kmax), _ptr(kmin),
                                             self._stream()), "avse_floor_inplace3")
 
+    @_on_device
     def floor_gather(self, spec, max_key, which, n_slices):
         """dp:49-57: SPEC [B,80,ld_t] (un-floored) -> floored slices [B,n_slices,80,20]."""
         B, _, ld_t = spec.shape
@@ -221,6 +259,7 @@ class SpectralEngine(object):
                                           _ptr(_keys(max_key)[0]), which, self._stream()), "avse_floor_gather")
         return out
 
+    @_on_device
     def max_db(self, max_key):
         """Decoded running maxima [B, 3] in dB."""
         max_key = _keys(max_key)[0]
@@ -228,6 +267,7 @@ class SpectralEngine(object):
         check(self._lib.avse_max_db(self._ctx, _ptr(max_key), max_key.numel(), _ptr(out), self._stream()), "avse_max_db")
         return out
 
+    @_on_device
     def min_db(self, keys):
         """Decoded running minima [B, 3] of the stored dB values (same key encoding as the maxima)."""
         kmin = _keys(keys)[1]
@@ -236,12 +276,15 @@ class SpectralEngine(object):
         return out
 
     # ------------------------------------------------------------------ batched reference-level operations
-    def preprocess_pairs(self, speech, noise, n_video_slices, lengths=None, snr_db=None, out=None):
+    @_on_device
+    def preprocess_pairs(self, speech, noise, n_video_slices, lengths=None, snr_db=None, out=None, noise_lengths=None, info=None):
         """Batched preprocess_audio_pair (dp:119-139) on device tensors.
 
-        speech, noise: [B, >=max(lengths)] float32, noise already fitted to the speech length
-        (dp:125-128, see fit_noise).  Returns (mixed_slices, speech_slices, noise_slices, mixed_pcm)
-        with shapes [B, n, 80, 20] x3 and [B, L]; n = min(n_video_slices, int(T/20)) (dp:50, dp:164).
+        speech, noise: [B, >=max(lengths)] float32 or int16, same row stride.  noise_lengths [B] int32 (optional): own
+        length of each noise file -- a noise shorter than its speech is tiled periodically inside the kernels
+        (dp:125-128); without it the noise rows must already cover the speech length (see fit_noise).
+        Returns (mixed_slices, speech_slices, noise_slices, mixed_pcm) with shapes [B, n, 80, 20] x3 and [B, L];
+        n = min(n_video_slices, int(T/20)) (dp:50, dp:164).  Batches of any size: nothing here is capped at 65 535.
         """
         i16 = speech.dtype == torch.int16 and noise.dtype == torch.int16
         speech, noise = self._as_batch(speech, i16), self._as_batch(noise, i16)
@@ -250,17 +293,17 @@ class SpectralEngine(object):
         n = min(int(n_video_slices), T // self.spss)
         if lengths is None and speech.shape[1] != L:
             lengths = torch.full((speech.shape[0],), speech.shape[1], dtype=torch.int32, device=self.device)
-        fl = None
-        if lengths is not None:
-            fl = lengths
-        # dp:130 variance is over the ORIGINAL speech length (before pad/truncate to L)
-        stats_L = speech.shape[1] if lengths is None else int(speech.shape[1])
-        factor, max_key = self.snr_factor(speech[:, :stats_L], noise[:, :stats_L], lengths=fl, snr_db=snr_db)
-        res = self.forward_raw(speech, noise, L=L, len_speech=fl, len_noise=fl, factor=factor, layout=LAYOUT_SLICES,
-                               n_slices=n, max_key=max_key, out=out)
+        # info: optional dict that receives the SNR factors and the dB keys
+        # dp:130: the variances are over the ORIGINAL speech length (the whole row), before the pad / truncate to L
+        factor, max_key = self.snr_factor(speech, noise, lengths=lengths, snr_db=snr_db, noise_lengths=noise_lengths)
+        res = self.forward_raw(speech, noise, L=L, len_speech=lengths, len_noise=lengths, factor=factor, layout=LAYOUT_SLICES,
+                               n_slices=n, max_key=max_key, out=out, noise_lengths=noise_lengths)
         self.floor3_(res["speech"], res["noise"], res["mixed"], max_key)
+        if info is not None:        # side data for callers that need it: the SNR factors (dp:130) and the dB extrema
+            info["factor"], info["keys"] = factor, max_key
         return res["mixed"], res["speech"], res["noise"], res["mixed_pcm"]
 
+    @_on_device
     def spectrogram(self, signals, lengths=None, stft=False):
         """Batched signal_to_spectrogram(mel=True, db=True) (dp:77-96): floored dB [B, 80, T] (+ complex STFT)."""
         signals = self._as_batch(signals)
@@ -273,6 +316,7 @@ class SpectralEngine(object):
         # pad columns (>= T) are untouched garbage; floor the whole padded rows (harmless)
         return self.floor_(spec, max_key, which)
 
+    @_on_device
     def preprocess_signals(self, signals, n_video_slices, lengths=None):
         """Batched preprocess_audio_signal (dp:35-57): [B, n, 80, 20] floored dB slices."""
         signals = self._as_batch(signals)
@@ -284,6 +328,7 @@ class SpectralEngine(object):
         res = self.forward_raw(signals, None, L=L, len_speech=lengths, layout=LAYOUT_SLICES, n_slices=n, want=("speech",), mixed_pcm=False)
         return self.floor_(res["speech"], res["max_key"], 0)
 
+    @_on_device
     def reconstruct(self, mixed_pcm, mel_slices, lengths=None, out=None, work=None, out_dtype=torch.float32):
         """Batched reconstruct_speech_signal (dp:60-74): mixture PCM [B, L] + dB slices [B, n, 80, 20] -> PCM [B, 160*(min(20n, T)-1)].
         out_dtype=torch.int16 fuses AudioSignal.save_to_wav_file's clip + cast (se:176-177) into the last store."""
@@ -314,6 +359,7 @@ class SpectralEngine(object):
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
 
+    @_on_device
     def reconstruct_with_phase(self, mel_db, phase):
         """reconstruct_signal_from_spectrogram(mel=True, db=True) (dp:99-116) with an explicit phase:
         mel_db [B, 80, T] dB, phase [B, T_ph, 321] complex64 (frame-major).  Returns PCM [B, 160*(min(T, T_ph)-1)]."""
@@ -337,6 +383,7 @@ class SpectralEngine(object):
         check(self._lib.avse_inverse(self._ctx, ctypes.byref(a), self._stream()), "avse_inverse")
         return out
 
+    @_on_device
     def reconstruct_spec(self, mixed_pcm, mel_db, lengths=None):
         """Same with a SPEC-layout spectrogram [B, 80, T_mel] (dp:99-116 called directly with mel=True, db=True)."""
         mixed_pcm = self._as_batch(mixed_pcm)
@@ -362,6 +409,7 @@ class SpectralEngine(object):
 
 
     # ------------------------------------------------------------------ next row f1: make_sample_set on the device
+    @_on_device
     def make_sample_set(self, mixed_slices, speech_slices, n_slices=None, permutation=None, generator=None, extra=None):
         """speech_enhancer.py:241-262 without the pickle / numpy round trip: concatenate the slices of all samples
         (np.concatenate over `sample.mixed_spectrograms` / `.speech_spectrograms`) and apply ONE shared permutation.
@@ -408,15 +456,28 @@ class VideoNormalizer(object):
     mouth-crop tensor [N, H, W, F] and the in-place normalisation."""
 
     def __init__(self, engine, video_samples):
-        v = self._as_dev(engine, video_samples)
-        N, H, W, F = v.shape
         self.eng = engine
-        self.shape = (H, W)
-        self.mean_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
-        self.std_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
-        scratch = torch.empty(2 * H * W, dtype=torch.float64, device=engine.device)
-        check(engine._lib.avse_video_stats(engine._ctx, _ptr(v), N, H * W, F, _ptr(scratch), _ptr(self.mean_image), _ptr(self.std_image),
-                                           engine._stream()), "avse_video_stats")
+        self.device = engine.device
+        if video_samples is None:
+            return
+        with torch.cuda.device(self.device):
+            v = self._as_dev(engine, video_samples)
+            N, H, W, F = v.shape
+            self.shape = (H, W)
+            self.mean_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
+            self.std_image = torch.empty((H, W), dtype=torch.float32, device=engine.device)
+            scratch = torch.empty(2 * H * W, dtype=torch.float64, device=engine.device)
+            check(engine._lib.avse_video_stats(engine._ctx, _ptr(v), N, H * W, F, _ptr(scratch), _ptr(self.mean_image),
+                                               _ptr(self.std_image), engine._stream()), "avse_video_stats")
+
+    @classmethod
+    def from_images(cls, engine, mean_image, std_image):
+        """Normaliser from stored statistics (the unpickled state of data_processor.VideoNormalizer, se:66-67)."""
+        self = cls(engine, None)
+        self.mean_image = torch.as_tensor(np.ascontiguousarray(mean_image, dtype=np.float32)).to(engine.device)
+        self.std_image = torch.as_tensor(np.ascontiguousarray(std_image, dtype=np.float32)).to(engine.device)
+        self.shape = tuple(self.mean_image.shape)
+        return self
 
     @staticmethod
     def _as_dev(engine, video_samples):
@@ -425,6 +486,7 @@ class VideoNormalizer(object):
         assert v.dim() == 4, "video_samples: slices x height x width x frames_per_slice"
         return v
 
+    @_on_device
     def normalize(self, video_samples):
         """In place like the reference: a CUDA float32 tensor is modified directly, a numpy array is overwritten."""
         on_dev = torch.is_tensor(video_samples) and video_samples.is_cuda and video_samples.dtype == torch.float32 and video_samples.is_contiguous()
@@ -446,9 +508,10 @@ def mse(engine, a, b):
     a = a.to(engine.device, dtype=torch.float32).contiguous()
     b = b.to(engine.device, dtype=torch.float32).contiguous()
     assert a.shape == b.shape
-    scratch = torch.empty(1, dtype=torch.float64, device=engine.device)
-    out = torch.empty(1, dtype=torch.float32, device=engine.device)
-    check(engine._lib.avse_mse(engine._ctx, _ptr(a), _ptr(b), a.numel(), _ptr(scratch), _ptr(out), engine._stream()), "avse_mse")
+    with torch.cuda.device(engine.device):
+        scratch = torch.empty(1, dtype=torch.float64, device=engine.device)
+        out = torch.empty(1, dtype=torch.float32, device=engine.device)
+        check(engine._lib.avse_mse(engine._ctx, _ptr(a), _ptr(b), a.numel(), _ptr(scratch), _ptr(out), engine._stream()), "avse_mse")
     return out
 
 
@@ -537,7 +600,9 @@ def shard_range(n_utterances, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def fit_noise(noise, n_noise, n_speech_max, lengths=None):
-    """dp:125-128 for a batch: periodic tiling noise[i mod n_noise] up to the speech length (torch gather; host-side prep)."""
+def fit_noise(noise, n_noise, n_speech_max):
+    """dp:125-128 for a batch as an explicit copy: periodic tiling noise[i mod n_noise] up to the speech length.  The
+    product path does not need it (pass `noise_lengths` to preprocess_pairs: the kernels address noise[i mod Ln]
+    themselves); kept for callers that want the fitted noise as a tensor."""
     idx = torch.arange(n_speech_max, device=noise.device) % int(n_noise)
     return noise[..., :n_noise].index_select(-1, idx).contiguous()

@@ -33,11 +33,12 @@ int main(void) {
 
     avse_ctx* ctx = NULL;
     CHECK_AVSE(avse_create(16000, 0.0, 8000.0, 0, &ctx));
-    float *d_s, *d_n, *d_factor, *d_sp, *d_nz, *d_mx, *d_pcm, *d_rec, *d_work;
+    float *d_s, *d_n, *d_factor, *d_eq, *d_sp, *d_nz, *d_mx, *d_pcm, *d_rec, *d_work;
     int* d_keys;
     CHECK_CUDA(cudaMalloc((void**)&d_s, n_in * 4));
     CHECK_CUDA(cudaMalloc((void**)&d_n, n_in * 4));
     CHECK_CUDA(cudaMalloc((void**)&d_factor, B * 4));
+    CHECK_CUDA(cudaMalloc((void**)&d_eq, B * 4));
     CHECK_CUDA(cudaMalloc((void**)&d_keys, 2 * B * 3 * 4));
     CHECK_CUDA(cudaMalloc((void**)&d_sp, n_out * 4));
     CHECK_CUDA(cudaMalloc((void**)&d_nz, n_out * 4));
@@ -48,9 +49,9 @@ int main(void) {
     int* d_max = d_keys;
     int* d_min = d_keys + B * 3;
 
-    CHECK_AVSE(avse_snr_factor(ctx, d_s, d_n, AVSE_SAMPLE_F32, L, NULL, B, L, NULL, d_factor, d_max, d_min, NULL));
+    CHECK_AVSE(avse_snr_factor(ctx, d_s, d_n, AVSE_SAMPLE_F32, L, NULL, NULL, B, L, NULL, d_factor, d_eq, d_max, d_min, NULL));
     avse_forward_args fa = {0};
-    fa.speech = d_s; fa.noise = d_n; fa.in_stride = L; fa.factor = d_factor;
+    fa.speech = d_s; fa.noise = d_n; fa.in_stride = L; fa.factor = d_factor; fa.equalizer = d_eq;
     fa.B = B; fa.L = L; fa.layout = AVSE_LAYOUT_SLICES; fa.n_slices = NS;
     fa.out_speech = d_sp; fa.out_noise = d_nz; fa.out_mixed = d_mx; fa.out_stride = (long long)NS * ROW;
     fa.mixed_pcm = d_pcm; fa.pcm_stride = L; fa.max_key = d_max; fa.min_key = d_min; fa.sample_format = AVSE_SAMPLE_F32;

@@ -68,19 +68,26 @@ const char* avse_version(void);
 int avse_get_filterbank(const avse_ctx* ctx, double* host_out);
 
 /* AudioMixer.snr_factor (dp:130): factor[u] = sqrt(var(speech_u) / var(noise_u)) * 10^(-snr_db[u]/20),
- * population variance over the first lengths[u] samples (lengths == NULL: L for all).
+ * population variance over the first lengths[u] samples (lengths == NULL: L for all; values are clamped to [0, L]).
  * Accumulates in float64.  snr_db == NULL means 0 dB for every utterance (the reference).
+ * noise_period (may be NULL): [B] own length Ln of each noise file.  Where Ln < lengths[u] the noise is the periodic tiling
+ *   noise[i] = nz[i mod Ln] -- what the reference's "double until long enough, then truncate" loop builds (dp:125-128) --
+ *   and only the first Ln samples of the noise row are read.
+ * equalizer_out (may be NULL): [B] sqrt(var(speech_u) / var(noise_u)) alone, the part of the factor that equalises the
+ *   levels of the two files; hand it to avse_forward (avse_forward_args::equalizer).
+ * lengths[u] == 0 gives factor 0 (the reference mixes two empty arrays and zero-pads them, dp:39-40); a silent noise
+ * (variance 0) gives inf / nan like numpy, and so does everything computed from it.
  * Also resets max_key[u][0..2] (the running dB maxima used by avse_forward / avse_floor_*) and, when
  * given, min_key[u][0..2] (the running minima of the stored values).
  * speech/noise: [B][stride] with stride >= L, float32 or int16 (sample_format = AVSE_SAMPLE_*). */
 int avse_snr_factor(avse_ctx* ctx, const void* speech, const void* noise, int sample_format, long long stride,
-                    const int* lengths, int B, int L, const float* snr_db,
-                    float* factor_out, int* max_key, int* min_key, void* stream);
+                    const int* lengths, const int* noise_period, int B, int L, const float* snr_db,
+                    float* factor_out, float* equalizer_out, int* max_key, int* min_key, void* stream);
 
 typedef struct avse_forward_args {
     /* inputs */
     const void* speech;      /* [B][in_stride], float32 or int16 (see sample_format) */
-    const void* noise;       /* [B][in_stride], already fitted to the speech length (dp:125-128); NULL: single signal */
+    const void* noise;       /* [B][in_stride]; covers the speech length unless noise_period says otherwise; NULL: single signal */
     long long in_stride;     /* elements between consecutive utterances */
     const int* len_speech;   /* [B] samples present (zeros beyond: pad_with_zeros dp:40); NULL: L */
     const int* len_noise;    /* [B]; NULL: same as len_speech */
@@ -103,6 +110,14 @@ typedef struct avse_forward_args {
                                 skip every utterance whose minimum is already >= max - 80 (nothing to clip) */
     int sample_format;       /* AVSE_SAMPLE_F32 (0) or AVSE_SAMPLE_I16: element type of speech / noise.  int16 is supported
                                 for pair batches (noise != NULL) without stft_speech */
+    const float* equalizer;  /* [B] from avse_snr_factor (equalizer_out), or NULL.  Numerical conditioning only: results are the
+                                reference's s + factor * n either way.  The float32 kernels carry speech and noise through ONE
+                                packed complex FFT; with the noise pre-scaled by equalizer[u] = sqrt(var_s / var_n) both channels
+                                have equal power whatever the raw levels of the two files (a float WAV next to an int16 one ...),
+                                and the remaining factor[u] / equalizer[u] = 10^(-snr/20) is applied by STFT linearity.
+                                NULL: the whole factor is applied before the transform */
+    const int* noise_period; /* [B] or NULL: own length Ln of each noise file; where Ln < len_noise[u] the kernels read
+                                noise[i mod Ln] (dp:125-128) and only the first Ln samples of the noise row need to exist */
 } avse_forward_args;
 
 /* preprocess_audio_pair's arithmetic (dp:130-137) / signal_to_spectrogram (dp:77-96) for a batch:

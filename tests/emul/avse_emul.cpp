@@ -60,16 +60,18 @@ extern "C" int emul_fft640(const float* re, const float* im, float* out_re, floa
     for (int i = 0; i < NFFT; ++i) { s[t * HOP - HALF + i] = re[i]; n[t * HOP - HALF + i] = im[i]; }
     FwdTile tl{};
     tl.sp = s.data(); tl.nz = n.data(); tl.L = L; tl.valid_s = L; tl.valid_n = L; tl.vmin = L; tl.T = 1 + L / HOP; tl.t0 = 8;
-    tl.factor = 0.0f; tl.mixed_pcm = nullptr;
+    tl.factor = 0.0f; tl.gain = 1.0f; tl.period_n = 0; tl.mixed_pcm = nullptr;
     emul_fft_stages(w, h, ones.data(), tl);
     for (int k = 0; k < NFFT; ++k) { out_re[k] = w.frames[2 * k]; out_im[k] = w.frames[2 * k + 1]; }
     return 0;
 }
 
 // mode: 0 = what the library would pick (scan when the tables allow it), 1 = force the generic path
-extern "C" int emul_forward_mode(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
-                                 int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
-                                 float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax, int mode) {
+// factor = the full SNR factor (dp:130); gain = its level-equaliser part applied to the noise at load (0: apply the whole
+// factor at load, like a NULL avse_forward_args::equalizer); period: noise[i] = noise[i mod period] (0: none).
+extern "C" int emul_forward_mode_ex(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor, float gain,
+                                    int period, int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                                    float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax, int mode) {
     HostTables h;
     if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
     const bool scan = h.scan_ok && mode == 0;
@@ -82,7 +84,10 @@ extern "C" int emul_forward_mode(const float* speech, const float* noise, int L,
     tl.valid_s = valid_s < L ? valid_s : L;
     tl.valid_n = valid_n < L ? valid_n : L;
     tl.vmin = have_noise ? (tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n) : 0;
-    tl.T = T; tl.factor = have_noise ? factor : 0.0f; tl.mixed_pcm = mixed_pcm;
+    if (gain == 0.0f) gain = factor;
+    tl.T = T; tl.gain = have_noise ? gain : 0.0f; tl.factor = have_noise ? (gain != 0.0f ? factor / gain : 0.0f) : 0.0f;
+    tl.period_n = (have_noise && period > 0 && period < tl.valid_n) ? period : 0;
+    tl.mixed_pcm = mixed_pcm;
     FwdOut out{};
     out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
     out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
@@ -115,6 +120,13 @@ extern "C" int emul_forward_mode(const float* speech, const float* noise, int L,
     return scan ? 1 : 0;
 }
 
+extern "C" int emul_forward_mode(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
+                                 int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                                 float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax, int mode) {
+    return emul_forward_mode_ex(speech, noise, L, valid_s, valid_n, factor, 0.0f, 0, layout, n_slices, ld_t, out_sp, out_nz, out_mix,
+                                mixed_pcm, max3, sample_rate, fmin, fmax, mode);
+}
+
 extern "C" int emul_forward(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
                             int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
                             float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
@@ -133,9 +145,9 @@ struct EmulWarp4 {
 };
 
 // Returns 1 when the F4 tables are usable, -3 when they are not (the library then uses the 2-frame kernel).
-extern "C" int emul_forward4(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
-                             int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
-                             float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
+extern "C" int emul_forward4_ex(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor, float gain,
+                                int period, int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                                float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
     HostTables h;
     if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
     if (!h.scan4_ok || noise == nullptr) return -3;
@@ -152,19 +164,23 @@ extern "C" int emul_forward4(const float* speech, const float* noise, int L, int
     tl.valid_s = valid_s < L ? valid_s : L;
     tl.valid_n = valid_n < L ? valid_n : L;
     tl.vmin = tl.valid_s < tl.valid_n ? tl.valid_s : tl.valid_n;
-    tl.T = T; tl.factor = factor; tl.mixed_pcm = mixed_pcm;
+    if (gain == 0.0f) gain = factor;
+    tl.T = T; tl.gain = gain; tl.factor = gain != 0.0f ? factor / gain : 0.0f;
+    tl.period_n = (period > 0 && period < tl.valid_n) ? period : 0;
+    tl.mixed_pcm = mixed_pcm;
     FwdOut out{};
     out.dst[0] = out_sp; out.dst[1] = out_nz; out.dst[2] = out_mix;
     out.layout = layout; out.n_slices = n_slices; out.ld_t = ld_t;
     float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * F4;
-        if (group4_interior(tl)) {
+        int nz_shift = 0;
+        if (group4_interior(tl, nz_shift)) {
             for (int lane = 0; lane < 32; ++lane) {
-                p4_load_raw(tl, lane, w.rs[lane], w.rn[lane]);
+                p4_load_raw(tl, nz_shift, lane, w.rs[lane], w.rn[lane]);
                 stage4_pass1_main(tl, lane, w.rs[lane], w.rn[lane], w.lc[lane], w.frames);
             }
-            for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, lane, h.window.data(), s_tw, w.frames);
+            for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, nz_shift, lane, h.window.data(), s_tw, w.frames);
         } else {
             for (int lane = 0; lane < 32; ++lane) stage4_pass1_edge(tl, lane, h.window.data(), s_tw, w.frames);
         }
@@ -184,4 +200,11 @@ extern "C" int emul_forward4(const float* speech, const float* noise, int L, int
     }
     for (int s = 0; s < 3; ++s) max3[s] = key_to_float(float_to_key(mx[s]));
     return 1;
+}
+
+extern "C" int emul_forward4(const float* speech, const float* noise, int L, int valid_s, int valid_n, float factor,
+                             int layout, int n_slices, int ld_t, float* out_sp, float* out_nz, float* out_mix,
+                             float* mixed_pcm, float* max3, int sample_rate, double fmin, double fmax) {
+    return emul_forward4_ex(speech, noise, L, valid_s, valid_n, factor, 0.0f, 0, layout, n_slices, ld_t, out_sp, out_nz, out_mix,
+                            mixed_pcm, max3, sample_rate, fmin, fmax);
 }

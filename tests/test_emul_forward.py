@@ -38,6 +38,11 @@ def emul():
     lib.emul_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    ex = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+          ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    lib.emul_forward4_ex.argtypes = ex
+    lib.emul_forward_mode_ex.argtypes = ex + [ctypes.c_int]
     lib.emul_filterbank.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
     lib.emul_tables_info.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
@@ -164,14 +169,19 @@ def test_scan_and_generic_paths_agree_with_oracle(emul):
 
 
 # ---- F4 kernel (avse_fwd4_stages.cuh): four frames per warp, dense emission ----
-def _run_emul4(emul, s, nf, L, fac, ns, valid=None, fmin=0.0, fmax=8000.0):
-    emul.emul_forward4.argtypes = emul.emul_forward.argtypes
+def _run_emul4(emul, s, nf, L, fac, ns, valid=None, fmin=0.0, fmax=8000.0, gain=0.0, period=0, f2=False):
+    """gain: the level-equaliser part of `fac` applied to the noise at load (0: all of `fac`, like a NULL
+    avse_forward_args::equalizer); period: noise[i] = nf[i mod period] (dp:125-128); f2: the 2-frame kernel's stages."""
     outs = [np.zeros((ns, 80, 20), np.float32) for _ in range(3)]
     pcm = np.zeros(L, np.float32)
     mx = np.zeros(3, np.float32)
     v = len(s) if valid is None else valid
-    rc = emul.emul_forward4(_p(s), _p(nf), L, v, v, fac, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm), _p(mx),
-                            SR, fmin, fmax)
+    if f2:
+        rc = emul.emul_forward_mode_ex(_p(s), _p(nf), L, v, v, fac, gain, period, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm),
+                                       _p(mx), SR, fmin, fmax, 0)
+    else:
+        rc = emul.emul_forward4_ex(_p(s), _p(nf), L, v, v, fac, gain, period, 0, ns, 0, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(pcm),
+                                   _p(mx), SR, fmin, fmax)
     assert rc == 1
     floored = [np.maximum(o, m - 80.0) for o, m in zip(outs, mx)]
     return dict(speech=floored[0], noise=floored[1], mixed=floored[2], mixed_pcm=pcm, max=mx)
@@ -239,9 +249,11 @@ def test_f4_stage_code_fuzz_against_oracle(emul):
     st = hyp.strategies
 
     @hyp.settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
-    @hyp.given(nvs=st.integers(1, 4), frac=st.floats(0.11, 1.0), log_scale=st.floats(-2.0, 4.5), fac=st.floats(0.05, 8.0),
-               seed=st.integers(0, 10 ** 6))
-    def check(nvs, frac, log_scale, fac, seed):
+    @hyp.given(nvs=st.integers(1, 4), frac=st.floats(0.11, 1.0), log_scale=st.floats(-2.0, 4.5), log_nscale=st.floats(-4.0, 4.5),
+               snr=st.floats(-10.0, 10.0), seed=st.integers(0, 10 ** 6))
+    def check(nvs, frac, log_scale, log_nscale, snr, seed):
+        # speech and noise levels are drawn INDEPENDENTLY (a float WAV next to an int16 one ...): the level equaliser
+        # g = sqrt(var_s / var_n) goes to the kernel stages as `gain`, the full factor g 10^(-snr/20) as `factor`
         L = 3200 * nvs
         nv = max(330, min(L, int(frac * L)))
         rng = np.random.RandomState(seed)
@@ -249,16 +261,85 @@ def test_f4_stage_code_fuzz_against_oracle(emul):
         s = np.zeros(L, np.float32)
         nf = np.zeros(L, np.float32)
         s[:nv] = (O.synth_speech(nv, SR, seed) * scale).astype(np.float32)
-        nf[:nv] = (0.05 * scale * rng.randn(nv)).astype(np.float32)
+        nf[:nv] = (10.0 ** log_nscale * rng.randn(nv)).astype(np.float32)
+        gain = np.float32(np.sqrt(np.var(s[:nv].astype(np.float64)) / np.var(nf[:nv].astype(np.float64))))
+        fac = np.float32(float(gain) * 10.0 ** (-snr / 20.0))
         ns = min(nvs, (1 + L // 160) // 20)
-        got = _run_emul4(emul, s, nf, L, np.float32(fac), ns, valid=nv)
-        f = float(np.float32(fac))
+        got = _run_emul4(emul, s, nf, L, fac, ns, valid=nv, gain=gain)
+        f = float(fac)
         mix = s.astype(np.float64) + f * nf.astype(np.float64)
         assert np.max(np.abs(got["mixed_pcm"] - mix)) <= TOL_PCM * max(np.max(np.abs(mix)), 1e-30)
         for k, x in (("speech", s.astype(np.float64)), ("noise", f * nf.astype(np.float64)), ("mixed", mix)):
             ref, _ = O.signal_to_spectrogram(O.AudioSignal(x, SR), 640, 160)
             want = np.stack([ref[:, 20 * i:20 * i + 20] for i in range(ns)])
-            assert np.max(np.abs(got[k] - want)) <= TOL_DB, (k, nvs, nv, scale, fac)
+            assert np.max(np.abs(got[k] - want)) <= TOL_DB, (k, nvs, nv, scale, log_nscale, snr)
             assert abs(got["max"][("speech", "noise", "mixed").index(k)] - ref.max()) <= TOL_DB
 
     check()
+
+
+# ---- level mismatch between the two files (VERDICT r1 "what's weak" #1): speech and noise at unrelated raw levels ----
+LEVELS = [(1.0, 1.0), (1.0, 10.0), (1.0, 100.0), (1.0, 32767.0), (100.0, 1.0), (32767.0, 1.0), (1e-4, 1.0), (1.0, 1e-4), (3000.0, 30000.0)]
+
+
+@pytest.mark.parametrize("f2", [False, True], ids=["f4", "f2"])
+@pytest.mark.parametrize("snr", [-10.0, 0.0, 10.0])
+def test_level_mismatch_holds_the_gate(emul, snr, f2):
+    """dp:130-133 exists precisely for files recorded at different levels.  With the noise equalised to the speech power
+    before the packed FFT (gain = sqrt(var_s / var_n)) and only 10^(-snr/20) applied by linearity, the three log-mels
+    stay within 1e-3 dB of the float64 oracle and the mixture PCM within 1e-4 of full scale for raw level ratios from
+    1e-4 to 3e4 (float WAV vs int16 WAV) at -10 / 0 / +10 dB."""
+    L = 16000
+    for ss, nsx in LEVELS:
+        s = (O.synth_speech(L, SR, 5) * ss).astype(np.float32)
+        n = (O.synth_noise(L, 5) * nsx).astype(np.float32)
+        if max(ss, nsx) > 1000.0:
+            s, n = np.round(s), np.round(n) if nsx > 1000.0 else n    # int16-valued samples at int16 scale
+        sp, nz = O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(n.astype(np.float64), SR)
+        fac = np.float32(O.AudioMixer.snr_factor(sp, nz, snr))
+        gain = np.float32(O.AudioMixer.snr_factor(sp, nz, 0.0))
+        mixed, speech, noise, msig = O.preprocess_audio_pair_signals(sp, nz, 200, 5, 25.0, snr_db=snr)
+        got = _run_emul4(emul, s, n, L, fac, 5, gain=gain, f2=f2)
+        for k, ref in (("speech", speech), ("noise", noise), ("mixed", mixed)):
+            assert np.max(np.abs(got[k] - ref)) <= TOL_DB, (k, ss, nsx, snr)
+        full = np.max(np.abs(msig.get_data()))
+        assert np.max(np.abs(got["mixed_pcm"] - msig.get_data())) <= TOL_PCM * full, (ss, nsx, snr)
+
+
+def test_unequalised_packing_would_fail(emul):
+    """The failure the equaliser removes, kept as a regression guard for the test itself: with the whole factor applied
+    only after the unpack (gain = 1) a 100x level gap breaks the speech log-mel by more than 10x the gate."""
+    L = 16000
+    s = O.synth_speech(L, SR, 5).astype(np.float32)
+    n = (O.synth_noise(L, 5) * 100.0).astype(np.float32)
+    sp, nz = O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(n.astype(np.float64), SR)
+    fac = np.float32(O.AudioMixer.snr_factor(sp, nz, 0.0))
+    _, speech, _, _ = O.preprocess_audio_pair_signals(sp, nz, 200, 5, 25.0, snr_db=0.0)
+    bad = _run_emul4(emul, s, n, L, fac, 5, gain=1.0)
+    good = _run_emul4(emul, s, n, L, fac, 5, gain=fac)
+    assert np.max(np.abs(bad["speech"] - speech)) > 10 * TOL_DB
+    assert np.max(np.abs(good["speech"] - speech)) <= TOL_DB
+
+
+@pytest.mark.parametrize("f2", [False, True], ids=["f4", "f2"])
+@pytest.mark.parametrize("n_noise", [5000, 1121, 640, 333, 15999, 16000, 40000])
+def test_in_kernel_noise_tiling(emul, n_noise, f2):
+    """dp:125-128: a noise file shorter than the speech is doubled until it covers it and truncated == noise[i mod Ln].
+    The stage code addresses the stored period itself (interior groups that do not straddle a period boundary keep
+    the fast loads, the others take the edge loader) and must equal the oracle run on the materialised tiling."""
+    L = 16000
+    s = O.synth_speech(L, SR, 11).astype(np.float32)
+    n = O.synth_noise(n_noise, 11).astype(np.float32)
+    sp, nz = O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(n.astype(np.float64), SR)
+    mixed, speech, noise, msig = O.preprocess_audio_pair_signals(sp, nz, 200, 5, 25.0, snr_db=3.0)
+    nfit = fitted_noise(s, n)
+    fac = np.float32(O.AudioMixer.snr_factor(O.AudioSignal(s.astype(np.float64), SR), O.AudioSignal(nfit.astype(np.float64), SR), 3.0))
+    gain = np.float32(float(fac) / 10.0 ** (-3.0 / 20.0))
+    row = np.zeros(L, np.float32)                       # only the first min(Ln, L) samples of the row exist
+    m = min(n_noise, L)
+    row[:m] = n[:m]
+    row[m:] = np.nan                                    # anything read past the period would poison the result
+    got = _run_emul4(emul, s, row, L, fac, 5, gain=gain, period=n_noise, f2=f2)
+    for k, ref in (("speech", speech), ("noise", noise), ("mixed", mixed)):
+        assert np.max(np.abs(got[k] - ref)) <= TOL_DB, k
+    assert np.max(np.abs(got["mixed_pcm"] - msig.get_data())) <= TOL_PCM * np.max(np.abs(msig.get_data()))

@@ -34,7 +34,7 @@ def test_c_abi_status_codes(eng, native):
     assert lib.avse_forward(eng._ctx, ctypes.byref(a), None) == -1          # AVSE_E_ARG: NULL speech / max_key
     assert b"required" in lib.avse_last_error()
     assert lib.avse_forward(None, ctypes.byref(a), None) == -1
-    assert lib.avse_snr_factor(eng._ctx, None, None, 0, 0, None, 1, 10, None, None, None, None, None) == -1
+    assert lib.avse_snr_factor(eng._ctx, None, None, 0, 0, None, None, 1, 10, None, None, None, None, None, None) == -1
     h = ctypes.c_void_p()
     assert lib.avse_create(16000, 0.0, 8000.0, 9999, ctypes.byref(h)) == -1 and not h.value   # bad device index
     assert lib.avse_create(16000, 9000.0, 8000.0, 0, ctypes.byref(h)) == -2 and not h.value   # AVSE_E_CONFIG: fmin > fmax
