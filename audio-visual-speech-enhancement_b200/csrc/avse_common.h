@@ -7,8 +7,10 @@
 
 #if defined(__CUDACC__)
 #define AVSE_HD __host__ __device__ __forceinline__
+#define AVSE_HD_COLD __host__ __device__ __noinline__     // cold helpers: ONE copy, kept out of the hot instruction stream
 #else
 #define AVSE_HD inline
+#define AVSE_HD_COLD inline
 #endif
 
 namespace avse {

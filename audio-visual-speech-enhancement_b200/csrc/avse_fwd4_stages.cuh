@@ -52,12 +52,13 @@ AVSE_HD void lane4_const_init(int lane, const float* s_win, const vec2* s_tw, La
 // periodically tiled noise (dp:125-128, period_n > 0) -- when the group's 1 120 samples do not straddle a period
 // boundary.  nz_shift is then the offset that maps the group's sample indices into the stored period:
 // noise[i] = nz[i + nz_shift] for every i of the group.
-template <typename S>
+// TILED = false compiles the period logic out (the common kernel instantiation: see avse_forward4_kernel).
+template <typename S, bool TILED>
 AVSE_HD bool group4_interior(const FwdTileT<S>& tl, int& nz_shift) {
     nz_shift = 0;
     const int a = tl.t0 * HOP - HALF;                       // first sample of the group
     if (!(tl.nz != nullptr && a >= 0 && (tl.t0 + 3) * HOP + HALF <= tl.vmin && tl.t0 + 3 < tl.T)) return false;
-    if (tl.period_n > 0) {
+    if (TILED && tl.period_n > 0) {
         const int q = a / tl.period_n;
         if ((a + (F4 - 1) * HOP + NFFT - 1) / tl.period_n != q) return false;
         nz_shift = -q * tl.period_n;
@@ -85,12 +86,23 @@ AVSE_HD void p4_load_raw(const FwdTileT<S>& tl, int nz_shift, int lane, float (&
 
 // Rounds 0..3 of an interior group: frame f, column n2 = lane.  Also stores the mixture PCM (dp:133) of the
 // group's own four hops (strides 8..23 of the batch) for the residues n2 < 32.
-// The raw noise samples are scaled by the level equaliser tl.gain here, once per group (see FwdTileT).
+// The raw noise samples are scaled by the level equaliser tl.gain here (see FwdTileT).
+// AVSE_P1_ROLL (tuning switch, A/B-measured on B200 -- profiles/README.md round 2):
+//   9 = all 28 strides scaled up front, mixture PCM stored first, four frames unrolled   (0.549 ms, the default)
+//   0 = scaled / stored frame by frame in consumption order, four frames unrolled         (0.558 ms)
+//   4 = ONE copy of the column code in a rolled loop whose 16-stride window slides through the raw registers by
+//       rotation: 590 fewer instructions in a hot loop that exceeds the 32 KB L1.5 instruction cache   (0.553 ms)
+//   2 = two frames per iteration
+#if !defined(AVSE_P1_ROLL)
+#define AVSE_P1_ROLL 9
+#endif
 template <typename S>
-AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs)[RAW4], float (&rn)[RAW4],
+AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4],
                                const Lane4Const& lc, float* frames) {
+    const float gain = tl.gain;
+#if AVSE_P1_ROLL == 9      // round-1 order: everything scaled up front, the mixture PCM stored first
 #pragma unroll
-    for (int j = 0; j < RAW4; ++j) rn[j] *= tl.gain;
+    for (int j = 0; j < RAW4; ++j) rn[j] *= gain;
     if (tl.mixed_pcm != nullptr) {
         float* pm = tl.mixed_pcm + tl.t0 * HOP + lane;
 #pragma unroll
@@ -103,6 +115,51 @@ AVSE_HD void stage4_pass1_main(const FwdTileT<S>& tl, int lane, const float (&rs
         for (int j = 0; j < 16; ++j) x[j] = cmake(rs[4 * f + j] * lc.win[j], rn[4 * f + j] * lc.win[j]);
         p4_column(x, lc.tw, frames + f * FRAME4_F + 2 * lane);
     }
+#elif AVSE_P1_ROLL == 0
+#pragma unroll
+    for (int j = 0; j < 12; ++j) rn[j] *= gain;
+#pragma unroll
+    for (int f = 0; f < F4; ++f) {
+#pragma unroll
+        for (int j = 12; j < 16; ++j) rn[4 * f + j] *= gain;
+        if (tl.mixed_pcm != nullptr) {         // this frame's own hop (dp:133): strides 8..11 of its window
+            float* pm = tl.mixed_pcm + (tl.t0 + f) * HOP + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pm[N2 * j] = rs[4 * f + 8 + j] + tl.factor * rn[4 * f + 8 + j];
+        }
+        cpx x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = cmake(rs[4 * f + j] * lc.win[j], rn[4 * f + j] * lc.win[j]);
+        p4_column(x, lc.tw, frames + f * FRAME4_F + 2 * lane);
+    }
+#else
+    constexpr int STEP = AVSE_P1_ROLL == 4 ? 1 : 2;      // frames per loop iteration
+    constexpr int W = 16 + 4 * (STEP - 1);              // strides the iteration reads
+#pragma unroll
+    for (int j = 0; j < 12; ++j) rn[j] *= gain;
+    float* pm = tl.mixed_pcm != nullptr ? tl.mixed_pcm + tl.t0 * HOP + lane : nullptr;
+    float* dst = frames + 2 * lane;
+#pragma unroll 1
+    for (int it = 0; it < F4 / STEP; ++it) {
+#pragma unroll
+        for (int j = 12; j < W; ++j) rn[j] *= gain;
+#pragma unroll
+        for (int f = 0; f < STEP; ++f) {
+            if (pm != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pm[N2 * j] = rs[4 * f + 8 + j] + tl.factor * rn[4 * f + 8 + j];
+                pm += HOP;
+            }
+            cpx x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(rs[4 * f + j] * lc.win[j], rn[4 * f + j] * lc.win[j]);
+            p4_column(x, lc.tw, dst);
+            dst += FRAME4_F;
+        }
+#pragma unroll
+        for (int j = 0; j + 4 * STEP < RAW4; ++j) { rs[j] = rs[j + 4 * STEP]; rn[j] = rn[j + 4 * STEP]; }
+    }
+#endif
 }
 
 // Round 4 of an interior group: lane = (f = lane / 8, r = lane % 8), column n2 = 32 + r of frame f.
@@ -147,7 +204,7 @@ AVSE_HD void stage4_pass1_tail(const FwdTileT<S>& tl, int nz_shift, int lane, co
 
 // Edge / generic groups (first and last frames of an utterance, short or zero-padded signals): every sample
 // goes through the reflect + zero-pad loader.  Cold code, rolled over the five rounds.
-template <typename S>
+template <typename S, bool TILED>
 AVSE_HD void stage4_pass1_edge(const FwdTileT<S>& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
 #pragma unroll 1
     for (int round = 0; round < 5; ++round) {
@@ -160,7 +217,7 @@ AVSE_HD void stage4_pass1_edge(const FwdTileT<S>& tl, int lane, const float* s_w
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             rs[j] = load_sample_edge(tl.sp, base + N2 * j, tl.L, tl.valid_s);
-            rn[j] = tl.gain * load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n, tl.period_n);
+            rn[j] = tl.gain * load_sample_edge(tl.nz, base + N2 * j, tl.L, tl.valid_n, TILED ? tl.period_n : 0);
         }
         if (tl.mixed_pcm != nullptr && t_raw < tl.T) {
 #pragma unroll

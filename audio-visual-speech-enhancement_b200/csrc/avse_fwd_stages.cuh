@@ -108,6 +108,11 @@ struct FwdTileT {
 };
 using FwdTile = FwdTileT<float>;
 
+// Sample i of a periodically tiled noise (dp:125-128).  Out of line: the integer modulo is ~25 instructions and the edge
+// loaders are unrolled 16 x, which would put 400 cold instructions into the middle of the kernel's instruction stream.
+template <typename S>
+AVSE_HD_COLD float load_sample_periodic(const S* p, int i, int period) { return (float)p[i % period]; }
+
 template <typename S>
 AVSE_HD float load_sample_edge(const S* p, int i, int L, int valid, int period = 0) {
     // np.pad(y, n_fft//2, mode='reflect') on the length-L (zero padded) signal
@@ -115,7 +120,7 @@ AVSE_HD float load_sample_edge(const S* p, int i, int L, int valid, int period =
     i = i >= L ? 2 * (L - 1) - i : i;
     i = i < 0 ? 0 : i;
     if (p == nullptr || i >= valid) return 0.0f;
-    return (float)p[period > 0 ? i % period : i];
+    return period > 0 ? load_sample_periodic(p, i, period) : (float)p[i];
 }
 
 // A group is "interior" when both of its frames exist and all their samples are present in both

@@ -393,7 +393,7 @@ struct MixGain { float gain, resid; };
 static __device__ __forceinline__ MixGain mix_gain(const avse_forward_args& A, int u) {
     const float f = A.factor ? A.factor[u] : 1.0f;
     MixGain m;
-    if (A.equalizer) { m.gain = A.equalizer[u]; m.resid = m.gain != 0.0f ? f / m.gain : 0.0f; }
+    if (A.equalizer) { m.gain = A.equalizer[u]; m.resid = m.gain != 0.0f ? __fdividef(f, m.gain) : 0.0f; }
     else { m.gain = f; m.resid = 1.0f; }
     return m;
 }
@@ -577,12 +577,16 @@ constexpr int F4_SM_TW = F4_SM_WIN + NFFT;                     // [16][40] vec2
 constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec2 (wa, wb)
 constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 2;        // [80] ivec4
 constexpr int F4_SM_MIN = F4_SM_LOC + NMEL * 4;                // [warps][3][32] per-lane running minima
-constexpr int F4_SMEM_F = F4_SM_MIN + F4_WARPS * 96;
+constexpr int F4_SM_UTT = F4_SM_MIN + F4_WARPS * 96;           // [warps][2][2] per-utterance (gain, noise period), see the kernel
+constexpr int F4_SMEM_F = F4_SM_UTT + F4_WARPS * 4;
 constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
-static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0, "table alignment");
+static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0 && (F4_SM_UTT % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
 
-template <typename S>
+// TILED: the batch carries per-utterance noise periods (avse_forward_args::noise_period, dp:125-128).  A separate
+// instantiation, because this kernel sits on the 255-register / 32 KB instruction-cache cliff: with the period logic
+// compiled into the common kernel, batches that do not use it ran 4.5 % slower (profiles/README.md, round 2).
+template <typename S, bool TILED>
 __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -615,9 +619,11 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     float mx[3] = {neg_inf(), neg_inf(), neg_inf()};
     float* mn = smem + F4_SM_MIN + warp * 96;
     mn[lane] = -neg_inf(); mn[32 + lane] = -neg_inf(); mn[64 + lane] = -neg_inf();
-    // per-utterance scalars that ride along the tile loop, packed to keep the loop-carried register count down
-    struct Utt { int vs, vn, period; float gain, factor; };
-    Utt ut = {0, 0, 0, 0.0f, 0.0f};
+    float factor = 0.0f;          // residual factor (see FwdTileT): rides along the tile loop like vs / vn
+    int vs = 0, vn = 0;
+    // the level-equaliser gain (and the noise period) are needed once per tile, at the top of pass 1: they live in a
+    // per-warp shared-memory slot, double-buffered by the utterance's parity, instead of in loop-carried registers
+    float* utt_sm = smem + F4_SM_UTT + warp * 4;
     const S* in_speech = reinterpret_cast<const S*>(A.speech);
     const S* in_noise = reinterpret_cast<const S*>(A.noise);
     constexpr int LINE = 128 / (int)sizeof(S);        // samples per 128-byte line
@@ -659,37 +665,40 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     };
     // Software-pipelined tile loop: the raw samples of tile it+1 are loaded into registers before the dB stage of
     // tile it, so their HBM/L2 latency is covered by the dB arithmetic and stores instead of stalling pass 1.
-    auto load_utt = [&](int uu, Utt& o) {
-        o.vs = A.len_speech ? A.len_speech[uu] : A.L;
-        o.vn = A.len_noise ? A.len_noise[uu] : o.vs;
-        o.vs = o.vs < 0 ? 0 : (o.vs < A.L ? o.vs : A.L);
-        o.vn = o.vn < 0 ? 0 : (o.vn < A.L ? o.vn : A.L);
+    auto load_utt = [&](int uu, int& ovs, int& ovn, float& of) {
+        ovs = A.len_speech ? A.len_speech[uu] : A.L;
+        ovn = A.len_noise ? A.len_noise[uu] : ovs;
+        ovs = ovs < 0 ? 0 : (ovs < A.L ? ovs : A.L);
+        ovn = ovn < 0 ? 0 : (ovn < A.L ? ovn : A.L);
         const MixGain mg = mix_gain(A, uu);
-        o.gain = mg.gain;
-        o.factor = mg.resid;
-        o.period = A.noise_period ? A.noise_period[uu] : 0;
-        if (o.period <= 0 || o.period >= o.vn) o.period = 0;      // the stored noise already covers [0, vn)
+        of = mg.resid;
+        utt_sm[2 * (uu & 1)] = mg.gain;                       // every lane writes the same value
+        if (TILED) {
+            int period = A.noise_period[uu];
+            if (period <= 0 || period >= ovn) period = 0;     // the stored noise already covers [0, vn)
+            reinterpret_cast<int*>(utt_sm)[2 * (uu & 1) + 1] = period;
+        }
     };
-    auto make_tile = [&](int uu, int gg, const Utt& o) {
+    auto make_tile = [&](int uu, int gg, int tvs, int tvn, float tf) {
         FwdTileT<S> t;
         t.sp = in_speech + (size_t)uu * A.in_stride;
         t.nz = in_noise + (size_t)uu * A.in_stride;
         t.L = A.L;
-        t.valid_s = o.vs;
-        t.valid_n = o.vn;
-        t.vmin = o.vs < o.vn ? o.vs : o.vn;
+        t.valid_s = tvs;
+        t.valid_n = tvn;
+        t.vmin = tvs < tvn ? tvs : tvn;
         t.T = P.T;
         t.t0 = gg * F4;
-        t.gain = o.gain;
-        t.factor = o.factor;
-        t.period_n = o.period;
+        t.factor = tf;
+        t.gain = 0.0f;            // read from the slot at the top of pass 1
+        t.period_n = TILED ? reinterpret_cast<const int*>(utt_sm)[2 * (uu & 1) + 1] : 0;
         t.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)uu * A.pcm_stride : nullptr;
         return t;
     };
-    load_utt(u, ut);
-    FwdTileT<S> tl = make_tile(u, g, ut);
+    load_utt(u, vs, vn, factor);
+    FwdTileT<S> tl = make_tile(u, g, vs, vn, factor);
     int nz_shift = 0;
-    bool interior = group4_interior(tl, nz_shift);
+    bool interior = group4_interior<S, TILED>(tl, nz_shift);
     float rs[RAW4], rn[RAW4], ts[16], tn[16];
     if (interior) {
         p4_load_raw(tl, nz_shift, lane, rs, rn);
@@ -699,11 +708,12 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     for (int it = 0; it < n_tiles; ++it) {
         prefetch_ahead(it, u, g);
         // ---- pass 1 ----
+        tl.gain = utt_sm[2 * (u & 1)];
         if (interior) {
             stage4_pass1_main(tl, lane, rs, rn, lc, frames);
             stage4_pass1_tail_compute(tl, lane, ts, tn, s_win, s_tw, frames);
         } else {
-            stage4_pass1_edge(tl, lane, s_win, s_tw, frames);
+            stage4_pass1_edge<S, TILED>(tl, lane, s_win, s_tw, frames);
         }
         __syncwarp();
 
@@ -723,13 +733,14 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
 
         // ---- next tile: issue its loads now ----
         int u2 = u, g2 = g + 1;
-        Utt ut2 = ut;
+        int vs2 = vs, vn2 = vn;
+        float factor2 = tl.factor;
         const bool last_of_utt = g2 == P.G;
         const bool have_next = it + 1 < n_tiles;
-        if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, ut2); }
-        FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, ut2);
+        if (last_of_utt) { g2 = 0; ++u2; if (have_next) load_utt(u2, vs2, vn2, factor2); }
+        FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
         int nz_shift2 = 0;
-        const bool interior2 = have_next && group4_interior(tnx, nz_shift2);
+        const bool interior2 = have_next && group4_interior<S, TILED>(tnx, nz_shift2);
         if (interior2) {
             p4_load_raw(tnx, nz_shift2, lane, rs, rn);
             p4_load_tail_raw(tnx, nz_shift2, lane, ts, tn);
@@ -750,7 +761,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         __syncwarp();
 
         if (last_of_utt || !have_next) flush_max(u);
-        u = u2; g = g2; ut = ut2;
+        u = u2; g = g2; vs = vs2; vn = vn2;
         tl = tnx;
         interior = interior2;
     }
@@ -797,8 +808,10 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     if (use_f4) {
         static thread_local int configured4_dev = -1;
         if (configured4_dev != dev) {
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
             configured4_dev = dev;
         }
         P.G = (P.T + F4 - 1) / F4;
@@ -809,8 +822,11 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
         const long long nwarps4 = blocks4 * F4_WARPS;
         P.total_tiles = (int)total4;
         P.per_warp = (int)((total4 + nwarps4 - 1) / nwarps4);
-        if (i16) avse_forward4_kernel<short><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        else avse_forward4_kernel<float><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        const bool tiled = a.noise_period != nullptr;
+        if (i16 && tiled) avse_forward4_kernel<short, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else if (i16) avse_forward4_kernel<short, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else if (tiled) avse_forward4_kernel<float, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else avse_forward4_kernel<float, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

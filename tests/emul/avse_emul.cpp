@@ -175,14 +175,14 @@ extern "C" int emul_forward4_ex(const float* speech, const float* noise, int L, 
     for (int g = 0; g < G; ++g) {
         tl.t0 = g * F4;
         int nz_shift = 0;
-        if (group4_interior(tl, nz_shift)) {
+        if (group4_interior<float, true>(tl, nz_shift)) {
             for (int lane = 0; lane < 32; ++lane) {
                 p4_load_raw(tl, nz_shift, lane, w.rs[lane], w.rn[lane]);
-                stage4_pass1_main(tl, lane, w.rs[lane], w.rn[lane], w.lc[lane], w.frames);
+                stage4_pass1_main(tl, lane, w.rs[lane], w.rn[lane], w.lc[lane], w.frames);     // consumes (rescales / rotates) rs, rn
             }
             for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, nz_shift, lane, h.window.data(), s_tw, w.frames);
         } else {
-            for (int lane = 0; lane < 32; ++lane) stage4_pass1_edge(tl, lane, h.window.data(), s_tw, w.frames);
+            for (int lane = 0; lane < 32; ++lane) stage4_pass1_edge<float, true>(tl, lane, h.window.data(), s_tw, w.frames);
         }
         for (int r = 0; r < 2; ++r) {
             for (int lane = 0; lane < 32; ++lane) p4_pass2_compute(lane, r, w.frames, w.x[lane]);
