@@ -52,6 +52,11 @@ def parse_args():
     ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inverse", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="also run the step back to back for at least this many seconds and report the steady-state figure (0: skip)")
+    ap.add_argument("--corpus", type=int, default=0,
+                    help="BASELINE configs[2]: a corpus of this many utterances sharded contiguously by utterance over the ranks "
+                         "(engine.shard_range, strong scaling); a step is one pass over the rank's whole shard in launches of --batch")
     return ap.parse_args()
 
 
@@ -333,6 +338,146 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def copy_ceiling(torch, dist, world, device, h_in, h_out, n_chunks, steps, barrier):
+    """Host-link ceiling of the e2e step: the SAME pinned buffers and byte counts moved by bare cudaMemcpyAsync -- H2D on one
+    stream, D2H on another, chunked like the pipeline, no kernels -- on all ranks at once (max over ranks).  What the
+    pipeline can reach at best on this host at this number of GPUs."""
+    d_in = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in h_in]
+    d_out = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in h_out]
+    s_up, s_down = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    B = h_in[0].shape[0]
+    ch = max(1, B // n_chunks)
+
+    def one_step():
+        for lo in range(0, B, ch):
+            with torch.cuda.stream(s_up):
+                for h, d in zip(h_in, d_in):
+                    d[lo:lo + ch].copy_(h[lo:lo + ch], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                for h, d in zip(h_out, d_out):
+                    h[lo:lo + ch].copy_(d[lo:lo + ch], non_blocking=True)
+
+    def timed(fn, streams):
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in streams]
+        for (a, _), st in zip(ev, streams):
+            a.record(st)
+        for _ in range(steps):
+            fn()
+        for (_, b), st in zip(ev, streams):
+            b.record(st)
+        barrier()
+        ms = max(a.elapsed_time(b) for a, b in ev) / steps
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    one_step()
+    both = timed(one_step, [s_up, s_down])
+
+    def up_only():
+        with torch.cuda.stream(s_up):
+            for h, d in zip(h_in, d_in):
+                d.copy_(h, non_blocking=True)
+
+    def down_only():
+        with torch.cuda.stream(s_down):
+            for h, d in zip(h_out, d_out):
+                h.copy_(d, non_blocking=True)
+
+    up = timed(up_only, [s_up])
+    down = timed(down_only, [s_down])
+    nb_in = sum(t.numel() * t.element_size() for t in h_in)
+    nb_out = sum(t.numel() * t.element_size() for t in h_out)
+    return {"ms_per_step": both, "h2d_alone_gbs": nb_in / up / 1e6, "d2h_alone_gbs": nb_out / down / 1e6,
+            "bidirectional_gbs": (nb_in + nb_out) / both / 1e6, "ranks": world,
+            "what": "bare pinned cudaMemcpyAsync of the step's buffers, H2D and D2H streams concurrently, all ranks at once, max over ranks"}
+
+
+def corpus_batch(torch, n, device, base_seed):
+    """n utterances of the synthetic corpus (synth_batch in blocks of 500 to bound the generator's temporaries)."""
+    speech = torch.empty((n, L), device=device)
+    noise = torch.empty((n, L), device=device)
+    for lo in range(0, n, 500):
+        m = min(500, n - lo)
+        s, z = synth_batch(torch, m, device, seed=base_seed + lo)
+        speech[lo:lo + m] = s
+        noise[lo:lo + m] = z
+    return speech, noise
+
+
+def run_corpus(args, torch, dist, eng, eng_mod, device, rank, world):
+    """BASELINE configs[2]: N utterances sharded contiguously by utterance over the ranks (engine.shard_range), no collective on
+    the data path.  One step = one pass over the rank's whole shard (resident in HBM), in launches of at most --batch utterances.
+    Strong scaling: the corpus is fixed, the shard shrinks with the number of GPUs."""
+    lo, hi = eng_mod.shard_range(args.corpus, rank, world)
+    n = hi - lo
+    speech, noise = corpus_batch(torch, n, device, base_seed=lo)
+    launch = min(n, max(1, args.batch if args.batch != 1000 else 12500))
+    outs = []
+    for a in range(0, n, launch):
+        m = min(launch, n - a)
+        outs.append({k: torch.empty((m, N_VIDEO_SLICES, 80, 20), device=device) for k in ("speech", "noise", "mixed")})
+        outs[-1]["mixed_pcm"] = torch.empty((m, L), device=device)
+
+    def step():
+        for j, a in enumerate(range(0, n, launch)):
+            m = min(launch, n - a)
+            f, keys = eng.snr_factor(speech[a:a + m], noise[a:a + m], max_key=outs[j].get("max_key"))
+            r = eng.forward_raw(speech[a:a + m], noise[a:a + m], L=L, factor=f, n_slices=N_VIDEO_SLICES, max_key=keys, out=outs[j])
+            eng.floor3_(r["speech"], r["noise"], r["mixed"], keys)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_max = -(-args.corpus // world)
+    line = {
+        "metric": "audio-sec/sec", "value": args.corpus * UTT_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: %d-utterance synthetic corpus (3 s, 16 kHz, white noise @ 0 dB) sharded contiguously by "
+                               "utterance over %d B200 (engine.shard_range): mix + 3x log-mel + top_db floor + 15 AV-aligned slices + mixed PCM" % (args.corpus, world),
+                   "corpus_utterances": args.corpus, "utterances_per_gpu": n_max, "utterances_per_launch": launch,
+                   "sharding": "contiguous by utterance, no collective", "n_gpus": world,
+                   "l2": "per-launch working set %.1f GB >> 126 MB L2; no explicit flush" % (launch * L * 18 / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": "step (snr_factor + avse_forward4_kernel + floor)", "achieved": n_max * L * BYTES_PER_SAMPLE_PAIR / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": n_max * L * BYTES_PER_SAMPLE_PAIR / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "note": "whole step of the largest shard (per-kernel figures: the default workload's line)"},
+        "gpu_launches": 3 * len(outs) * args.steps, "clocks": clocks, "cpu_baseline": None, "e2e": None,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     set_workload(args.seconds, args.snr_sweep)
@@ -355,6 +500,8 @@ def main():
     eng_mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
     eng = eng_mod.SpectralEngine(SR, FPS, SLICE_MS, device=device)
     B = args.batch
+    if args.corpus:
+        return run_corpus(args, torch, dist, eng, eng_mod, device, rank, world)
 
     speech, noise = synth_batch(torch, B, device, seed=rank)
     T = eng.n_frames(L)
@@ -430,6 +577,37 @@ def main():
         "gpu_launches": 3 * args.steps, "clocks": clocks, "host_cpus_bound_to_gpu_numa_node": numa,
     }
 
+    # ---------------- steady state: the same step back to back for >= --sustain-s seconds ----------------
+    if args.sustain_s > 0:
+        # blocks of steps, each bracketed by CUDA events, until the events add up to the requested time (the host stays ahead:
+        # a block is queued while the previous one still runs only at the block boundary, one ~20 us bubble per >= 0.25 s block)
+        blk = max(args.steps, int(0.25 / (ms_per_step * 1e-3)) + 1)
+        sampler2 = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler2.start()
+        sus_total, n_s = 0.0, 0
+        while sus_total < args.sustain_s * 1e3:
+            s0 = torch.cuda.Event(enable_timing=True)
+            s1 = torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(blk):
+                step()
+            s1.record()
+            s1.synchronize()
+            ts = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)      # every rank sees the same total and leaves the loop together
+            sus_total += float(ts[0])
+            n_s += blk
+        barrier()
+        clocks2 = sampler2.stop() if rank == 0 else None
+        sus_ms = sus_total / n_s
+        line["sustained"] = {"value": world * B * UTT_SECONDS / (sus_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": sus_ms, "steps": n_s,
+                             "seconds": sus_total * 1e-3, "clocks": clocks2,
+                             "note": "same step() as the headline, back to back in blocks of %d; the headline's %d timed steps last only %.0f ms" % (
+                                 blk, args.steps, ms_total)}
+
     # ---------------- inverse path (config 4), reported beside the headline ----------------
     if not args.no_inverse and hasattr(eng._lib, "avse_inverse"):
         res = step()
@@ -496,8 +674,10 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te[0])
         d2h = 3 * B * N_VIDEO_SLICES * 80 * 20 * 4 + B * L * 4
+        ceiling = copy_ceiling(torch, dist, world, device, [h_s, h_n], h_out + [h_pcm], NCH, steps_e, barrier)
         line["e2e"] = {"value": world * B * UTT_SECONDS / (e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e_ms,
                        "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": d2h,
+                       "ceiling": ceiling, "frac_of_ceiling": ceiling["ms_per_step"] / e_ms,
                        "api": "engine.HostPipeline.submit (SNR factor + fused forward + floor over the C ABI) on pinned host buffers; %d chunks per step round-robin over %d streams so H2D, kernels and D2H overlap within and across steps; all copies inside the timed region" % (NCH, args.e2e_streams),
                        "gpu_launches": 3 * NCH * steps_e,
                        "bound": "PCIe: D2H %.0f MB + H2D %.0f MB per step" % (d2h / 1e6, 2 * B * L * 4 / 1e6)}

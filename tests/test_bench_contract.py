@@ -53,3 +53,16 @@ def test_gpu_arm_line_small_batch():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["inverse"]["value"] > 0
+    su = d["sustained"]                                   # >= 2 s of back-to-back steps beside the short headline region
+    assert su["seconds"] >= 2.0 and su["steps"] >= d["steps"] and su["value"] > 0
+    c = e["ceiling"]                                      # bare pinned-memcpy ceiling of the same buffers, measured live
+    assert c["ms_per_step"] > 0 and c["h2d_alone_gbs"] > 0 and c["d2h_alone_gbs"] > 0 and 0 < e["frac_of_ceiling"] <= 1.5
+
+
+@pytest.mark.gpu
+def test_corpus_mode_line():
+    """BASELINE configs[2] shape at a small size: a corpus sharded by utterance (strong scaling), one pass per step."""
+    d = _run(["--corpus", "96", "--batch", "40", "--steps", "2", "--warmup", "3"])
+    assert BASE_KEYS <= set(d) and d["scaling"] == "strong" and d["n_gpus"] == 1
+    assert d["config"]["corpus_utterances"] == 96 and d["config"]["utterances_per_launch"] == 40
+    assert d["gpu_launches"] == 3 * 3 * 2 and d["value"] > 0
