@@ -241,11 +241,15 @@ AVSE_HD void stage4_pass1_edge(const FwdTileT<S>& tl, int lane, const float* s_w
 // pass 2, round r: lane = (f = 2 r + lane / 16, k1 = lane % 16): row -> in-place DFT-40 -> (after a warp
 // sync) natural order Z[k1 + 16 k2] over the same frame buffer.
 // ---------------------------------------------------------------------------------------
-AVSE_HD void p4_pass2_compute(int lane, int r, const float* frames, cpx (&x)[40]) {
+AVSE_HD void p4_pass2_load(int lane, int r, const float* frames, cpx (&x)[40]) {
     const int f = 2 * r + (lane >> 4), k1 = lane & 15;
     const float* row = frames + f * FRAME4_F + k1 * ROW_F;
 #pragma unroll
     for (int q = 0; q < 20; ++q) cload2(row + 4 * q, x[2 * q], x[2 * q + 1]);
+}
+
+AVSE_HD void p4_pass2_compute(int lane, int r, const float* frames, cpx (&x)[40]) {
+    p4_pass2_load(lane, r, frames, x);
     dft40_inplace(x);
 }
 

@@ -211,11 +211,15 @@ AVSE_HD void stage_pass1(const FwdTile& tl, int lane, const float* s_win2, const
 // pass 2: lane = (f = lane/16, k1 = lane%16): load row, in-place DFT-40; after a warp sync the
 // results are stored in natural order Z[k1 + 16 k2] over the same frame buffer.
 // ---------------------------------------------------------------------------------------
-AVSE_HD void pass2_compute(int lane, const float* frames, cpx (&x)[40]) {
+AVSE_HD void pass2_load(int lane, const float* frames, cpx (&x)[40]) {
     const int f = lane >> 4, k1 = lane & 15;
     const float* row = frames + f * FRAME_F + k1 * ROW_F;
 #pragma unroll
     for (int q = 0; q < 20; ++q) cload2(row + 4 * q, x[2 * q], x[2 * q + 1]);
+}
+
+AVSE_HD void pass2_compute(int lane, const float* frames, cpx (&x)[40]) {
+    pass2_load(lane, frames, x);
     dft40_inplace(x);
 }
 

@@ -20,6 +20,10 @@
 #include "avse_dft.cuh"
 #include "avse_fwd_stages.cuh"
 
+#if !defined(AVSE_INV_POST_UNROLL)
+#define AVSE_INV_POST_UNROLL 3      // unroll factor of the post stage's bin loop (21 bins): code size vs loads in flight
+#endif
+
 namespace avse {
 
 constexpr int INV_FPG = 4;                 // real frames per group (2 packed complex FFTs)
@@ -157,7 +161,7 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
     const bool liveA = EXT || fr[FRAME_ZERO_F] != 0.0f;       // see inv_mark_nonzero
     const bool liveB = EXT || fr[FRAME_ZERO_F + 1] != 0.0f;
     constexpr int LAST_N = (NBINS - 1) - 15 * POST_CHUNK;
-#pragma unroll 3
+    AVSE_UNROLL_N_(AVSE_INV_POST_UNROLL)
     for (int i = 0; i < POST_CHUNK; ++i) {
         // chunk 15 holds only bins 315..320: the tail iterations compute on harmless in-range slots and keep their stores
         // predicated off (a branch here diverges in every iteration of the hot loop); the Nyquist bin (lin = 0) stores 0
@@ -199,12 +203,18 @@ AVSE_HD void inv_stage_post(int lane, const ivec4* s_col, const float* ybuf, flo
 // W_640^{n1' k2'}; after a warp sync the 40 results are written as row n1' = [k2'].
 // s_twT: [40][16] vec2, W_640^{n1' k2'} with n1' minor (conflict-free for lane = n1').
 // ---------------------------------------------------------------------------------------
-AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames, cpx (&x)[40]) {
+// The three pieces of pass A (gather, DFT-40, twiddle) are separate functions so that the kernel can run pass 2 and pass A
+// through ONE copy of the DFT-40 codelet (a rolled two-phase loop): the kernel's hot loop is larger than the 32 KB L1.5
+// instruction cache and "no instruction" was its top stall reason (profiles/inverse_kernels_r1.txt).
+AVSE_HD void inv_passA_load(int lane, const float* frames, cpx (&x)[40]) {
     const int f = lane >> 4, n1 = lane & 15;
     const float* z = frames + f * FRAME_F + 2 * n1;
 #pragma unroll
     for (int n2 = 0; n2 < 40; ++n2) x[n2] = cload(z + 2 * N1 * n2);
-    dft40_inplace(x);
+}
+
+AVSE_HD void inv_passA_twiddle(int lane, const vec2* s_twT, cpx (&x)[40]) {
+    const int n1 = lane & 15;
 #pragma unroll
     for (int c = 0; c < 5; ++c)
 #pragma unroll
@@ -214,6 +224,12 @@ AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames,
             const vec2 t = s_twT[k2 * N1 + n1];
             x[idx] = cmul(x[idx], t.x, t.y);
         }
+}
+
+AVSE_HD void inv_passA_compute(int lane, const vec2* s_twT, const float* frames, cpx (&x)[40]) {
+    inv_passA_load(lane, frames, x);
+    dft40_inplace(x);
+    inv_passA_twiddle(lane, s_twT, x);
 }
 
 AVSE_HD void inv_passA_store(int lane, float* frames, const cpx (&x)[40]) {
@@ -248,6 +264,30 @@ AVSE_HD void inv_passB_column(int f, int k2, const float* s_win2, const float* f
         const cpx y = cmul_pp(x[k1], cmul_pp(cload(s_win2 + 2 * (N2 * k1 + k2)), cmake(INV_SCALE, -INV_SCALE)));
         c[k1] += cre(y);           // frame tA sample 40 k1 + k2
         c[k1 + 4] += cim(y);       // frame tA + 1 (= -Im / 640), one hop (4 rows) later
+    }
+}
+
+// Pass B as ONE rolled loop over four column rounds (r = 0, 1: the main rounds f = r with k2' = lane; r = 2, 3: the two ordered
+// side phases) so that the column code (DFT-16 + window) exists once in the instruction stream instead of three times.
+// Only the 20 accumulations differ per round.  Must be followed by a __syncwarp() for r >= 2 (the caller's loop does it).
+AVSE_HD void inv_stage_passB_round(int lane, int r, const float* s_win2, const float* frames, float (&acc)[INV_SIDE_ROWS], float* side) {
+    const bool main = r < 2;
+    const int f = main ? r : (lane >> 3);
+    const int k2 = main ? lane : 32 + (lane & 7);
+    if (!main && (lane >= 16 || f != r - 2)) return;
+    float c[20];
+    inv_passB_column(f, k2, s_win2, frames, c);
+    if (main) {
+        if (r == 0) {
+#pragma unroll
+            for (int j = 0; j < 20; ++j) acc[j] += c[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 20; ++j) acc[j + 8] += c[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 20; ++j) side[(j + 8 * f) * 8 + (lane & 7)] += c[j];
     }
 }
 

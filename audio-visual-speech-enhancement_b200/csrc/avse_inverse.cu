@@ -1,11 +1,13 @@
 // Inverse path (predict time): dB log-mel + mixture PCM -> PCM.  See include/avse_b200.h, avse_inv_stages.cuh.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/avse_b200.h"
 #include "avse_common.h"
 #include "avse_ctx.h"
 #include "avse_inv_stages.cuh"
+#include "avse_inv8_stages.cuh"
 
 using namespace avse;
 
@@ -19,8 +21,8 @@ __global__ void __launch_bounds__(128) avse_mel_to_coef_kernel(const float* __re
                                                                const float* __restrict__ tri_w, const float* __restrict__ tri_ipiv,
                                                                const float* __restrict__ tri_sup, float* __restrict__ work,
                                                                long long work_stride) {
-    const int u = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = blockIdx.x;                               // utterance on grid.x: B is not capped at 65 535
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
     if (t >= T_pad) return;
     float* dst = work + (size_t)u * work_stride + t;
     if (t >= T_use) {
@@ -54,6 +56,13 @@ __global__ void __launch_bounds__(128) avse_mel_to_coef_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 // kernel 2: phase of the mixture, lin * phase, packed inverse FFT, overlap-add in registers
 // ---------------------------------------------------------------------------------------------
+// Code-size switches (A/B-measured on B200, profiles/README.md round 2): the hot loop exceeds the 32 KB L1.5 instruction cache.
+#if !defined(AVSE_INV_SHARED_DFT40)
+#define AVSE_INV_SHARED_DFT40 1     // pass 2 and pass A share one DFT-40 copy (rolled two-phase loop)
+#endif
+#if !defined(AVSE_INV_ROLLED_PASSB)
+#define AVSE_INV_ROLLED_PASSB 1     // pass B main / side rounds share one column (DFT-16 + window) copy
+#endif
 constexpr int INV_WARPS = 6;
 constexpr int INV_THREADS = INV_WARPS * 32;
 constexpr int INV_SM_WIN = INV_WARPS * INV_WARP_SMEM_F;      // [640]
@@ -78,6 +87,9 @@ struct InvParams {
     int chunks;       // chunks per utterance
     int cg;           // groups per chunk
     int out_len;      // 160 (T_use - 1)
+    long long total_groups;   // I8 kernel: B * G groups, cut into one contiguous range per warp
+    int base_groups;          // I8 kernel: groups per warp (the first rem_warps warps take one more)
+    int rem_warps;
 };
 
 // EXT: explicit phase array (dp:99 signature) instead of the recomputed mixture STFT; a separate instantiation keeps each
@@ -167,6 +179,35 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                     const int m = lane + 32 * q;
                     if (m < NMEL) *reinterpret_cast<float4*>(ybuf + 4 * m) = cf[q];
                 }
+#if AVSE_INV_SHARED_DFT40
+                __syncwarp();
+                if (EXT) {
+                    const int tA = tl.t0 + 2 * (lane & 1);
+                    const vec2* ph = reinterpret_cast<const vec2*>(A.phase) + (size_t)u * A.phase_stride;
+                    const vec2* phA = tA < P.T_use ? ph + (size_t)tA * NBINS : nullptr;
+                    const vec2* phB = tA + 1 < P.T_use ? ph + (size_t)(tA + 1) * NBINS : nullptr;
+                    inv_stage_post<true>(lane, s_col, ybuf, frames, phA, phB);
+                    __syncwarp();
+                }
+                // pass 2 (phase 0: rows -> Z, then the post stage) and pass A (phase 1: V -> rows) through ONE copy of the
+                // DFT-40 codelet
+#pragma unroll 1
+                for (int phs = EXT ? 1 : 0; phs < 2; ++phs) {
+                    cpx x[40];
+                    if (phs == 0) pass2_load(lane, frames, x);
+                    else inv_passA_load(lane, frames, x);
+                    dft40_inplace(x);
+                    if (phs != 0) inv_passA_twiddle(lane, s_twT, x);
+                    __syncwarp();
+                    if (phs == 0) pass2_store(lane, frames, x);
+                    else inv_passA_store(lane, frames, x);
+                    __syncwarp();
+                    if (phs == 0) {
+                        inv_stage_post<false>(lane, s_col, ybuf, frames, nullptr, nullptr);
+                        __syncwarp();
+                    }
+                }
+#else
                 if (!EXT) {
                     __syncwarp();
                     {
@@ -193,12 +234,21 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
                     inv_passA_store(lane, frames, x);
                 }
                 __syncwarp();
+#endif
+#if AVSE_INV_ROLLED_PASSB
+#pragma unroll 1
+                for (int r = 0; r < 4; ++r) {
+                    inv_stage_passB_round(lane, r, s_win, frames, acc, side);
+                    if (r >= 2) __syncwarp();
+                }
+#else
                 inv_stage_passB_main(lane, s_win, frames, acc);
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {      // rolled: one copy of the column code for both side phases
                     inv_stage_passB_side(lane, ph, s_win, frames, side);
                     __syncwarp();
                 }
+#endif
             }
             const bool write = g >= g0;
             inv_stage_emit_main(lane, tl.t0, P.T_use, P.out_len, write, s_win, out, acc);
@@ -212,10 +262,182 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// I8 kernel: eight real frames (four packed FFTs) per group, 8 warps per SM.  See avse_inv8_stages.cuh.
+// ---------------------------------------------------------------------------------------------
+constexpr int I8_WARPS = 8;
+constexpr int I8_THREADS = I8_WARPS * 32;
+constexpr int I8_SM_WIN = I8_WARPS * I8_WARP_SMEM_F;         // [640] window
+constexpr int I8_SM_TW = I8_SM_WIN + NFFT;                   // [16][40] vec2   W^{n2 k1}, n2 minor
+constexpr int I8_SM_TWT = I8_SM_TW + N1 * N2 * 2;            // [40][16] vec2   W^{n1' k2'}, n1' minor
+constexpr int I8_SM_COL = I8_SM_TWT + N1 * N2 * 2;           // [SCAN4_BINS] ivec4 (b0, b1, w0 / 640, w1 / 640)
+constexpr int I8_SMEM_F = I8_SM_COL + SCAN4_BINS * 4;
+constexpr int I8_SMEM_BYTES = I8_SMEM_F * 4;
+static_assert((I8_SM_COL % 4) == 0 && (I8_SM_TW % 2) == 0 && (I8_WARP_SMEM_F % 4) == 0, "table alignment");
+static_assert(I8_SMEM_BYTES + 1024 <= 232448, "I8 shared memory must fit in one SM");
+
+template <bool EXT, typename O>
+__global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __grid_constant__ InvParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NFFT; i += I8_THREADS) smem[I8_SM_WIN + i] = P.window[2 * i];       // P.window holds (w, w) pairs
+    for (int i = threadIdx.x; i < N1 * N2; i += I8_THREADS) {
+        const int k1 = i / N2, n2 = i - k1 * N2;
+        const float re = P.tw1t[2 * i], im = P.tw1t[2 * i + 1];
+        smem[I8_SM_TW + 2 * i] = re; smem[I8_SM_TW + 2 * i + 1] = im;
+        smem[I8_SM_TWT + 2 * (n2 * N1 + k1)] = re; smem[I8_SM_TWT + 2 * (n2 * N1 + k1) + 1] = im;   // symmetric in (n2, k1)
+    }
+    for (int i = threadIdx.x; i < SCAN4_BINS; i += I8_THREADS) {
+        int* e = reinterpret_cast<int*>(smem + I8_SM_COL) + 4 * i;
+        if (i < NBINS) {
+            e[0] = P.col_band[2 * i]; e[1] = P.col_band[2 * i + 1];
+            e[2] = __float_as_int(P.col_w[2 * i] * INV_SCALE); e[3] = __float_as_int(P.col_w[2 * i + 1] * INV_SCALE);   // irfft's 1/640 folded in
+        } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
+    }
+    float* frames = smem + warp * I8_WARP_SMEM_F;
+    float* ybuf = frames + I8_NC * FRAME4_F;
+    float* side = ybuf + I8_Y_F;
+    for (int i = lane; i < I8_WARP_SMEM_F; i += 32) frames[i] = 0.0f;
+    __syncthreads();
+
+    const float* s_win = smem + I8_SM_WIN;
+    const vec2* s_tw = reinterpret_cast<const vec2*>(smem + I8_SM_TW);
+    const vec2* s_twT = reinterpret_cast<const vec2*>(smem + I8_SM_TWT);
+    const ivec4* s_col = reinterpret_cast<const ivec4*>(smem + I8_SM_COL);
+    const avse_inverse_args& A = P.a;
+    Lane4Const lc;
+    lane4_const_init(lane, s_win, s_tw, lc);
+
+    // Work distribution: the B * G groups of the launch, in (utterance, group) order, are cut into ONE contiguous range per warp
+    // (like the forward kernel's tiles).  A range that starts inside an utterance first recomputes the group before it (no
+    // stores) to rebuild the overlap-add carry; a range that ends an utterance also drains the carry (group G).  Against
+    // whole-utterance items this removes the idle SMs of a 1 000-utterance launch (1 000 items on 1 184 warps: 23 SMs had no work).
+    const long long gw = (long long)blockIdx.x * I8_WARPS + warp;
+    long long tile = gw * P.base_groups + (gw < P.rem_warps ? gw : P.rem_warps);
+    const long long tile_end = tile + P.base_groups + (gw < P.rem_warps ? 1 : 0);
+#pragma unroll 1
+    while (tile < tile_end) {
+        const int u = (int)(tile / P.G);
+        const int g0 = (int)(tile - (long long)u * P.G);
+        int g1 = g0 + (int)(tile_end - tile);
+        const bool last_chunk = g1 >= P.G;
+        if (last_chunk) g1 = P.G;
+        tile += g1 - g0;
+        const int g_first = g0 > 0 ? g0 - 1 : 0;          // warm-up group rebuilds the overlap-add carry
+        const int g_last = last_chunk ? P.G : g1 - 1;     // the end of an utterance also drains the carry (group G)
+
+        InvTile tl;
+        tl.pcm = A.mixed_pcm + (size_t)u * A.pcm_stride;
+        tl.L = A.L;
+        int valid = A.len_pcm ? A.len_pcm[u] : A.L;
+        tl.valid = valid < 0 ? 0 : (valid < A.L ? valid : A.L);
+        tl.T = P.T;
+        tl.T_use = P.T_use;
+        const float* ycoef = A.work + (size_t)u * A.work_stride;
+        O* out = static_cast<O*>(A.out_pcm) + (size_t)u * A.out_stride;
+
+        float acc[I8_ACC];
+#pragma unroll
+        for (int J = 0; J < I8_ACC; ++J) acc[J] = 0.0f;
+        for (int i = lane; i < 2 * I8_SIDE_F; i += 32) side[i] = 0.0f;
+        __syncwarp();
+
+        // software pipeline: the samples of the next computed group are loaded before pass B of the current one
+        float raw[I8_RAW], rt[20];
+        bool interior = false;
+        tl.t0 = g_first * I8_FPG;
+        if (!EXT && tl.t0 < P.T_use) {
+            interior = i8_group_interior(tl);
+            if (interior) { i8_load_raw(tl, lane, raw); i8_load_tail_raw(tl, lane, rt); }
+        }
+
+#pragma unroll 1
+        for (int g = g_first; g <= g_last; ++g) {
+            tl.t0 = g * I8_FPG;
+            const bool have = tl.t0 < P.T_use;
+            const bool write = g >= g0;
+            const float* side_in = side + I8_SIDE_F * (g & 1);
+            float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
+            if (have) {
+                // coefficients of the 8 frames -> ybuf[band][8]: 160 16-byte loads per warp, issued now, stored after pass 1
+                float4 cf[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int idx = lane + 32 * q, m = idx >> 1, hf = idx & 1;
+                    cf[q] = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0 + 4 * hf);
+                }
+                if (!EXT) {
+                    if (interior) {
+                        i8_pass1_main(lane, raw, lc, frames);
+                        i8_pass1_tail(lane, rt, s_win, s_tw, frames);
+                    } else {
+                        i8_pass1_edge(tl, lane, s_win, s_tw, frames);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int idx = lane + 32 * q;
+                    *reinterpret_cast<float4*>(ybuf + 4 * idx) = cf[q];       // [band m][8]: 8 m + 4 hf = 4 idx
+                }
+                __syncwarp();
+                if (EXT) {
+                    const int tA = tl.t0 + 2 * (lane >> 3);
+                    const vec2* ph = reinterpret_cast<const vec2*>(A.phase) + (size_t)u * A.phase_stride;
+                    const vec2* phA = tA < P.T_use ? ph + (size_t)tA * NBINS : nullptr;
+                    const vec2* phB = tA + 1 < P.T_use ? ph + (size_t)(tA + 1) * NBINS : nullptr;
+                    i8_stage_post<true>(lane, s_col, ybuf, frames, phA, phB);
+                    __syncwarp();
+                }
+                // pass 2 (iterations 0, 1: rows -> Z), the post stage, pass A (iterations 2, 3: V -> rows): ONE DFT-40 copy
+#pragma unroll 1
+                for (int it = EXT ? 2 : 0; it < 4; ++it) {
+                    const int r = it & 1;
+                    if (it == 2 && !EXT) {
+                        i8_stage_post<false>(lane, s_col, ybuf, frames, nullptr, nullptr);
+                        __syncwarp();
+                    }
+                    cpx x[40];
+                    if (it < 2) p4_pass2_load(lane, r, frames, x);
+                    else i8_passA_load(lane, r, frames, x);
+                    dft40_inplace(x);
+                    if (it >= 2) inv_passA_twiddle(lane, s_twT, x);
+                    __syncwarp();
+                    if (it < 2) p4_pass2_store(lane, r, frames, x);
+                    else i8_passA_store(lane, r, frames, x);
+                    __syncwarp();
+                }
+            }
+            // ---- next computed group: issue its loads now (they land during pass B / emit) ----
+            bool interior2 = false;
+            if (!EXT && g < g_last) {
+                InvTile tn = tl;
+                tn.t0 = (g + 1) * I8_FPG;
+                if (tn.t0 < P.T_use) {
+                    interior2 = i8_group_interior(tn);
+                    if (interior2) { i8_load_raw(tn, lane, raw); i8_load_tail_raw(tn, lane, rt); }
+                }
+            }
+            // ---- pass B + emit: one FFT at a time (rolled), two finished hops leave after each ----
+#pragma unroll 1
+            for (int cc = 0; cc < I8_NC; ++cc) {
+                if (have) i8_passB_add(lane, cc, lc, frames, acc);
+                i8_emit_main(lane, tl.t0 + 2 * cc, P.T_use, P.out_len, write, s_win, out, acc);
+            }
+            if (have) i8_passB_tail(lane, s_win, frames, ybuf);
+            __syncwarp();
+            i8_tail_reduce_emit(lane, tl.t0, P.T_use, P.out_len, write, have, s_win, out, ybuf, side_in, side_out);
+            __syncwarp();
+            interior = interior2;
+        }
+    }
+}
+
+// Scratch per utterance: the coefficient rows [80][T_pad], T_pad = frames padded to whole groups plus one drain group.  Sized for
+// the 8-frame groups of the I8 kernel, which also covers the 4-frame kernel's padding.
 extern "C" int avse_inverse_work_elems(int n_frames_use, long long* per_utterance) {
     if (n_frames_use <= 0 || per_utterance == nullptr) return avse_fail(AVSE_E_ARG, "avse_inverse_work_elems: bad argument");
-    const int G = (n_frames_use + INV_FPG - 1) / INV_FPG;
-    *per_utterance = (long long)NMEL * (INV_FPG * (G + 1));
+    const int G = (n_frames_use + I8_FPG - 1) / I8_FPG;
+    *per_utterance = (long long)NMEL * (I8_FPG * (G + 1));
     return 0;
 }
 
@@ -243,8 +465,12 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (t_mel <= 0) return avse_fail(AVSE_E_ARG, "avse_inverse: no mel frames");
     P.T_use = t_mel < P.T ? t_mel : P.T;                       // dp:68
     if (P.T_use < 2) return avse_fail(AVSE_E_ARG, "avse_inverse: fewer than 2 frames gives an empty signal");
-    P.G = (P.T_use + INV_FPG - 1) / INV_FPG;
-    P.T_pad = INV_FPG * (P.G + 1);
+    // kernel choice: the I8 kernel (8 frames per group, 8 warps / SM); AVSE_INV4=1 keeps the round-1 4-frame kernel (A/B runs, tests)
+    static const bool force4 = [] { const char* e = getenv("AVSE_INV4"); return e != nullptr && e[0] == '1'; }();
+    const bool use8 = !force4;
+    const int fpg = use8 ? I8_FPG : INV_FPG;
+    P.G = (P.T_use + fpg - 1) / fpg;
+    P.T_pad = fpg * (P.G + 1);
     P.out_len = HOP * (P.T_use - 1);
     if (a.layout == AVSE_LAYOUT_SPEC && a.ld_t < P.T_use) return avse_fail(AVSE_E_ARG, "avse_inverse: ld_t < frames used");
     if (a.work_stride < (long long)NMEL * P.T_pad) return avse_fail(AVSE_E_ARG, "avse_inverse: work_stride too small (see avse_inverse_work_elems)");
@@ -266,11 +492,15 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
         CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<false, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(avse_inverse_kernel<true, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse8_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse8_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse8_kernel<false, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(avse_inverse8_kernel<true, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
         configured_dev = dev;
     }
     cudaStream_t st = (cudaStream_t)stream;
     {
-        dim3 grid((unsigned)((P.T_pad + 127) / 128), (unsigned)a.B);
+        dim3 grid((unsigned)a.B, (unsigned)((P.T_pad + 127) / 128));
         avse_mel_to_coef_kernel<<<grid, 128, 0, st>>>(a.mel_db, a.layout, a.ld_t, a.mel_stride, P.T_use, P.T_pad, ctx->d_tri_w,
                                                       ctx->d_tri_ipiv, ctx->d_tri_sup, a.work, a.work_stride);
         CUDA_TRY(cudaGetLastError());
@@ -278,8 +508,9 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     // chunking: a warp streams through one (utterance, chunk) item at a time; every chunk but the first pays one
     // recomputed warm-up group, and the launch ends when the warp with the most items finishes.  Pick the chunk count
     // that minimises  rounds x (groups per chunk + warm-up)  with rounds = ceil(items / resident warps).
-    const long long n_warps = 2LL * ctx->num_sms * INV_WARPS;
-    const long long max_chunks = P.G / 4 > 0 ? P.G / 4 : 1;   // chunks of >= 4 groups
+    const long long n_warps = use8 ? (long long)ctx->num_sms * I8_WARPS : 2LL * ctx->num_sms * INV_WARPS;
+    const int min_cg = use8 ? 2 : 4;                                       // smallest chunk worth its warm-up group
+    const long long max_chunks = P.G / min_cg > 0 ? P.G / min_cg : 1;
     long long best_cost = -1;
     int best_cg = P.G;
     for (long long c = 1; c <= max_chunks; ++c) {
@@ -291,10 +522,28 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     }
     P.cg = best_cg;
     P.chunks = (P.G + P.cg - 1) / P.cg;
+    const bool o16 = a.out_format == AVSE_SAMPLE_I16;
+    if (use8) {
+        P.total_groups = (long long)a.B * P.G;
+        long long blocks = ctx->num_sms;
+        const long long need = (P.total_groups + I8_WARPS - 1) / I8_WARPS;
+        if (blocks > need) blocks = need;
+        const long long nw = blocks * I8_WARPS;
+        P.base_groups = (int)(P.total_groups / nw);
+        P.rem_warps = (int)(P.total_groups % nw);
+        if (a.phase) {
+            if (o16) avse_inverse8_kernel<true, short><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);
+            else avse_inverse8_kernel<true, float><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);
+        } else {
+            if (o16) avse_inverse8_kernel<false, short><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);
+            else avse_inverse8_kernel<false, float><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);
+        }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     long long blocks = 2LL * ctx->num_sms;
     const long long need = ((long long)a.B * P.chunks + INV_WARPS - 1) / INV_WARPS;
     if (blocks > need) blocks = need;
-    const bool o16 = a.out_format == AVSE_SAMPLE_I16;
     if (a.phase) {
         if (o16) avse_inverse_kernel<true, short><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);
         else avse_inverse_kernel<true, float><<<(unsigned)blocks, INV_THREADS, INV_SMEM_BYTES, st>>>(P);

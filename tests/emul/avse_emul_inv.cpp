@@ -7,6 +7,7 @@
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_common.h"
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_tables.h"
 #include "../../audio-visual-speech-enhancement_b200/csrc/avse_inv_stages.cuh"
+#include "../../audio-visual-speech-enhancement_b200/csrc/avse_inv8_stages.cuh"
 
 using namespace avse;
 
@@ -107,6 +108,115 @@ extern "C" int emul_inverse(const float* mel_slices, int n_slices, const float* 
             for (int lane = 0; lane < 32; ++lane)
                 inv_stage_emit_side(lane, tl.t0, T_use, out_len, write, s_win, out, side, w.keep[lane], w.carry[lane]);
             for (int lane = 0; lane < 32; ++lane) inv_stage_rotate_side(lane, side, w.carry[lane]);
+        }
+    }
+    return out_len;
+}
+
+
+// ---- I8 kernel (avse_inv8_stages.cuh): one emulated warp = eight real frames per group; mirrors avse_inverse8_kernel's loop ----
+namespace {
+struct Inv8Warp {
+    alignas(16) float smem[I8_WARP_SMEM_F];
+    cpx x[32][40];
+    float acc[32][I8_ACC];
+    float raw[32][I8_RAW], rt[32][20];
+    Lane4Const lc[32];
+};
+}  // namespace
+
+extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float* pcm, int L, int valid, float* out, int out_cap,
+                             int chunks, int sample_rate, double fmin, double fmax) {
+    HostTables h;
+    if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
+    const int T = 1 + L / HOP;
+    const int T_use = n_slices * SPSS < T ? n_slices * SPSS : T;
+    const int G = (T_use + I8_FPG - 1) / I8_FPG;
+    const int T_pad = I8_FPG * (G + 1);
+    const int out_len = HOP * (T_use - 1);
+    if (out_cap < out_len) return -1;
+    std::vector<float> work;
+    mel_to_coef(h, mel_slices, T_use, T_pad, work);
+
+    std::vector<vec2> tw(N1 * N2), twT(N1 * N2);
+    for (int k1 = 0; k1 < N1; ++k1)
+        for (int n2 = 0; n2 < N2; ++n2) {
+            vec2 v; v.x = h.tw1t[(k1 * N2 + n2) * 2]; v.y = h.tw1t[(k1 * N2 + n2) * 2 + 1];
+            tw[k1 * N2 + n2] = v;
+            twT[n2 * N1 + k1] = v;
+        }
+    std::vector<ivec4> col(SCAN4_BINS);
+    for (int k = 0; k < SCAN4_BINS; ++k) {
+        ivec4 e; e.x = e.y = e.z = e.w = 0;
+        if (k < NBINS) {
+            e.x = h.col_band[2 * k]; e.y = h.col_band[2 * k + 1];
+            union { float f; int i; } u0, u1; u0.f = h.col_w[2 * k] * INV_SCALE; u1.f = h.col_w[2 * k + 1] * INV_SCALE;
+            e.z = u0.i; e.w = u1.i;
+        }
+        col[k] = e;
+    }
+    const float* s_win = h.window.data();
+
+    static Inv8Warp w;
+    for (int lane = 0; lane < 32; ++lane) lane4_const_init(lane, s_win, tw.data(), w.lc[lane]);
+    const int cg = (G + chunks - 1) / chunks;
+    const int n_chunks = (G + cg - 1) / cg;
+    memset(w.smem, 0, sizeof(w.smem));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int g0 = c * cg;
+        int g1 = g0 + cg;
+        const bool last_chunk = g1 >= G;
+        if (last_chunk) g1 = G;
+        const int g_first = g0 > 0 ? g0 - 1 : 0;
+        const int g_last = last_chunk ? G : g1 - 1;
+        float* frames = w.smem;
+        float* ybuf = frames + I8_NC * FRAME4_F;
+        float* side = ybuf + I8_Y_F;
+        memset(w.acc, 0, sizeof(w.acc));
+        memset(side, 0, sizeof(float) * 2 * I8_SIDE_F);
+        InvTile tl{};
+        tl.pcm = pcm; tl.L = L; tl.valid = valid < L ? valid : L; tl.T = T; tl.T_use = T_use;
+        for (int g = g_first; g <= g_last; ++g) {
+            tl.t0 = g * I8_FPG;
+            const bool have = tl.t0 < T_use;
+            const bool write = g >= g0;
+            const float* side_in = side + I8_SIDE_F * (g & 1);
+            float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
+            if (have) {
+                if (i8_group_interior(tl)) {
+                    for (int lane = 0; lane < 32; ++lane) { i8_load_raw(tl, lane, w.raw[lane]); i8_load_tail_raw(tl, lane, w.rt[lane]); }
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames);
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_tail(lane, w.rt[lane], s_win, tw.data(), frames);
+                } else {
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames);
+                }
+                for (int m = 0; m < NMEL; ++m)
+                    for (int e = 0; e < I8_FPG; ++e) ybuf[I8_FPG * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it & 1;
+                    if (it == 2)
+                        for (int lane = 0; lane < 32; ++lane) i8_stage_post<false>(lane, col.data(), ybuf, frames, nullptr, nullptr);
+                    for (int lane = 0; lane < 32; ++lane) {
+                        if (it < 2) p4_pass2_load(lane, r, frames, w.x[lane]);
+                        else i8_passA_load(lane, r, frames, w.x[lane]);
+                        dft40_inplace(w.x[lane]);
+                        if (it >= 2) inv_passA_twiddle(lane, twT.data(), w.x[lane]);
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        if (it < 2) p4_pass2_store(lane, r, frames, w.x[lane]);
+                        else i8_passA_store(lane, r, frames, w.x[lane]);
+                    }
+                }
+            }
+            for (int cc = 0; cc < I8_NC; ++cc)
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (have) i8_passB_add(lane, cc, w.lc[lane], frames, w.acc[lane]);
+                    i8_emit_main(lane, tl.t0 + 2 * cc, T_use, out_len, write, s_win, out, w.acc[lane]);
+                }
+            if (have)
+                for (int lane = 0; lane < 32; ++lane) i8_passB_tail(lane, s_win, frames, ybuf);
+            for (int lane = 0; lane < 32; ++lane)
+                i8_tail_reduce_emit(lane, tl.t0, T_use, out_len, write, have, s_win, out, ybuf, side_in, side_out);
         }
     }
     return out_len;

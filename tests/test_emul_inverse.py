@@ -10,24 +10,29 @@ from tests.cases import GOLDEN_CASES, SR, oracle_pair
 from tests.test_emul_forward import emul, _p, GOLD, TOL_PCM  # noqa: F401  (session fixture that builds the emulation library)
 
 
-def _run(emul, mel, pcm, valid, chunks):
-    emul.emul_inverse.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+KERNEL = "i8"      # stage code under test: "i8" = avse_inv8_stages.cuh (the shipped kernel), "i4" = the round-1 4-frame kernel
+
+
+def _run(emul, mel, pcm, valid, chunks, kernel=None):
+    fn = emul.emul_inverse8 if (kernel or KERNEL) == "i8" else emul.emul_inverse
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
     T_use = min(20 * mel.shape[0], 1 + len(pcm) // 160)
-    out = np.zeros(160 * (T_use - 1), np.float32)
-    n = emul.emul_inverse(_p(mel), mel.shape[0], _p(pcm), len(pcm), valid, _p(out), len(out), chunks, SR, 0.0, 8000.0)
+    out = np.full(160 * (T_use - 1), np.nan, np.float32)        # every sample must be written exactly by the kernel's stores
+    n = fn(_p(mel), mel.shape[0], _p(pcm), len(pcm), valid, _p(out), len(out), chunks, SR, 0.0, 8000.0)
     assert n == len(out)
     return out
 
 
+@pytest.mark.parametrize("kernel", ["i8", "i4"])
 @pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
 @pytest.mark.parametrize("chunks", [1, 3])
-def test_inverse_stage_code_matches_oracle_and_golden(emul, case, chunks):
+def test_inverse_stage_code_matches_oracle_and_golden(emul, case, chunks, kernel):
     ref = oracle_pair(case)
     gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
     mel = np.ascontiguousarray(gold["speech"])          # float32 dB slices, as the network would hand them over
     pcm = np.ascontiguousarray(gold["mixed_pcm"])
-    out = _run(emul, mel, pcm, len(pcm), chunks)
+    out = _run(emul, mel, pcm, len(pcm), chunks, kernel)
     want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
     scale = np.max(np.abs(ref["mixed_pcm"]))
     assert out.shape == want.shape == gold["recon"].shape
@@ -64,3 +69,22 @@ def test_inverse_silent_frames_keep_unit_phase(emul):
     out = _run(emul, mel, pcm, len(pcm), 1)
     want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
     assert np.max(np.abs(out - want)) <= TOL_PCM * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("n_slices,L,valid,chunks", [(1, 3200, 3200, 1), (2, 6400, 5000, 1), (3, 9000, 9000, 2), (5, 16000, 330, 1),
+                                                       (6, 19200, 19200, 3), (7, 22400, 22000, 2), (8, 25600, 25600, 4), (13, 41600, 30001, 5)])
+def test_i8_lengths_around_the_group_size(emul, n_slices, L, valid, chunks):
+    """Frame counts on both sides of the I8 kernel's 8-frame groups (T_use = 20, 40, 57, 100, 120, 140, 160 = 8 x 20: the drain
+    group carries the last rows; 260), zero-padded mixtures (valid < L: all-zero frames keep phase 1 + 0j), chunked utterances
+    (warm-up group per chunk) -- against the oracle and against the round-1 4-frame stage code."""
+    rng = np.random.RandomState(n_slices)
+    pcm = np.zeros(L, np.float32)
+    pcm[:valid] = (0.1 * rng.randn(valid)).astype(np.float32)
+    mel = (rng.rand(n_slices, 80, 20) * 40.0 - 60.0).astype(np.float32)
+    out = _run(emul, mel, pcm, valid, chunks, "i8")
+    want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    assert out.shape == want.shape and np.isfinite(out).all()
+    full = max(np.max(np.abs(want)), 1e-3)
+    assert np.max(np.abs(out - want)) <= TOL_PCM * full
+    old = _run(emul, mel, pcm, valid, 1, "i4")
+    assert np.max(np.abs(out - old)) <= 0.2 * TOL_PCM * full
