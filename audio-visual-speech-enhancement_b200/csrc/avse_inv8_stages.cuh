@@ -25,6 +25,9 @@
 #include "avse_fwd4_stages.cuh"
 #include "avse_inv_stages.cuh"
 
+#if !defined(AVSE_I8_POST_UNROLL)
+#define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
+#endif
 #if !defined(AVSE_I8_ROLL_P1)
 #define AVSE_I8_ROLL_P1 1        // pass 1: one copy of the column code, the 20-stride window slides through the raw registers
 #endif
@@ -34,13 +37,18 @@ namespace avse {
 constexpr int I8_FPG = 8;                          // real frames per group
 constexpr int I8_NC = 4;                           // packed complex FFTs per group
 constexpr int I8_RAW = 16 + 4 * (I8_FPG - 1);      // 44 strides of 40 samples cover the eight frames of a group
-constexpr int I8_Y_F = NMEL * I8_FPG;              // coefficient buffer [80][8]; re-used as the tail-column staging [4][20][8]
+#if !defined(AVSE_I8_YS)
+#define AVSE_I8_YS 10            // floats per band row of the coefficient buffer (8 used): 10 spreads the post stage's band gathers
+#endif                           // over 16 bank groups instead of 4 (8 = dense rows)
+constexpr int I8_YS = AVSE_I8_YS;
+constexpr int I8_Y_F = NMEL * I8_YS;               // coefficient buffer [80][I8_YS]; re-used as the tail-column staging [4][20][8]
+constexpr int I8_ST_C = I8_YS == 8 ? 160 : 168;    // staging stride between FFTs: 168 = 8 (mod 32) keeps the four lanes groups apart
 constexpr int I8_ACC = 20;                         // accumulator rows (40 samples each) alive while one FFT is added
 constexpr int I8_SIDE_ROWS = 12;                   // tail-column rows carried from one group to the next
 constexpr int I8_SIDE_F = I8_SIDE_ROWS * 8;        // 96 floats, double-buffered
 constexpr int I8_FLAG_F = N1 * ROW_F;              // per frame buffer: floats [1344, 1346) = "windowed frame A / B is non-zero"
 constexpr int I8_WARP_SMEM_F = I8_NC * FRAME4_F + I8_Y_F + 2 * I8_SIDE_F;     // 5440 + 640 + 192 = 6272 floats
-static_assert(I8_NC * 20 * 8 == I8_Y_F, "the tail staging re-uses the coefficient buffer exactly");
+static_assert(3 * I8_ST_C + 160 <= I8_Y_F && (I8_YS % 2) == 0, "the tail staging re-uses the coefficient buffer");
 static_assert(I8_FLAG_F + 2 <= FRAME4_F, "flags live in the frame buffer's pad");
 
 // librosa.istft window sum-square at padded position P (see inv_wss_recip), plain [640] window table.
@@ -170,7 +178,7 @@ AVSE_HD void i8_post_bin(int i, int p, const ivec4* tab, const float* yb, float*
     const bool tail = k > NBINS - 1;            // chunk 7 ends with slots that mirror other bins: compute harmlessly, do not store
     const bool nyq = k == NBINS - 1;            // lin = 0 at the Nyquist bin (the filterbank's last column is empty)
     const ivec4 t = tab[i];
-    const cpx y0 = cload(yb + I8_FPG * t.x), y1 = cload(yb + I8_FPG * t.y);
+    const cpx y0 = cload(yb + I8_YS * t.x), y1 = cload(yb + I8_YS * t.y);
     const cpx lin = cfma_s(y1, bits_to_float(t.w), cmul_s(y0, bits_to_float(t.z)));   // (lin_A, lin_B) / 640
     float yar, yai, ybr, ybi;
     if (EXT) {
@@ -203,14 +211,14 @@ AVSE_HD void i8_stage_post(int lane, const ivec4* s_col, const float* ybuf, floa
     float* za = fr + 2 * CHUNK4 * p;
     float* zc = fr + 2 * (NFFT - CHUNK4 * p);
     const ivec4* tab = s_col + CHUNK4 * p;
-    const float* yb = ybuf + 2 * c;            // (c_A, c_B) of band b at yb[8 b]
+    const float* yb = ybuf + 2 * c;            // (c_A, c_B) of band b at yb[I8_YS b]
     const bool liveA = EXT || fr[I8_FLAG_F] != 0.0f;
     const bool liveB = EXT || fr[I8_FLAG_F + 1] != 0.0f;
-    static_assert(CHUNK4 == 41, "10 blocks of 4 bins + 1");
+    static_assert(CHUNK4 == 41 && (40 % AVSE_I8_POST_UNROLL) == 0, "blocks of AVSE_I8_POST_UNROLL bins + 1");
 #pragma unroll 1
-    for (int ib = 0; ib < 40; ib += 4) {
+    for (int ib = 0; ib < 40; ib += AVSE_I8_POST_UNROLL) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) i8_post_bin<EXT>(ib + j, p, tab, yb, za, zc, liveA, liveB, phA, phB);
+        for (int j = 0; j < AVSE_I8_POST_UNROLL; ++j) i8_post_bin<EXT>(ib + j, p, tab, yb, za, zc, liveA, liveB, phA, phB);
     }
     i8_post_bin<EXT>(40, p, tab, yb, za, zc, liveA, liveB, phA, phB);
 }
@@ -302,7 +310,7 @@ AVSE_HD void i8_passB_tail(int lane, const float* s_win, const float* frames, fl
         cc[k1] = fmaf(cre(x[k1]), w, cc[k1]);
         cc[k1 + 4] = fmaf(-cim(x[k1]), w, cc[k1 + 4]);
     }
-    float* d = st + (c * 20) * 8 + r;
+    float* d = st + c * I8_ST_C + r;
 #pragma unroll
     for (int j = 0; j < 20; ++j) d[8 * j] = cc[j];
 }
@@ -328,9 +336,9 @@ AVSE_HD void i8_tail_reduce_emit(int lane, int t0, int T_use, int out_len, bool 
             const int R = 8 * m + e;
             float v = (m == 0 || (m == 1 && half == 0)) ? side_in[R * 8 + r] : 0.0f;          // rows < 12 carry over
             if (have) {
-                if (half == 0 && m >= 2 && m - 2 < I8_NC) v += st[((m - 2) * 20 + e + 16) * 8 + r];
-                if (m >= 1 && m - 1 < I8_NC) v += st[((m - 1) * 20 + e + 8) * 8 + r];
-                if (m < I8_NC) v += st[(m * 20 + e) * 8 + r];
+                if (half == 0 && m >= 2 && m - 2 < I8_NC) v += st[(m - 2) * I8_ST_C + (e + 16) * 8 + r];
+                if (m >= 1 && m - 1 < I8_NC) v += st[(m - 1) * I8_ST_C + (e + 8) * 8 + r];
+                if (m < I8_NC) v += st[m * I8_ST_C + e * 8 + r];
             }
             if (m < 4) {
                 if (write) {

@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
 #pragma unroll
                 for (int q = 0; q < 5; ++q) {
                     const int idx = lane + 32 * q;
-                    *reinterpret_cast<float4*>(ybuf + 4 * idx) = cf[q];       // [band m][8]: 8 m + 4 hf = 4 idx
+                    float* yd = ybuf + I8_YS * (idx >> 1) + 4 * (idx & 1);      // [band m][I8_YS]: 8-byte aligned for any even I8_YS
+                    *reinterpret_cast<float2*>(yd) = make_float2(cf[q].x, cf[q].y);
+                    *reinterpret_cast<float2*>(yd + 2) = make_float2(cf[q].z, cf[q].w);
                 }
                 __syncwarp();
                 if (EXT) {

@@ -10,16 +10,55 @@
 
 namespace {
 
-// partial sums of one chunk of slices: thread = pixel, its F frame values are contiguous (coalesced 4 F-byte runs)
+// partial sums of one chunk of slices.  VEC: thread = one 16-byte group of the flattened (pixel, frame) row -- every slice is one
+// fully coalesced float4 load per thread, the four elements keep their own float64 sums (each is a fixed (pixel, frame) pair)
+// and meet in the per-pixel accumulators at the end.  Scalar variant (row length not a multiple of 4): thread = pixel.
+template <bool VEC>
 __global__ void __launch_bounds__(256) avse_video_stats_kernel(const float* __restrict__ video, long long n_slices, int hw, int frames,
                                                                int slices_per_block, double* __restrict__ acc /* [hw][2] */) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= hw) return;
     const long long s0 = (long long)blockIdx.y * slices_per_block;
     long long s1 = s0 + slices_per_block;
     if (s1 > n_slices) s1 = n_slices;
-    double sum = 0.0, sq = 0.0;
     const size_t stride = (size_t)hw * frames;
+    if (VEC) {
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index inside a slice
+        if (4LL * j >= (long long)stride) return;
+        double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+        const float4* q = reinterpret_cast<const float4*>(video + (size_t)s0 * stride) + j;
+        const size_t stride4 = stride / 4;
+        long long s = s0;
+        for (; s + 1 < s1; s += 2, q += 2 * stride4) {                // two independent 16-byte loads in flight
+            const float4 a = __ldg(q), b = __ldg(q + stride4);
+            const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sum[e] += (double)va[e] + (double)vb[e];
+                sq[e] = fma((double)va[e], (double)va[e], fma((double)vb[e], (double)vb[e], sq[e]));
+            }
+        }
+        if (s < s1) {
+            const float4 a = __ldg(q);
+            const float va[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { sum[e] += (double)va[e]; sq[e] = fma((double)va[e], (double)va[e], sq[e]); }
+        }
+        // elements 4j .. 4j+3 belong to at most two pixels: merge before the atomics
+        int p = (4 * j) / frames, r = (4 * j) - p * frames;
+        double ps = 0.0, pq = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            ps += sum[e]; pq += sq[e];
+            if (++r == frames || e == 3) {
+                atomicAdd(acc + 2 * (size_t)p, ps);
+                atomicAdd(acc + 2 * (size_t)p + 1, pq);
+                ps = 0.0; pq = 0.0; r = 0; ++p;
+            }
+        }
+        return;
+    }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= hw) return;
+    double sum = 0.0, sq = 0.0;
     const float* q = video + (size_t)s0 * stride + (size_t)p * frames;
     for (long long s = s0; s < s1; ++s, q += stride)
         for (int f = 0; f < frames; ++f) {
@@ -42,12 +81,35 @@ __global__ void __launch_bounds__(256) avse_video_finalize_kernel(const double* 
     stdv[p] = (float)sqrt(var);
 }
 
+// In place, 16 bytes per thread when the tensor allows it (VEC): the (pixel, frame) position of a float4's first element is
+// found with one division and then walked; scalar variant otherwise.
+template <bool VEC>
 __global__ void __launch_bounds__(256) avse_video_normalize_kernel(float* __restrict__ video, long long total, int hw, int frames,
                                                                    const float* __restrict__ mean, const float* __restrict__ stdv) {
     const long long step = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        const long long n4 = total >> 2;
+        float4* v4 = reinterpret_cast<float4*>(video);
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += step) {
+            float4 x = v4[j];
+            const long long i0 = 4 * j;
+            long long pix = i0 / frames;
+            int r = (int)(i0 - pix * frames);
+            int p = (int)(pix % hw);
+            float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v[e] = (v[e] - __ldg(mean + p)) / __ldg(stdv + p);           // dp:211-212: no epsilon, like the reference
+                if (++r == frames) { r = 0; if (++p == hw) p = 0; }
+            }
+            x.x = v[0]; x.y = v[1]; x.z = v[2]; x.w = v[3];
+            v4[j] = x;
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         const int p = (int)((i / frames) % hw);
-        video[i] = (video[i] - mean[p]) / stdv[p];             // dp:211-212: no epsilon, like the reference
+        video[i] = (video[i] - mean[p]) / stdv[p];
     }
 }
 
@@ -55,7 +117,15 @@ __global__ void __launch_bounds__(256) avse_mse_kernel(const float* __restrict__
                                                        double* __restrict__ acc) {
     double s = 0.0;
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((((size_t)a | (size_t)b) & 15) == 0);
+    const long long n4 = vec ? (n >> 2) : 0;
+    for (long long i = tid; i < n4; i += step) {                      // 16-byte loads of both operands
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+        const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y, d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+        s = fma(d0, d0, fma(d1, d1, fma(d2, d2, fma(d3, d3, s))));
+    }
+    for (long long i = 4 * n4 + tid; i < n; i += step) {
         const double d = (double)a[i] - (double)b[i];
         s = fma(d, d, s);
     }
@@ -81,15 +151,18 @@ extern "C" int avse_video_stats(avse_ctx* ctx, const float* video, long long n_s
     if (n_slices <= 0 || hw <= 0 || frames <= 0) return avse_fail(AVSE_E_ARG, "avse_video_stats: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)hw, st));
-    const int bx = (hw + 255) / 256;
+    const long long row = (long long)hw * frames;
+    const bool vec = (row % 4) == 0 && (((size_t)video) & 15) == 0;
+    const int bx = vec ? (int)((row / 4 + 255) / 256) : (hw + 255) / 256;
     long long by = (8LL * ctx->num_sms + bx - 1) / bx;        // ~8 CTAs per SM in flight
     if (by > n_slices) by = n_slices;
     if (by > 65535) by = 65535;
     const int per = (int)((n_slices + by - 1) / by);
     by = (n_slices + per - 1) / per;
-    avse_video_stats_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(video, n_slices, hw, frames, per, scratch);
+    if (vec) avse_video_stats_kernel<true><<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(video, n_slices, hw, frames, per, scratch);
+    else avse_video_stats_kernel<false><<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(video, n_slices, hw, frames, per, scratch);
     CUDA_TRY(cudaGetLastError());
-    avse_video_finalize_kernel<<<bx, 256, 0, st>>>(scratch, hw, (double)n_slices * frames, mean_out, std_out);
+    avse_video_finalize_kernel<<<(hw + 255) / 256, 256, 0, st>>>(scratch, hw, (double)n_slices * frames, mean_out, std_out);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -102,7 +175,9 @@ extern "C" int avse_video_normalize(avse_ctx* ctx, float* video, long long n_sli
     long long bx = (total + 256 * 8 - 1) / (256 * 8);
     const long long cap = 16LL * ctx->num_sms;
     if (bx > cap) bx = cap;
-    avse_video_normalize_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(video, total, hw, frames, mean, stdv);
+    const bool vec = (total % 4) == 0 && (((size_t)video) & 15) == 0;
+    if (vec) avse_video_normalize_kernel<true><<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(video, total, hw, frames, mean, stdv);
+    else avse_video_normalize_kernel<false><<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(video, total, hw, frames, mean, stdv);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

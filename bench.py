@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inverse", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the HBM-bound neighbours of the path (sample-set gather, video normaliser, MSE)")
     ap.add_argument("--sustain-s", type=float, default=2.0,
                     help="also run the step back to back for at least this many seconds and report the steady-state figure (0: skip)")
     ap.add_argument("--corpus", type=int, default=0,
@@ -634,6 +635,45 @@ def main():
                            "value": world * B * UTT_SECONDS / (inv_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": inv_ms,
                            "roofline": {"bound": "hbm", "kernel": "avse_inverse_kernel", "achieved": inv_bytes / (inv_ms * 1e-3) / 1e9,
                                         "peak": peak, "unit": "GB/s", "frac": inv_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
+
+    # ---------------- SURVEY 8(f) neighbours of the path: HBM-bound kernels, each against the copy roofline ----------------
+    if not args.no_aux and rank == 0:
+        def timed(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True)
+            a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+        res = step()
+        rows = B * N_VIDEO_SLICES
+        perm = torch.randperm(rows, device=device)
+        ms = timed(lambda: eng.make_sample_set(res["mixed"], res["speech"], permutation=perm))
+        gb = 2 * 2 * rows * 6400 / 1e9                       # two arrays, every row read once and written once
+        aux = {"make_sample_set": {"kernel": "avse_gather_rows_kernel", "what": "se:241-262: concat + one shared permutation of %d (80,20) slices x 2 arrays" % rows,
+                                   "ms": ms, "achieved_gbs": gb / (ms * 1e-3), "frac_of_hbm_peak": gb / (ms * 1e-3) / peak,
+                                   "note": "includes the index construction (torch glue) of SpectralEngine.make_sample_set"}}
+        nv = 2000
+        video = torch.rand((nv, 128, 128, 5), device=device) * 255.0
+        vn_holder = {}
+        ms = timed(lambda: vn_holder.__setitem__("vn", eng_mod.VideoNormalizer(eng, video)))
+        gb = video.numel() * 4 / 1e9
+        aux["video_stats"] = {"kernel": "avse_video_stats_kernel<true>", "what": "dp:201-205: per-pixel mean / std over %d x (128,128,5) crops" % nv,
+                              "ms": ms, "achieved_gbs": gb / (ms * 1e-3), "frac_of_hbm_peak": gb / (ms * 1e-3) / peak}
+        ms = timed(lambda: vn_holder["vn"].normalize(video))
+        aux["video_normalize"] = {"kernel": "avse_video_normalize_kernel<true>", "what": "dp:207-212 in place (read + write)",
+                                  "ms": ms, "achieved_gbs": 2 * gb / (ms * 1e-3), "frac_of_hbm_peak": 2 * gb / (ms * 1e-3) / peak}
+        ms = timed(lambda: eng_mod.mse(eng, res["mixed"], res["speech"]))
+        gb = 2 * res["mixed"].numel() * 4 / 1e9
+        aux["mse"] = {"kernel": "avse_mse_kernel", "what": "network.py:214-220 loss over the step's slices", "ms": ms,
+                      "achieved_gbs": gb / (ms * 1e-3), "frac_of_hbm_peak": gb / (ms * 1e-3) / peak}
+        del video, vn_holder
+        line["aux"] = aux
 
     # ---------------- end to end through the host-facing API ----------------
     if not args.no_e2e:

@@ -191,7 +191,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames);
                 }
                 for (int m = 0; m < NMEL; ++m)
-                    for (int e = 0; e < I8_FPG; ++e) ybuf[I8_FPG * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
+                    for (int e = 0; e < I8_FPG; ++e) ybuf[I8_YS * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
                 for (int it = 0; it < 4; ++it) {
                     const int r = it & 1;
                     if (it == 2)

@@ -40,6 +40,25 @@ def test_sass_is_sm100a(native):
     assert "sm_100a" in out
 
 
+def test_hot_kernels_use_blackwell_packed_fp32(native):
+    """The FFT codelets are written with add/mul/fma.rn.f32x2 (avse_dft.cuh): the hot kernels' SASS must carry the sm_100-only
+    packed FP32 instructions FADD2 / FFMA2 / FMUL2 -- a recompile that silently fell back to scalar code would halve the
+    butterfly issue rate.  (profiles/sass_histogram_r2.txt is the committed listing; no TMA / tcgen05 is expected: the path has
+    no GEMM-shaped stage and its tiles do not fit a bulk-copy ring next to the FFT buffers)"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    txt = subprocess.run(["cuobjdump", "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
+    parts = {p.split("\n", 1)[0].strip(): p for p in re.split(r"\n\s*Function : ", txt)[1:]}
+    for key in ("avse_forward4_kernelIfLb0", "avse_inverse8_kernelILb0Ef"):
+        body = [v for k, v in parts.items() if key in k]
+        assert body, key
+        n2 = len(re.findall(r"\b(?:FADD2|FFMA2|FMUL2)\b", body[0]))
+        n1 = len(re.findall(r"\b(?:FADD|FFMA|FMUL)\b", body[0]))
+        assert n2 >= 500 and n2 >= 0.4 * n1, (key, n2, n1)
+
+
 def test_no_cpu_fallback(native):
     import torch
     if torch.cuda.is_available():

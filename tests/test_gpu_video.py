@@ -19,7 +19,7 @@ def eng(mod):
     return mod.SpectralEngine(16000, 25.0, 200, device="cuda:0")
 
 
-@pytest.mark.parametrize("shape", [(37, 128, 128, 5), (1, 16, 24, 5), (300, 32, 32, 3)])
+@pytest.mark.parametrize("shape", [(37, 128, 128, 5), (1, 16, 24, 5), (300, 32, 32, 3), (9, 5, 7, 5), (11, 6, 6, 1)])
 def test_video_normalizer_matches_numpy(mod, eng, shape):
     rng = np.random.RandomState(sum(shape))
     video = (rng.rand(*shape) * 255.0).astype(np.float32)           # grey-scale mouth crops (dp:20-22)
