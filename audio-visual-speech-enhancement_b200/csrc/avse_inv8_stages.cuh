@@ -24,6 +24,7 @@
 #include "avse_fwd_stages.cuh"
 #include "avse_fwd4_stages.cuh"
 #include "avse_inv_stages.cuh"
+#include "avse_tables.h"
 
 #if !defined(AVSE_I8_POST_UNROLL)
 #define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
@@ -47,7 +48,8 @@ constexpr int I8_ACC = 20;                         // accumulator rows (40 sampl
 constexpr int I8_SIDE_ROWS = 12;                   // tail-column rows carried from one group to the next
 constexpr int I8_SIDE_F = I8_SIDE_ROWS * 8;        // 96 floats, double-buffered
 constexpr int I8_FLAG_F = N1 * ROW_F;              // per frame buffer: floats [1344, 1346) = "windowed frame A / B is non-zero"
-constexpr int I8_WARP_SMEM_F = I8_NC * FRAME4_F + I8_Y_F + 2 * I8_SIDE_F;     // 5440 + 640 + 192 = 6272 floats
+constexpr int I8_XCH_F = 2 * SPIKE_P * I8_FPG;     // 64 floats: (top, bottom) of every partition's local solve, per frame
+constexpr int I8_WARP_SMEM_F = I8_NC * FRAME4_F + I8_Y_F + 2 * I8_SIDE_F + I8_XCH_F;     // 5440 + 800 + 192 + 64 = 6496 floats
 static_assert(3 * I8_ST_C + 160 <= I8_Y_F && (I8_YS % 2) == 0, "the tail staging re-uses the coefficient buffer");
 static_assert(I8_FLAG_F + 2 <= FRAME4_F, "flags live in the frame buffer's pad");
 
@@ -165,6 +167,70 @@ AVSE_HD void i8_pass1_edge(const InvTile& tl, int lane, const float* s_win, cons
         tw[0].x = 1.0f; tw[0].y = 0.0f;
         p4_column(x, tw, frames + c * FRAME4_F + 2 * n2);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Coefficients c = (F F^T)^-1 10^(dB/20) of the group's eight frames, inside the kernel (round 1 and the 4-frame kernel run a
+// separate kernel over all frames: 48 us plus a 96 MB write + read through HBM).  Replaces np.linalg.pinv + np.dot of dp:112
+// together with db_to_amplitude (dp:101).  lane = (frame f = lane / 4, partition p = lane % 4): the 80-band tridiagonal system
+// is solved in "SPIKE" form -- four independent 20-band Thomas solves per frame, the 8 x 8 interface system (a constant matrix,
+// inverted on the host in float64) applied to the partitions' (top, bottom) values, which the lanes of a frame exchange through
+// 64 floats of shared memory, then one rank-2 correction per band with the precomputed spikes.  All 32 lanes busy, two dependent
+// chains of 20 steps instead of 80.  s_spk: [4][SPIKE_ROW] (avse_tables.h).
+// Three stages: load (issued early, the values ride through pass 1), local solve, correction + store into ybuf[band][I8_YS].
+// ---------------------------------------------------------------------------------------
+AVSE_HD void i8_coef_load(int lane, const float* mel, int layout, int ld_t, int t0, int T_use, float (&d)[SPIKE_Q]) {
+    const int f = lane >> 2, p = lane & 3, t = t0 + f;
+    if (t >= T_use) {                   // frames of the padded last group: 10^(-inf / 20) = 0 amplitude, zero coefficients
+#pragma unroll
+        for (int i = 0; i < SPIKE_Q; ++i) d[i] = -1.0e30f;
+        return;
+    }
+    const float* q;
+    int mstride;
+    if (layout == 0) {                  // AVSE_LAYOUT_SLICES [n_slices][80][20]
+        const int sl = t / SPSS, tt = t - sl * SPSS;
+        q = mel + ((size_t)sl * NMEL + SPIKE_Q * p) * SPSS + tt;
+        mstride = SPSS;
+    } else {                            // AVSE_LAYOUT_SPEC [80][ld_t]
+        q = mel + (size_t)(SPIKE_Q * p) * ld_t + t;
+        mstride = ld_t;
+    }
+#pragma unroll
+    for (int i = 0; i < SPIKE_Q; ++i) d[i] = q[(size_t)i * mstride];
+}
+
+AVSE_HD void i8_coef_local(int lane, const float* s_spk, float (&d)[SPIKE_Q], float* xch) {
+    constexpr float K = 0.16609640474436813f;   // log2(10) / 20 :  10^(dB/20) = 2^(K dB)   (librosa.db_to_amplitude)
+    const int f = lane >> 2, p = lane & 3;
+    const float* tb = s_spk + p * SPIKE_ROW;
+#pragma unroll
+    for (int i = 0; i < SPIKE_Q; ++i) d[i] = exp2f(K * d[i]);
+#pragma unroll
+    for (int i = 1; i < SPIKE_Q; ++i) d[i] = fmaf(-tb[i], d[i - 1], d[i]);
+    d[SPIKE_Q - 1] *= tb[SPIKE_Q + SPIKE_Q - 1];
+#pragma unroll
+    for (int i = SPIKE_Q - 2; i >= 0; --i) d[i] = fmaf(-tb[2 * SPIKE_Q + i], d[i + 1], d[i]) * tb[SPIKE_Q + i];
+    xch[8 * f + 2 * p] = d[0];
+    xch[8 * f + 2 * p + 1] = d[SPIKE_Q - 1];
+}
+
+AVSE_HD void i8_coef_finish(int lane, const float* s_spk, const float (&d)[SPIKE_Q], const float* xch, float* ybuf) {
+    const int f = lane >> 2, p = lane & 3;
+    const float* tb = s_spk + p * SPIKE_ROW;
+    const float* rb = tb + 5 * SPIKE_Q;
+    const float* rt = rb + 2 * SPIKE_P;
+    float bprev = 0.0f, tnext = 0.0f;           // x[20 p - 1] and x[20 p + 20] of the full solution
+#pragma unroll
+    for (int k = 0; k < 2 * SPIKE_P; ++k) {
+        const float y = xch[8 * f + k];
+        bprev = fmaf(rb[k], y, bprev);
+        tnext = fmaf(rt[k], y, tnext);
+    }
+    float* dst = ybuf + I8_YS * (SPIKE_Q * p) + f;
+#pragma unroll
+    for (int i = 0; i < SPIKE_Q; ++i)
+        dst[I8_YS * i] = fmaf(-tb[4 * SPIKE_Q + i], tnext, fmaf(-tb[3 * SPIKE_Q + i], bprev, d[i]));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -80,6 +80,7 @@ struct InvParams {
     const float* tw1t;
     const int* col_band;
     const float* col_w;
+    const float* spike;
     int T;            // mixture STFT frames
     int T_use;        // frames reconstructed
     int T_pad;        // coefficient row length (multiple of 4, >= 4 (G + 1))
@@ -271,7 +272,8 @@ constexpr int I8_SM_WIN = I8_WARPS * I8_WARP_SMEM_F;         // [640] window
 constexpr int I8_SM_TW = I8_SM_WIN + NFFT;                   // [16][40] vec2   W^{n2 k1}, n2 minor
 constexpr int I8_SM_TWT = I8_SM_TW + N1 * N2 * 2;            // [40][16] vec2   W^{n1' k2'}, n1' minor
 constexpr int I8_SM_COL = I8_SM_TWT + N1 * N2 * 2;           // [SCAN4_BINS] ivec4 (b0, b1, w0 / 640, w1 / 640)
-constexpr int I8_SMEM_F = I8_SM_COL + SCAN4_BINS * 4;
+constexpr int I8_SM_SPK = I8_SM_COL + SCAN4_BINS * 4;        // [4][SPIKE_ROW] partitioned tridiagonal solve (avse_tables.h)
+constexpr int I8_SMEM_F = I8_SM_SPK + SPIKE_P * SPIKE_ROW;
 constexpr int I8_SMEM_BYTES = I8_SMEM_F * 4;
 static_assert((I8_SM_COL % 4) == 0 && (I8_SM_TW % 2) == 0 && (I8_WARP_SMEM_F % 4) == 0, "table alignment");
 static_assert(I8_SMEM_BYTES + 1024 <= 232448, "I8 shared memory must fit in one SM");
@@ -294,9 +296,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             e[2] = __float_as_int(P.col_w[2 * i] * INV_SCALE); e[3] = __float_as_int(P.col_w[2 * i + 1] * INV_SCALE);   // irfft's 1/640 folded in
         } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
     }
+    for (int i = threadIdx.x; i < SPIKE_P * SPIKE_ROW; i += I8_THREADS) smem[I8_SM_SPK + i] = P.spike[i];
     float* frames = smem + warp * I8_WARP_SMEM_F;
     float* ybuf = frames + I8_NC * FRAME4_F;
     float* side = ybuf + I8_Y_F;
+    float* xch = side + 2 * I8_SIDE_F;
     for (int i = lane; i < I8_WARP_SMEM_F; i += 32) frames[i] = 0.0f;
     __syncthreads();
 
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
     const vec2* s_tw = reinterpret_cast<const vec2*>(smem + I8_SM_TW);
     const vec2* s_twT = reinterpret_cast<const vec2*>(smem + I8_SM_TWT);
     const ivec4* s_col = reinterpret_cast<const ivec4*>(smem + I8_SM_COL);
+    const float* s_spk = smem + I8_SM_SPK;
     const avse_inverse_args& A = P.a;
     Lane4Const lc;
     lane4_const_init(lane, s_win, s_tw, lc);
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
         tl.valid = valid < 0 ? 0 : (valid < A.L ? valid : A.L);
         tl.T = P.T;
         tl.T_use = P.T_use;
-        const float* ycoef = A.work + (size_t)u * A.work_stride;
+        const float* mel = A.mel_db + (size_t)u * A.mel_stride;
         O* out = static_cast<O*>(A.out_pcm) + (size_t)u * A.out_stride;
 
         float acc[I8_ACC];
@@ -359,13 +364,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             const float* side_in = side + I8_SIDE_F * (g & 1);
             float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
             if (have) {
-                // coefficients of the 8 frames -> ybuf[band][8]: 160 16-byte loads per warp, issued now, stored after pass 1
-                float4 cf[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int idx = lane + 32 * q, m = idx >> 1, hf = idx & 1;
-                    cf[q] = *reinterpret_cast<const float4*>(ycoef + (size_t)m * P.T_pad + tl.t0 + 4 * hf);
-                }
+                // coefficients of the 8 frames -> ybuf[band][I8_YS] (i8_coef_*): the 20 dB values of this lane are loaded now and
+                // ride through pass 1; the partitioned tridiagonal solve runs after it
+                float cd[SPIKE_Q];
+                i8_coef_load(lane, mel, A.layout, A.ld_t, tl.t0, P.T_use, cd);
                 if (!EXT) {
                     if (interior) {
                         i8_pass1_main(lane, raw, lc, frames);
@@ -374,13 +376,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                         i8_pass1_edge(tl, lane, s_win, s_tw, frames);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int idx = lane + 32 * q;
-                    float* yd = ybuf + I8_YS * (idx >> 1) + 4 * (idx & 1);      // [band m][I8_YS]: 8-byte aligned for any even I8_YS
-                    *reinterpret_cast<float2*>(yd) = make_float2(cf[q].x, cf[q].y);
-                    *reinterpret_cast<float2*>(yd + 2) = make_float2(cf[q].z, cf[q].w);
-                }
+                i8_coef_local(lane, s_spk, cd, xch);
+                __syncwarp();
+                i8_coef_finish(lane, s_spk, cd, xch, ybuf);
                 __syncwarp();
                 if (EXT) {
                     const int tA = tl.t0 + 2 * (lane >> 3);
@@ -456,7 +454,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     if (!ctx || !args) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL argument");
     if (ctx->generic) return avse_generic_inverse(ctx, args, stream);
     const avse_inverse_args& a = *args;
-    if (!a.mel_db || (!a.mixed_pcm && !a.phase) || !a.out_pcm || !a.work) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
+    if (!a.mel_db || (!a.mixed_pcm && !a.phase) || !a.out_pcm) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
     if (a.B <= 0 || (!a.phase && a.L <= HALF)) return avse_fail(AVSE_E_ARG, "avse_inverse: need B > 0 and L > 320");
     if (a.layout != AVSE_LAYOUT_SLICES && a.layout != AVSE_LAYOUT_SPEC) return avse_fail(AVSE_E_ARG, "avse_inverse: bad layout");
     if (a.out_format != AVSE_SAMPLE_F32 && a.out_format != AVSE_SAMPLE_I16) return avse_fail(AVSE_E_ARG, "avse_inverse: bad out_format");
@@ -475,8 +473,11 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     P.T_pad = fpg * (P.G + 1);
     P.out_len = HOP * (P.T_use - 1);
     if (a.layout == AVSE_LAYOUT_SPEC && a.ld_t < P.T_use) return avse_fail(AVSE_E_ARG, "avse_inverse: ld_t < frames used");
-    if (a.work_stride < (long long)NMEL * P.T_pad) return avse_fail(AVSE_E_ARG, "avse_inverse: work_stride too small (see avse_inverse_work_elems)");
-    if (((size_t)a.work & 15) || (a.work_stride & 3)) return avse_fail(AVSE_E_ARG, "avse_inverse: work must be 16-byte aligned with work_stride % 4 == 0");
+    if (!use8) {      // scratch is only used by the 4-frame kernel (the I8 kernel keeps the coefficients on chip)
+        if (!a.work) return avse_fail(AVSE_E_ARG, "avse_inverse: NULL buffer");
+        if (a.work_stride < (long long)NMEL * P.T_pad) return avse_fail(AVSE_E_ARG, "avse_inverse: work_stride too small (see avse_inverse_work_elems)");
+        if (((size_t)a.work & 15) || (a.work_stride & 3)) return avse_fail(AVSE_E_ARG, "avse_inverse: work must be 16-byte aligned with work_stride % 4 == 0");
+    }
     if (a.out_stride < P.out_len) return avse_fail(AVSE_E_ARG, "avse_inverse: out_stride < 160 (T_use - 1)");
     if (a.phase && a.phase_stride < (long long)P.T_use * NBINS) return avse_fail(AVSE_E_ARG, "avse_inverse: phase_stride too small");
     if (!a.phase && !a.len_pcm && a.pcm_stride < a.L) return avse_fail(AVSE_E_ARG, "avse_inverse: pcm_stride < L needs len_pcm");
@@ -484,6 +485,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     P.tw1t = ctx->fwd.tw1t;
     P.col_band = ctx->d_col_band;
     P.col_w = ctx->d_col_w;
+    P.spike = ctx->d_spike;
 
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -501,7 +503,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
         configured_dev = dev;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    {
+    if (!use8) {      // the I8 kernel solves for the coefficients itself (i8_coef_*); only the 4-frame kernel needs this pass
         dim3 grid((unsigned)a.B, (unsigned)((P.T_pad + 127) / 128));
         avse_mel_to_coef_kernel<<<grid, 128, 0, st>>>(a.mel_db, a.layout, a.ld_t, a.mel_stride, P.T_use, P.T_pad, ctx->d_tri_w,
                                                       ctx->d_tri_ipiv, ctx->d_tri_sup, a.work, a.work_stride);

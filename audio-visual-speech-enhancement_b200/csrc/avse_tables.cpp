@@ -132,6 +132,64 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
         t.tri_sup[i] = (float)sup[i];
     }
 
+    // ---- SPIKE partition of the same system (see avse_tables.h): everything in float64, rounded once ----
+    {
+        const int P = SPIKE_P, Q = SPIKE_Q;
+        t.spike.assign((size_t)P * SPIKE_ROW, 0.0f);
+        std::vector<std::vector<double>> wv(P, std::vector<double>(Q, 0.0)), vv(P, std::vector<double>(Q, 0.0));
+        for (int p = 0; p < P; ++p) {
+            const int r0 = Q * p;
+            float* row = t.spike.data() + (size_t)p * SPIKE_ROW;
+            std::vector<double> lp(Q), lw(Q, 0.0);
+            lp[0] = diag[r0];
+            for (int i = 1; i < Q; ++i) { lw[i] = sub[r0 + i] / lp[i - 1]; lp[i] = diag[r0 + i] - lw[i] * sup[r0 + i - 1]; }
+            auto solve = [&](std::vector<double> d) {          // local Thomas solve in float64
+                for (int i = 1; i < Q; ++i) d[i] -= lw[i] * d[i - 1];
+                d[Q - 1] /= lp[Q - 1];
+                for (int i = Q - 2; i >= 0; --i) d[i] = (d[i] - sup[r0 + i] * d[i + 1]) / lp[i];
+                return d;
+            };
+            if (p > 0) { std::vector<double> e(Q, 0.0); e[0] = sub[r0]; wv[p] = solve(e); }
+            if (p < P - 1) { std::vector<double> e(Q, 0.0); e[Q - 1] = sup[r0 + Q - 1]; vv[p] = solve(e); }
+            for (int i = 0; i < Q; ++i) {
+                row[i] = (float)lw[i];
+                row[Q + i] = (float)(1.0 / lp[i]);
+                row[2 * Q + i] = (float)(i < Q - 1 ? sup[r0 + i] : 0.0);
+                row[3 * Q + i] = (float)wv[p][i];
+                row[4 * Q + i] = (float)vv[p][i];
+            }
+        }
+        // interface system (I + S) z = y,  z = (t_0, b_0, ..., t_3, b_3)
+        const int M = 2 * P;
+        std::vector<double> A((size_t)M * M, 0.0), R((size_t)M * M, 0.0);
+        for (int i = 0; i < M; ++i) { A[(size_t)i * M + i] = 1.0; R[(size_t)i * M + i] = 1.0; }
+        for (int p = 0; p < P; ++p) {
+            if (p > 0) { A[(size_t)(2 * p) * M + 2 * (p - 1) + 1] = wv[p][0]; A[(size_t)(2 * p + 1) * M + 2 * (p - 1) + 1] = wv[p][Q - 1]; }
+            if (p < P - 1) { A[(size_t)(2 * p) * M + 2 * (p + 1)] = vv[p][0]; A[(size_t)(2 * p + 1) * M + 2 * (p + 1)] = vv[p][Q - 1]; }
+        }
+        for (int c = 0; c < M; ++c) {                           // Gauss-Jordan with partial pivoting (8 x 8, diagonally dominant)
+            int piv_r = c;
+            for (int r = c + 1; r < M; ++r) if (std::fabs(A[(size_t)r * M + c]) > std::fabs(A[(size_t)piv_r * M + c])) piv_r = r;
+            if (A[(size_t)piv_r * M + c] == 0.0) { t.error = "SPIKE interface system singular"; return false; }
+            for (int k = 0; k < M; ++k) { std::swap(A[(size_t)c * M + k], A[(size_t)piv_r * M + k]); std::swap(R[(size_t)c * M + k], R[(size_t)piv_r * M + k]); }
+            const double inv = 1.0 / A[(size_t)c * M + c];
+            for (int k = 0; k < M; ++k) { A[(size_t)c * M + k] *= inv; R[(size_t)c * M + k] *= inv; }
+            for (int r = 0; r < M; ++r) {
+                if (r == c) continue;
+                const double f = A[(size_t)r * M + c];
+                if (f == 0.0) continue;
+                for (int k = 0; k < M; ++k) { A[(size_t)r * M + k] -= f * A[(size_t)c * M + k]; R[(size_t)r * M + k] -= f * R[(size_t)c * M + k]; }
+            }
+        }
+        for (int p = 0; p < P; ++p) {
+            float* row = t.spike.data() + (size_t)p * SPIKE_ROW + 5 * SPIKE_Q;
+            for (int k = 0; k < M; ++k) {
+                row[k] = p > 0 ? (float)R[(size_t)(2 * (p - 1) + 1) * M + k] : 0.0f;          // x[r0 - 1]  = b_{p-1}
+                row[M + k] = p < P - 1 ? (float)R[(size_t)(2 * (p + 1)) * M + k] : 0.0f;      // x[r0 + 20] = t_{p+1}
+            }
+        }
+    }
+
     // ---- fused post+mel scan tables ----
     // Segment j = [mel_f[j], mel_f[j+1]); a bin in segment j feeds band j-1 (falling edge, accumulator A)
     // and band j (rising edge, accumulator B).  Lane chunk p scans bins 21p..21p+20 (p = 15: 315..319) and

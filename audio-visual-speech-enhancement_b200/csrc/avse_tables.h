@@ -10,6 +10,11 @@
 
 namespace avse {
 
+constexpr int SPIKE_P = 4;            // partitions of the 80-band tridiagonal solve
+constexpr int SPIKE_Q = NMEL / SPIKE_P;   // 20 bands each
+constexpr int SPIKE_ROW = 5 * SPIKE_Q + 16;   // 116 floats per partition
+static_assert(SPIKE_P * SPIKE_Q == NMEL, "partition of the mel bands");
+
 struct HostTables {
     int sample_rate = 16000;
     double fmin = 0.0, fmax = 8000.0;
@@ -39,6 +44,10 @@ struct HostTables {
     std::vector<float> tri_w;         // [80] Thomas forward multipliers (w[0] unused)
     std::vector<float> tri_ipiv;      // [80] 1 / pivot
     std::vector<float> tri_sup;       // [80] super-diagonal (sup[79] unused)
+    // the same solve partitioned for a warp (I8 inverse kernel): 4 blocks of 20 bands, "SPIKE" form -- per block the local Thomas
+    // factors (w, 1/pivot, super-diagonal), the left / right spikes A_p^-1 (T[r0][r0-1] e_0), A_p^-1 (T[r0+19][r0+20] e_19) and the
+    // two rows of the inverse 8 x 8 interface system that give x[r0-1] and x[r0+20] from the blocks' local (top, bottom) values
+    std::vector<float> spike;         // [4][SPIKE_ROW]: lw[20] lipiv[20] lsup[20] wv[20] vv[20] rb[8] rt[8]
     std::vector<int> col_band;        // [321][2] band index of the (<=2) non-zeros in column k (or 0)
     std::vector<float> col_w;         // [321][2] their weights (0 when absent)
 

@@ -410,7 +410,7 @@ class SpectralEngine(object):
 
     # ------------------------------------------------------------------ next row f1: make_sample_set on the device
     @_on_device
-    def make_sample_set(self, mixed_slices, speech_slices, n_slices=None, permutation=None, generator=None, extra=None):
+    def make_sample_set(self, mixed_slices, speech_slices, n_slices=None, permutation=None, generator=None, extra=None, check=True):
         """speech_enhancer.py:241-262 without the pickle / numpy round trip: concatenate the slices of all samples
         (np.concatenate over `sample.mixed_spectrograms` / `.speech_spectrograms`) and apply ONE shared permutation.
 
@@ -418,6 +418,8 @@ class SpectralEngine(object):
         slice counts [B] (dp:164 min(video, audio); None: n_max for all); permutation: int64 permutation of the
         sum(n_slices) concatenated rows (None: torch.randperm with `generator`); extra: optional third [B, n_max, ...]
         float32 array gathered with the same permutation (e.g. noise slices).
+        check: validate a caller-supplied permutation (the kernel flags out-of-range indices; reading the flag back is the
+        call's only host synchronisation -- pass False to stay asynchronous).
         Returns (mixed [N, 80, 20], speech [N, 80, 20], permutation) (+ extra rows when given)."""
         B, n_max = mixed_slices.shape[0], mixed_slices.shape[1]
         srcs = [mixed_slices, speech_slices] + ([extra] if extra is not None else [])
@@ -425,29 +427,38 @@ class SpectralEngine(object):
             assert t.dtype == torch.float32 and t.is_contiguous() and t.shape[:2] == (B, n_max)
         row = mixed_slices[0, 0].numel()
         assert all(t[0, 0].numel() == row for t in srcs), "rows of all arrays must have the same size"
-        if n_slices is None:
-            rows = torch.arange(B * n_max, device=self.device, dtype=torch.int64)
-        else:
+        rows = None                                  # None: every row is kept, concatenated row i is source row i
+        N = B * n_max
+        if n_slices is not None:
             ns = torch.as_tensor(n_slices, device=self.device, dtype=torch.int64)
             j = torch.arange(n_max, device=self.device, dtype=torch.int64)
             keep = j.unsqueeze(0) < ns.unsqueeze(1)                        # concatenation order: sample-major, slice-minor
             rows = (torch.arange(B, device=self.device, dtype=torch.int64).unsqueeze(1) * n_max + j.unsqueeze(0))[keep]
-        N = rows.numel()
+            N = rows.numel()
         user_perm = permutation is not None
         if permutation is None:
             permutation = torch.randperm(N, device=self.device, generator=generator)
         permutation = torch.as_tensor(permutation, device=self.device, dtype=torch.int64)
-        if permutation.numel() != N or (user_perm and N and (int(permutation.min()) < 0 or int(permutation.max()) >= N)):
+        if permutation.numel() != N:
             raise IndexError("permutation must hold %d indices in [0, %d)" % (N, N))
-        index = rows[permutation].contiguous()
+        if rows is None:
+            index = permutation.contiguous()
+            src_rows = B * n_max
+        else:
+            # out-of-range entries must reach the kernel's own check instead of faulting in this gather
+            index = rows[permutation.clamp(0, max(N - 1, 0))].contiguous()
+            if user_perm:
+                index = torch.where((permutation < 0) | (permutation >= N), torch.full_like(index, -1), index)
+            src_rows = B * n_max
         outs = [torch.empty((N,) + tuple(t.shape[2:]), dtype=torch.float32, device=self.device) for t in srcs]
         bad = torch.zeros(1, dtype=torch.int32, device=self.device)
         p = [_ptr(t) for t in srcs] + [0] * (3 - len(srcs))
         q = [_ptr(t) for t in outs] + [0] * (3 - len(outs))
-        check(self._lib.avse_gather_rows(self._ctx, p[0], p[1], p[2], B * n_max, row, _ptr(index), N, q[0], q[1], q[2], _ptr(bad),
-                                         self._stream()), "avse_gather_rows")
-        if user_perm and int(bad.item()):
-            raise IndexError("avse_gather_rows: index out of range")
+        rc = self._lib.avse_gather_rows(self._ctx, p[0], p[1], p[2], src_rows, row, _ptr(index), N, q[0], q[1], q[2], _ptr(bad),
+                                              self._stream())
+        _native.check(rc, "avse_gather_rows")
+        if user_perm and check and int(bad.item()):
+            raise IndexError("permutation must hold %d indices in [0, %d)" % (N, N))
         return tuple(outs[:2]) + (permutation,) + tuple(outs[2:])
 
 

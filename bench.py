@@ -653,11 +653,11 @@ def main():
         res = step()
         rows = B * N_VIDEO_SLICES
         perm = torch.randperm(rows, device=device)
-        ms = timed(lambda: eng.make_sample_set(res["mixed"], res["speech"], permutation=perm))
+        ms = timed(lambda: eng.make_sample_set(res["mixed"], res["speech"], permutation=perm, check=False))
         gb = 2 * 2 * rows * 6400 / 1e9                       # two arrays, every row read once and written once
         aux = {"make_sample_set": {"kernel": "avse_gather_rows_kernel", "what": "se:241-262: concat + one shared permutation of %d (80,20) slices x 2 arrays" % rows,
                                    "ms": ms, "achieved_gbs": gb / (ms * 1e-3), "frac_of_hbm_peak": gb / (ms * 1e-3) / peak,
-                                   "note": "includes the index construction (torch glue) of SpectralEngine.make_sample_set"}}
+                                   "note": "SpectralEngine.make_sample_set incl. its output allocations; asynchronous (check=False)"}}
         nv = 2000
         video = torch.rand((nv, 128, 128, 5), device=device) * 255.0
         vn_holder = {}

@@ -121,6 +121,7 @@ struct Inv8Warp {
     cpx x[32][40];
     float acc[32][I8_ACC];
     float raw[32][I8_RAW], rt[32][20];
+    float cd[32][SPIKE_Q];
     Lane4Const lc[32];
 };
 }  // namespace
@@ -135,8 +136,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
     const int T_pad = I8_FPG * (G + 1);
     const int out_len = HOP * (T_use - 1);
     if (out_cap < out_len) return -1;
-    std::vector<float> work;
-    mel_to_coef(h, mel_slices, T_use, T_pad, work);
+    (void)T_pad;
 
     std::vector<vec2> tw(N1 * N2), twT(N1 * N2);
     for (int k1 = 0; k1 < N1; ++k1)
@@ -172,6 +172,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
         float* frames = w.smem;
         float* ybuf = frames + I8_NC * FRAME4_F;
         float* side = ybuf + I8_Y_F;
+        float* xch = side + 2 * I8_SIDE_F;
         memset(w.acc, 0, sizeof(w.acc));
         memset(side, 0, sizeof(float) * 2 * I8_SIDE_F);
         InvTile tl{};
@@ -183,6 +184,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
             const float* side_in = side + I8_SIDE_F * (g & 1);
             float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
             if (have) {
+                for (int lane = 0; lane < 32; ++lane) i8_coef_load(lane, mel_slices, 0, 0, tl.t0, T_use, w.cd[lane]);
                 if (i8_group_interior(tl)) {
                     for (int lane = 0; lane < 32; ++lane) { i8_load_raw(tl, lane, w.raw[lane]); i8_load_tail_raw(tl, lane, w.rt[lane]); }
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames);
@@ -190,8 +192,8 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                 } else {
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames);
                 }
-                for (int m = 0; m < NMEL; ++m)
-                    for (int e = 0; e < I8_FPG; ++e) ybuf[I8_YS * m + e] = work[(size_t)m * T_pad + tl.t0 + e];
+                for (int lane = 0; lane < 32; ++lane) i8_coef_local(lane, h.spike.data(), w.cd[lane], xch);
+                for (int lane = 0; lane < 32; ++lane) i8_coef_finish(lane, h.spike.data(), w.cd[lane], xch, ybuf);
                 for (int it = 0; it < 4; ++it) {
                     const int r = it & 1;
                     if (it == 2)
@@ -220,4 +222,20 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
         }
     }
     return out_len;
+}
+
+// The I8 kernel's partitioned ("SPIKE") coefficient solve alone: dB slices [n_slices][80][20] -> c[t][80] for the 8 frames of group g.
+extern "C" int emul_coefficients8(const float* mel_slices, int n_slices, int g, float* out /* [8][80] */, int sample_rate, double fmin,
+                                  double fmax) {
+    HostTables h;
+    if (!build_tables(h, sample_rate, fmin, fmax)) return -2;
+    const int T_use = n_slices * SPSS;
+    static float cd[32][SPIKE_Q];
+    std::vector<float> ybuf(I8_Y_F, 0.0f), xch(I8_XCH_F, 0.0f);
+    for (int lane = 0; lane < 32; ++lane) i8_coef_load(lane, mel_slices, 0, 0, g * I8_FPG, T_use, cd[lane]);
+    for (int lane = 0; lane < 32; ++lane) i8_coef_local(lane, h.spike.data(), cd[lane], xch.data());
+    for (int lane = 0; lane < 32; ++lane) i8_coef_finish(lane, h.spike.data(), cd[lane], xch.data(), ybuf.data());
+    for (int f = 0; f < I8_FPG; ++f)
+        for (int m = 0; m < NMEL; ++m) out[f * NMEL + m] = ybuf[I8_YS * m + f];
+    return 0;
 }

@@ -88,3 +88,26 @@ def test_i8_lengths_around_the_group_size(emul, n_slices, L, valid, chunks):
     assert np.max(np.abs(out - want)) <= TOL_PCM * full
     old = _run(emul, mel, pcm, valid, 1, "i4")
     assert np.max(np.abs(out - old)) <= 0.2 * TOL_PCM * full
+
+
+def test_partitioned_tridiagonal_solve_equals_pinv(emul):
+    """The I8 kernel's coefficient stage (4 x 20-band SPIKE partition of F F^T, interface system inverted on the host in float64)
+    against numpy: F^T c must equal np.linalg.pinv(F) @ 10^(dB/20) (dp:101, dp:112) for every frame of a group, including the
+    zero-padded frames beyond the last one (coefficients exactly 0)."""
+    rng = np.random.RandomState(8)
+    fb = O.mel_filterbank(SR, 640, 80, 0.0, 8000.0)
+    pinv = np.linalg.pinv(fb)
+    mel = (rng.rand(1, 80, 20) * 90.0 - 80.0).astype(np.float32)        # 20 frames: group 2 holds frames 16..19 + 4 padded ones
+    emul.emul_coefficients8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    for g in (0, 2):
+        c = np.zeros((8, 80), np.float32)
+        assert emul.emul_coefficients8(_p(mel), 1, g, _p(c), SR, 0.0, 8000.0) == 0
+        for f in range(8):
+            t = 8 * g + f
+            if t >= 20:
+                assert np.all(c[f] == 0.0)
+                continue
+            amp = 10.0 ** (mel[0, :, t].astype(np.float64) / 20.0)
+            want = pinv @ amp
+            got = fb.T @ c[f].astype(np.float64)
+            assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want)), (g, f)
