@@ -29,6 +29,9 @@
 #if !defined(AVSE_I8_POST_UNROLL)
 #define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
 #endif
+#if !defined(AVSE_I8_PREFETCH_MEL)
+#define AVSE_I8_PREFETCH_MEL 0
+#endif
 #if !defined(AVSE_I8_ROLL_P1)
 #define AVSE_I8_ROLL_P1 1        // pass 1: one copy of the column code, the 20-stride window slides through the raw registers
 #endif
@@ -97,9 +100,28 @@ AVSE_HD void i8_mark(const float* r, int n2, float* frame_base) {
     if ((b & 0x7fffffff) != 0) frame_base[I8_FLAG_F + 1] = 1.0f;
 }
 
+// The same flags for the eight frames of a main lane (column n2 = lane) in one go, from the 44 raw strides: frame t uses strides
+// [4t, 4t + 16); its n = 0 sample (w[0] = 0) is stride 4t of column 0.  ORs of 4-stride blocks are shared between the frames
+// (~50 logic instructions per group; marking inside the rolled column loop cost 55 instructions per frame).
+AVSE_HD void i8_mark_group(const float (&raw)[I8_RAW], int lane, float* frames) {
+    int rest[11], blk[11];       // rest[b] = OR of strides 4b+1 .. 4b+3, blk[b] = rest[b] | stride 4b
+#pragma unroll
+    for (int b = 0; b < 11; ++b) {
+        rest[b] = float_bits(raw[4 * b + 1]) | float_bits(raw[4 * b + 2]) | float_bits(raw[4 * b + 3]);
+        blk[b] = rest[b] | float_bits(raw[4 * b]);
+    }
+#pragma unroll
+    for (int t = 0; t < I8_FPG; ++t) {
+        const int first = lane != 0 ? float_bits(raw[4 * t]) : 0;
+        const int any = rest[t] | first | blk[t + 1] | blk[t + 2] | blk[t + 3];
+        if ((any & 0x7fffffff) != 0) frames[(t >> 1) * FRAME4_F + I8_FLAG_F + (t & 1)] = 1.0f;
+    }
+}
+
 // pass 1, interior groups, columns n2 = lane of the four FFTs.  FFT c packs frames (t0 + 2c, t0 + 2c + 1): strides [8c, 8c+16)
 // and [8c+4, 8c+20) of the batch.  Consumes (rotates) raw[] when rolled.
 AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames) {
+    i8_mark_group(raw, lane, frames);
 #if AVSE_I8_ROLL_P1
     float* dst = frames + 2 * lane;
 #pragma unroll 1
@@ -107,7 +129,6 @@ AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc,
         cpx x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j] * lc.win[j], raw[j + 4] * lc.win[j]);
-        i8_mark(raw, lane, dst - 2 * lane);
         p4_column(x, lc.tw, dst);
         dst += FRAME4_F;
 #pragma unroll
@@ -119,7 +140,6 @@ AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc,
         cpx x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = cmake(raw[8 * c + j] * lc.win[j], raw[8 * c + j + 4] * lc.win[j]);
-        i8_mark(raw + 8 * c, lane, frames + c * FRAME4_F);
         p4_column(x, lc.tw, frames + c * FRAME4_F + 2 * lane);
     }
 #endif
@@ -198,6 +218,20 @@ AVSE_HD void i8_coef_load(int lane, const float* mel, int layout, int ld_t, int 
     }
 #pragma unroll
     for (int i = 0; i < SPIKE_Q; ++i) d[i] = q[(size_t)i * mstride];
+#if defined(__CUDA_ARCH__) && AVSE_I8_PREFETCH_MEL
+    // L2 prefetch of the same bands two groups ahead (SPEC layout: 16 floats further; SLICES: the frame 16 later, possibly in the
+    // next slice).  One lane per (partition, band-row sector): the frame lanes f = 0 of each partition issue them.
+    if ((lane >> 2) == 0) {
+        const int t2 = t + 2 * I8_FPG;
+        if (t2 < T_use) {
+            const float* q2;
+            if (layout == 0) { const int sl = t2 / SPSS, tt = t2 - sl * SPSS; q2 = mel + ((size_t)sl * NMEL + SPIKE_Q * p) * SPSS + tt; }
+            else q2 = q + 2 * I8_FPG;
+#pragma unroll
+            for (int i = 0; i < SPIKE_Q; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(q2 + (size_t)i * mstride));
+        }
+    }
+#endif
 }
 
 AVSE_HD void i8_coef_local(int lane, const float* s_spk, float (&d)[SPIKE_Q], float* xch) {

@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(INV_THREADS, 2) avse_inverse_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 // I8 kernel: eight real frames (four packed FFTs) per group, 8 warps per SM.  See avse_inv8_stages.cuh.
 // ---------------------------------------------------------------------------------------------
+#if !defined(AVSE_I8_PIPE_MEL)
+#define AVSE_I8_PIPE_MEL 0       // 1: the next group's dB values are loaded a whole group ahead (20 more loop-carried registers)
+#endif
 constexpr int I8_WARPS = 8;
 constexpr int I8_THREADS = I8_WARPS * 32;
 constexpr int I8_SM_WIN = I8_WARPS * I8_WARP_SMEM_F;         // [640] window
@@ -348,12 +351,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
         __syncwarp();
 
         // software pipeline: the samples of the next computed group are loaded before pass B of the current one
-        float raw[I8_RAW], rt[20];
+        float raw[I8_RAW], rt[20], cd[SPIKE_Q];
         bool interior = false;
         tl.t0 = g_first * I8_FPG;
-        if (!EXT && tl.t0 < P.T_use) {
-            interior = i8_group_interior(tl);
-            if (interior) { i8_load_raw(tl, lane, raw); i8_load_tail_raw(tl, lane, rt); }
+        if (tl.t0 < P.T_use) {
+#if AVSE_I8_PIPE_MEL
+            i8_coef_load(lane, mel, A.layout, A.ld_t, tl.t0, P.T_use, cd);
+#endif
+            if (!EXT) {
+                interior = i8_group_interior(tl);
+                if (interior) { i8_load_raw(tl, lane, raw); i8_load_tail_raw(tl, lane, rt); }
+            }
         }
 
 #pragma unroll 1
@@ -364,10 +372,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             const float* side_in = side + I8_SIDE_F * (g & 1);
             float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
             if (have) {
-                // coefficients of the 8 frames -> ybuf[band][I8_YS] (i8_coef_*): the 20 dB values of this lane are loaded now and
-                // ride through pass 1; the partitioned tridiagonal solve runs after it
-                float cd[SPIKE_Q];
+                // coefficients of the 8 frames -> ybuf[band][I8_YS] (i8_coef_*): the 20 dB values of this lane are loaded ahead of
+                // pass 1 (AVSE_I8_PIPE_MEL: one whole group ahead, with the samples); the partitioned solve runs after pass 1
+#if !AVSE_I8_PIPE_MEL
                 i8_coef_load(lane, mel, A.layout, A.ld_t, tl.t0, P.T_use, cd);
+#endif
                 if (!EXT) {
                     if (interior) {
                         i8_pass1_main(lane, raw, lc, frames);
@@ -409,12 +418,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             }
             // ---- next computed group: issue its loads now (they land during pass B / emit) ----
             bool interior2 = false;
-            if (!EXT && g < g_last) {
+            if (g < g_last) {
                 InvTile tn = tl;
                 tn.t0 = (g + 1) * I8_FPG;
                 if (tn.t0 < P.T_use) {
-                    interior2 = i8_group_interior(tn);
-                    if (interior2) { i8_load_raw(tn, lane, raw); i8_load_tail_raw(tn, lane, rt); }
+#if AVSE_I8_PIPE_MEL
+                    i8_coef_load(lane, mel, A.layout, A.ld_t, tn.t0, P.T_use, cd);
+#endif
+                    if (!EXT) {
+                        interior2 = i8_group_interior(tn);
+                        if (interior2) { i8_load_raw(tn, lane, raw); i8_load_tail_raw(tn, lane, rt); }
+                    }
                 }
             }
             // ---- pass B + emit: one FFT at a time (rolled), two finished hops leave after each ----

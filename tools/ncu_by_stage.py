@@ -58,7 +58,13 @@ for l in lines:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KFILTER, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; ix = {n: i for i, n in enumerate(h)}
-data = [r for r in rows[2:] if len(r) >= len(h)]
+data = []
+for r in rows[2:]:                       # a report with several launches repeats the header: keep the first launch only
+    if len(r) < len(h):
+        continue
+    if r[ix["Address"]] == "Address":
+        break
+    data.append(r)
 base = int(data[0][ix["Address"]], 16)
 byoff = {int(r[ix["Address"]], 16) - base: r for r in data}
 agg = collections.defaultdict(lambda: collections.Counter())

@@ -48,6 +48,8 @@ tot = tots = 0
 for r in rows[2:]:
     if len(r) < len(h):
         continue
+    if r[ix["Source"]] == "Source":       # a report with several launches repeats the header: keep the first launch only
+        break
     toks = r[ix["Source"]].split()
     o = toks[1] if toks[0].startswith("@") else toks[0]
     o = o.split(".")[0]
