@@ -611,6 +611,62 @@ def shard_range(n_utterances, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class CorpusDriver(object):
+    """Product-level multi-GPU driver (BASELINE configs[2]): ONE corpus, cut into contiguous utterance shards, one
+    process per GPU.  Utterances are independent units (the variance of dp:130 and the top_db maximum of dp:94 are
+    per-utterance), so there is NO collective on the data path: every rank runs `preprocess` on its own shard in launches of
+    at most `launch` utterances.  The only communication is the optional `gather` of the results to one rank at the very end
+    (torch.distributed: NCCL over NVLink for CUDA tensors, gloo in the CPU tests), outside the hot path.
+
+    The reference's counterpart is `multiprocess.Pool(16).map` over samples (dp:194-195); `--gpus` is parsed and never read
+    (se:283, se:289)."""
+
+    def __init__(self, engine, rank=None, world_size=None, launch=12500):
+        import torch.distributed as dist
+        self.eng = engine
+        ready = dist.is_available() and dist.is_initialized()
+        self.rank = int(rank if rank is not None else (dist.get_rank() if ready else 0))
+        self.world_size = int(world_size if world_size is not None else (dist.get_world_size() if ready else 1))
+        self.launch = int(launch)
+        self.launches = 0
+
+    def shard(self, n_utterances):
+        """[lo, hi) of this rank."""
+        return shard_range(n_utterances, self.rank, self.world_size)
+
+    def preprocess(self, speech, noise, n_video_slices, lengths=None, snr_db=None, noise_lengths=None, out=None):
+        """preprocess_audio_pair (dp:119-139) over THIS rank's shard (device tensors [n, >= L]); returns a list with one
+        (mixed, speech, noise, mixed_pcm) tuple per launch, or fills / re-uses `out` (a list of dicts from a previous call)."""
+        n = speech.shape[0]
+        results = []
+        outs = out if out is not None else [dict() for _ in range(0, n, self.launch)]
+        for j, a in enumerate(range(0, n, self.launch)):
+            b = min(n, a + self.launch)
+            cut = lambda t: None if t is None else t[a:b]
+            results.append(self.eng.preprocess_pairs(speech[a:b], noise[a:b], n_video_slices, lengths=cut(lengths), snr_db=cut(snr_db),
+                                                     noise_lengths=cut(noise_lengths), out=outs[j]))
+            self.launches += 3
+        self.out = outs
+        return results
+
+    def gather(self, shard_tensor, n_utterances, dst=0):
+        """Optional final gather of a per-utterance result [n_shard, ...] to rank `dst` (None elsewhere); rows come back in
+        corpus order.  Shards differ by at most one row, so they are padded to the largest and trimmed after the collective."""
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return shard_tensor
+        sizes = [b - a for a, b in (shard_range(n_utterances, r, self.world_size) for r in range(self.world_size))]
+        m = max(sizes)
+        pad = shard_tensor
+        if shard_tensor.shape[0] < m:
+            pad = torch.cat([shard_tensor, shard_tensor.new_zeros((m - shard_tensor.shape[0],) + tuple(shard_tensor.shape[1:]))])
+        pieces = [torch.empty_like(pad) for _ in range(self.world_size)] if self.rank == dst else None
+        dist.gather(pad.contiguous(), pieces, dst=dst)
+        if self.rank != dst:
+            return None
+        return torch.cat([p[:k] for p, k in zip(pieces, sizes)])
+
+
 def fit_noise(noise, n_noise, n_speech_max):
     """dp:125-128 for a batch as an explicit copy: periodic tiling noise[i mod n_noise] up to the speech length.  The
     product path does not need it (pass `noise_lengths` to preprocess_pairs: the kernels address noise[i mod Ln]

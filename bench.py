@@ -416,18 +416,12 @@ def run_corpus(args, torch, dist, eng, eng_mod, device, rank, world):
     n = hi - lo
     speech, noise = corpus_batch(torch, n, device, base_seed=lo)
     launch = min(n, max(1, args.batch if args.batch != 1000 else 12500))
-    outs = []
-    for a in range(0, n, launch):
-        m = min(launch, n - a)
-        outs.append({k: torch.empty((m, N_VIDEO_SLICES, 80, 20), device=device) for k in ("speech", "noise", "mixed")})
-        outs[-1]["mixed_pcm"] = torch.empty((m, L), device=device)
+    drv = eng_mod.CorpusDriver(eng, rank=rank, world_size=world, launch=launch)       # the product-level sharding driver
+    assert drv.shard(args.corpus) == (lo, hi)
+    outs = [dict() for _ in range(0, n, launch)]
 
     def step():
-        for j, a in enumerate(range(0, n, launch)):
-            m = min(launch, n - a)
-            f, keys = eng.snr_factor(speech[a:a + m], noise[a:a + m], max_key=outs[j].get("max_key"))
-            r = eng.forward_raw(speech[a:a + m], noise[a:a + m], L=L, factor=f, n_slices=N_VIDEO_SLICES, max_key=keys, out=outs[j])
-            eng.floor3_(r["speech"], r["noise"], r["mixed"], keys)
+        drv.preprocess(speech, noise, N_VIDEO_SLICES, out=outs)
 
     def barrier():
         if world > 1:

@@ -95,3 +95,23 @@ def test_config5_long_form_batch_matches_oracle(eng):
         print("config 5 (64 x 60 s, SNR sweep): worst log-mel error %.2e dB" % worst)
     finally:
         bench.set_workload(3.0, False)
+
+
+def test_corpus_driver_shards_equal_the_whole(eng):
+    """engine.CorpusDriver (the product-level multi-GPU driver): two ranks' shards, each processed in launches of 40 utterances,
+    concatenate to exactly what one launch over the whole corpus gives (no collective on the data path)."""
+    mod = importlib.import_module("audio-visual-speech-enhancement_b200.engine")
+    bench.set_workload(3.0, False)
+    n = 101
+    speech, noise = bench.synth_batch(torch, n, torch.device("cuda", 0), seed=3)
+    snr = torch.linspace(-10, 10, n, device="cuda")
+    whole = eng.preprocess_pairs(speech, noise, 15, snr_db=snr)
+    parts = []
+    for rank in range(2):
+        drv = mod.CorpusDriver(eng, rank=rank, world_size=2, launch=40)
+        lo, hi = drv.shard(n)
+        res = drv.preprocess(speech[lo:hi], noise[lo:hi], 15, snr_db=snr[lo:hi])
+        assert len(res) == -(-(hi - lo) // 40) and drv.launches == 3 * len(res)
+        parts.append([torch.cat([r[k] for r in res]) for k in range(4)])
+    for k in range(4):
+        assert torch.equal(torch.cat([parts[0][k], parts[1][k]]), whole[k])

@@ -30,8 +30,20 @@ def _worker(rank, world, port, n_utt, q):
     dist.all_reduce(cover)                      # test-only check that the shards tile the corpus exactly once
     t = torch.tensor([float(hi - lo) * 1e-3])   # stand-in for this rank's CUDA-event time
     dist.all_reduce(t, op=dist.ReduceOp.MAX)    # bench.py: max over ranks
+    # the product-level driver's optional final gather (engine.CorpusDriver.gather): rows come back in corpus order
+    drv = eng.CorpusDriver(None, launch=7)
+    assert (drv.rank, drv.world_size) == (rank, world) and drv.shard(n_utt) == (lo, hi)
+    mine = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1).expand(hi - lo, 3).contiguous()
+    full = drv.gather(mine, n_utt, dst=0)
+    gathered_ok = True
     if rank == 0:
-        q.put((bool((cover == 1).all()), float(t[0]), hi - lo))
+        gathered_ok = full.shape == (n_utt, 3) and bool((full[:, 0] == torch.arange(n_utt, dtype=torch.float32)).all())
+    else:
+        gathered_ok = full is None
+    flag = torch.tensor([1 if gathered_ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put((bool((cover == 1).all()) and bool(flag[0] == 1), float(t[0]), hi - lo))
     dist.barrier()
     dist.destroy_process_group()
 
