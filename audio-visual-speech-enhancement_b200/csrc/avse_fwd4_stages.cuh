@@ -202,6 +202,71 @@ AVSE_HD void stage4_pass1_tail(const FwdTileT<S>& tl, int nz_shift, int lane, co
     stage4_pass1_tail_compute(tl, lane, rs, rn, s_win, s_tw, frames);
 }
 
+// Pass 1 of an interior group as ONE rolled loop over its five rounds (four main rounds + the tail round): the round-specific
+// part is only the 32 window multiplies (a switch over the round picks the statically indexed raw registers), the DFT-16 +
+// twiddle + store code exists once.  The twiddles of a lane are no longer kernel-lifetime registers: they are (re)loaded from
+// the CTA's table at round 0 (n2 = lane) and round 4 (n2 = 32 + lane % 8), 15 + 15 8-byte loads per group, which also frees 32
+// registers.  Motivation: the hot loop of this kernel is ~45 KB against a 32 KB L1.5 instruction cache, and pass 1 was 1 500
+// of its 2 800 instructions (AVSE_P1_UNIFIED, A/B in profiles/README.md).
+template <typename S>
+AVSE_HD void stage4_pass1_unified(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4], const float (&ts)[16], float (&tn)[16],
+                                  const Lane4Const& lc, const float* s_win, const vec2* s_tw, float* frames) {
+    const float gain = tl.gain;
+    const int tf = lane >> 3, tn2 = 32 + (lane & 7);          // the lane's (frame, column) in the tail round
+#pragma unroll
+    for (int j = 0; j < RAW4; ++j) rn[j] *= gain;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tn[j] *= gain;
+    if (tl.mixed_pcm != nullptr) {
+        float* pm = tl.mixed_pcm + tl.t0 * HOP + lane;
+#pragma unroll
+        for (int j = 8; j < 24; ++j) pm[N2 * (j - 8)] = rs[j] + tl.factor * rn[j];
+        float* pt = tl.mixed_pcm + (tl.t0 + tf) * HOP + tn2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pt[N2 * j] = ts[8 + j] + tl.factor * tn[8 + j];
+    }
+    vec2 tw[16];
+    tw[0].x = 1.0f; tw[0].y = 0.0f;
+#pragma unroll 1
+    for (int round = 0; round < 5; ++round) {
+        if (round == 0 || round == 4) {
+            const int n2 = round == 0 ? lane : tn2;
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw[k1 * N2 + n2];
+        }
+        cpx x[16];
+        float* dst;
+        switch (round) {
+        case 0:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(rs[j] * lc.win[j], rn[j] * lc.win[j]);
+            dst = frames + 2 * lane;
+            break;
+        case 1:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(rs[4 + j] * lc.win[j], rn[4 + j] * lc.win[j]);
+            dst = frames + FRAME4_F + 2 * lane;
+            break;
+        case 2:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(rs[8 + j] * lc.win[j], rn[8 + j] * lc.win[j]);
+            dst = frames + 2 * FRAME4_F + 2 * lane;
+            break;
+        case 3:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = cmake(rs[12 + j] * lc.win[j], rn[12 + j] * lc.win[j]);
+            dst = frames + 3 * FRAME4_F + 2 * lane;
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float w = s_win[N2 * j + tn2]; x[j] = cmake(ts[j] * w, tn[j] * w); }
+            dst = frames + tf * FRAME4_F + 2 * tn2;
+            break;
+        }
+        p4_column(x, tw, dst);
+    }
+}
+
 // Edge / generic groups (first and last frames of an utterance, short or zero-padded signals): every sample
 // goes through the reflect + zero-pad loader.  Cold code, rolled over the five rounds.
 template <typename S, bool TILED>

@@ -566,6 +566,9 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
 // up to 255 registers per thread so that the pass-1 window / twiddle values stay in registers for the whole
 // kernel.  See avse_fwd4_stages.cuh for the stage functions and the reasoning.
 // ---------------------------------------------------------------------------------------------
+#ifndef AVSE_P1_UNIFIED
+#define AVSE_P1_UNIFIED 0      // 1: pass 1 as one rolled five-round loop (stage4_pass1_unified)
+#endif
 #ifndef AVSE_F4_PREFETCH
 #define AVSE_F4_PREFETCH 2
 #endif
@@ -712,8 +715,12 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         // ---- pass 1 ----
         tl.gain = utt_sm[2 * (u & 1)];
         if (interior) {
+#if AVSE_P1_UNIFIED
+            stage4_pass1_unified(tl, lane, rs, rn, ts, tn, lc, s_win, s_tw, frames);
+#else
             stage4_pass1_main(tl, lane, rs, rn, lc, frames);
             stage4_pass1_tail_compute(tl, lane, ts, tn, s_win, s_tw, frames);
+#endif
         } else {
             stage4_pass1_edge<S, TILED>(tl, lane, s_win, s_tw, frames);
         }

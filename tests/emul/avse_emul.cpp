@@ -140,7 +140,7 @@ extern "C" int emul_forward(const float* speech, const float* noise, int L, int 
 struct EmulWarp4 {
     alignas(16) float frames[WARP4_SMEM_F];
     cpx x[32][40];
-    float rs[32][RAW4], rn[32][RAW4];
+    float rs[32][RAW4], rn[32][RAW4], ts[32][16], tn[32][16];
     Lane4Const lc[32];
 };
 
@@ -176,11 +176,19 @@ extern "C" int emul_forward4_ex(const float* speech, const float* noise, int L, 
         tl.t0 = g * F4;
         int nz_shift = 0;
         if (group4_interior<float, true>(tl, nz_shift)) {
+#if defined(AVSE_EMUL_P1_UNIFIED)
+            for (int lane = 0; lane < 32; ++lane) {
+                p4_load_raw(tl, nz_shift, lane, w.rs[lane], w.rn[lane]);
+                p4_load_tail_raw(tl, nz_shift, lane, w.ts[lane], w.tn[lane]);
+                stage4_pass1_unified(tl, lane, w.rs[lane], w.rn[lane], w.ts[lane], w.tn[lane], w.lc[lane], h.window.data(), s_tw, w.frames);
+            }
+#else
             for (int lane = 0; lane < 32; ++lane) {
                 p4_load_raw(tl, nz_shift, lane, w.rs[lane], w.rn[lane]);
                 stage4_pass1_main(tl, lane, w.rs[lane], w.rn[lane], w.lc[lane], w.frames);     // consumes (rescales / rotates) rs, rn
             }
             for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, nz_shift, lane, h.window.data(), s_tw, w.frames);
+#endif
         } else {
             for (int lane = 0; lane < 32; ++lane) stage4_pass1_edge<float, true>(tl, lane, h.window.data(), s_tw, w.frames);
         }
