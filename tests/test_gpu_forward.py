@@ -415,3 +415,25 @@ def test_batch_beyond_65535_utterances(eng):
     assert float(sp.max() - sp.min()) <= 80.0 + 1e-4
     rec = eng.reconstruct(pcm[65530:65540], speech[65530:65540])
     assert torch.isfinite(rec).all()
+
+
+def test_noise_tiling_on_the_two_frame_kernel(eng):
+    """The 2-frame kernel (taken when a complex STFT output is requested) reads a periodically tiled noise through its edge
+    loader: same log-mels as the F4 kernel's TILED instantiation on the same batch."""
+    L, nvs = 16000, 5
+    S = np.stack([O.synth_speech(L, SR, 60 + i).astype(np.float32) for i in range(3)])
+    n_noise = [5000, 640, 16000]
+    Z = np.full((3, L), np.nan, np.float32)
+    for i, n in enumerate(n_noise):
+        Z[i, :n] = O.synth_noise(n, 60 + i).astype(np.float32)
+    nl = _dev(np.array(n_noise, np.int32))
+    f, keys = eng.snr_factor(_dev(S), _dev(Z), noise_lengths=nl)
+    r2 = eng.forward_raw(_dev(S), _dev(Z), factor=f, max_key=keys, stft=True, noise_lengths=nl)
+    eng.floor3_(r2["speech"], r2["noise"], r2["mixed"], keys)
+    ref = eng.preprocess_pairs(_dev(S), _dev(Z), nvs, noise_lengths=nl)
+    for k, b in zip(("mixed", "speech", "noise", "mixed_pcm"), ref):
+        # two kernels with different summation orders, each within 1e-3 dB of the oracle: <= 2e-3 dB between them
+        assert torch.isfinite(r2[k]).all() and torch.allclose(r2[k], b, rtol=0, atol=2e-3 if k != "mixed_pcm" else 1e-6), k
+    D = r2["stft"][0].cpu().numpy().T
+    want = O.stft(S[0].astype(np.float64), 640, 160)
+    assert np.max(np.abs(D - want)) <= 2e-5 * np.max(np.abs(want))

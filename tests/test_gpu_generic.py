@@ -135,3 +135,29 @@ def test_generic_int16_in_and_out(mod):
     f32 = eng.reconstruct(a[3], a[0] + 6.0)
     i16 = eng.reconstruct(a[3], a[0] + 6.0, out_dtype=torch.int16)
     assert torch.equal(i16, torch.clamp(f32, -32768.0, 32767.0).to(torch.int32).to(torch.int16))
+
+
+def test_generic_kernels_tile_short_noise_in_kernel(mod):
+    """dp:125-128 on the generic path (50 fps: n_fft 320): the noise row holds only the file's own samples (rest poisoned) and the
+    kernels address noise[i mod Ln]; result == the explicit host-side tiling."""
+    sr, fps, nvs = 16000, 50.0, 6
+    eng = mod.SpectralEngine(sr, fps, 200, device="cuda:0")
+    assert not eng.specialised
+    n_s, n_n = [19200, 15000, 19200], [4000, 333, 25000]
+    W = max(n_s)
+    S = np.zeros((3, W), np.float32)
+    Zp = np.full((3, W), np.nan, np.float32)
+    Zf = np.zeros((3, W), np.float32)
+    for i in range(3):
+        s, _ = _case(sr, n_s[i], 500 + i)
+        z = O.synth_noise(n_n[i], 500 + i).astype(np.float32)
+        S[i, :n_s[i]] = s
+        m = min(n_n[i], n_s[i])
+        Zp[i, :m] = z[:m]
+        Zf[i, :n_s[i]] = z[np.arange(n_s[i]) % n_n[i]] if n_n[i] < n_s[i] else z[:n_s[i]]
+    lens = _d(np.array(n_s, np.int32))
+    nl = _d(np.array([min(a, b) for a, b in zip(n_n, n_s)], np.int32))
+    got = eng.preprocess_pairs(_d(S), _d(Zp), nvs, lengths=lens, noise_lengths=nl)
+    ref = eng.preprocess_pairs(_d(S), _d(Zf), nvs, lengths=lens)
+    for a, b in zip(got, ref):
+        assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=0, atol=2e-5)
