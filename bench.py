@@ -473,6 +473,24 @@ def run_corpus(args, torch, dist, eng, eng_mod, device, rank, world):
         dist.destroy_process_group()
 
 
+def set_host_memory_policy(policy):
+    """policy "interleave": spread this process's future host allocations (the pinned staging buffers) round-robin over all NUMA
+    nodes (set_mempolicy(MPOL_INTERLEAVE)); "local": the default first-touch policy.  Returns the node count seen, or None."""
+    if policy != "interleave":
+        return None
+    try:
+        import ctypes
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2:
+            return len(nodes)
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))      # x86_64 set_mempolicy, MPOL_INTERLEAVE
+        return len(nodes) if rc == 0 else None
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     set_workload(args.seconds, args.snr_sweep)

@@ -25,6 +25,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     numa = bench.bind_to_gpu_numa_node(local_rank)
+    policy = os.environ.get("AVSE_HOST_MEM", "local")           # "interleave": pinned buffers spread over all NUMA nodes
+    nodes = bench.set_host_memory_policy(policy)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     B, L = 1000, 48000
@@ -38,6 +40,8 @@ def main():
 
     c = bench.copy_ceiling(torch, dist, world, device, h_in, h_out, 8, 10, barrier)
     c["host_cpus_bound_to_gpu_numa_node"] = numa
+    c["host_memory_policy"] = policy
+    c["numa_nodes"] = nodes
     c["aggregate_bidirectional_gbs"] = c["bidirectional_gbs"] * world
     c["e2e_ceiling_audio_s_per_s"] = world * B * 3.0 / (c["ms_per_step"] * 1e-3)
     if rank == 0:
