@@ -29,6 +29,9 @@
 #if !defined(AVSE_I8_POST_UNROLL)
 #define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
 #endif
+#if !defined(AVSE_I8_TW_IN_B)
+#define AVSE_I8_TW_IN_B 1        // inter-pass twiddles applied on pass B's column loads (lane-resident registers) instead of in pass A
+#endif
 #if !defined(AVSE_I8_PREFETCH_MEL)
 #define AVSE_I8_PREFETCH_MEL 0
 #endif
@@ -351,11 +354,21 @@ AVSE_HD void i8_passA_store(int lane, int r, float* frames, const cpx (&x)[40]) 
 // pass B.  Column k2' of FFT c: DFT-16 over n1' gives (y_A - i y_B) at n = 40 k1' + k2' (already / 640).
 // acc[J]: row J = samples 160 (t0 + 2c) + 40 J + lane, J = 0..19, while FFT c is being added.
 // ---------------------------------------------------------------------------------------
+// AVSE_I8_TW_IN_B: the inter-pass twiddle W_640^{n1' k2'} is applied HERE, on the column loads, instead of at the end of pass A:
+// with lane = k2' the 15 factors are exactly the lane's pass-1 twiddle registers (the table is symmetric in its two indices), so
+// pass A loses its 39 table loads + 39 complex multiplies per lane and pass B gains 15 multiplies per column -- same products,
+// same rounding, bit-identical results.
 AVSE_HD void i8_passB_add(int lane, int c, const Lane4Const& lc, const float* frames, float (&acc)[I8_ACC]) {
     const float* col = frames + c * FRAME4_F + 2 * lane;
     cpx x[16];
+#if AVSE_I8_TW_IN_B
+    x[0] = cload(col);
+#pragma unroll
+    for (int n1 = 1; n1 < 16; ++n1) x[n1] = cmul(cload(col + n1 * ROW_F), lc.tw[n1].x, lc.tw[n1].y);
+#else
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) x[n1] = cload(col + n1 * ROW_F);
+#endif
     dft16(x);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
@@ -394,12 +407,19 @@ AVSE_HD void i8_emit_main(int lane, int h0, int T_use, int out_len, bool write, 
 
 // Tail columns k2' = 32 + r: lane = (c, r) computes its column and parks the 20 row contributions in the staging buffer
 // st[c][j][r] (the dead coefficient buffer); window from the CTA's table.
-AVSE_HD void i8_passB_tail(int lane, const float* s_win, const float* frames, float* st) {
+AVSE_HD void i8_passB_tail(int lane, const float* s_win, const vec2* s_tw, const float* frames, float* st) {
     const int c = lane >> 3, r = lane & 7, k2 = 32 + r;
     const float* col = frames + c * FRAME4_F + 2 * k2;
     cpx x[16];
+#if AVSE_I8_TW_IN_B
+    x[0] = cload(col);
+#pragma unroll
+    for (int n1 = 1; n1 < 16; ++n1) { const vec2 t = s_tw[n1 * N2 + k2]; x[n1] = cmul(cload(col + n1 * ROW_F), t.x, t.y); }
+#else
+    (void)s_tw;
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) x[n1] = cload(col + n1 * ROW_F);
+#endif
     dft16(x);
     float cc[20];
 #pragma unroll

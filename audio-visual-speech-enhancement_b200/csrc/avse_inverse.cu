@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                     if (it < 2) p4_pass2_load(lane, r, frames, x);
                     else i8_passA_load(lane, r, frames, x);
                     dft40_inplace(x);
+#if !AVSE_I8_TW_IN_B
                     if (it >= 2) inv_passA_twiddle(lane, s_twT, x);
+#endif
                     __syncwarp();
                     if (it < 2) p4_pass2_store(lane, r, frames, x);
                     else i8_passA_store(lane, r, frames, x);
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                 if (have) i8_passB_add(lane, cc, lc, frames, acc);
                 i8_emit_main(lane, tl.t0 + 2 * cc, P.T_use, P.out_len, write, s_win, out, acc);
             }
-            if (have) i8_passB_tail(lane, s_win, frames, ybuf);
+            if (have) i8_passB_tail(lane, s_win, s_tw, frames, ybuf);
             __syncwarp();
             i8_tail_reduce_emit(lane, tl.t0, P.T_use, P.out_len, write, have, s_win, out, ybuf, side_in, side_out);
             __syncwarp();

@@ -202,7 +202,9 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                         if (it < 2) p4_pass2_load(lane, r, frames, w.x[lane]);
                         else i8_passA_load(lane, r, frames, w.x[lane]);
                         dft40_inplace(w.x[lane]);
+#if !AVSE_I8_TW_IN_B
                         if (it >= 2) inv_passA_twiddle(lane, twT.data(), w.x[lane]);
+#endif
                     }
                     for (int lane = 0; lane < 32; ++lane) {
                         if (it < 2) p4_pass2_store(lane, r, frames, w.x[lane]);
@@ -216,7 +218,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                     i8_emit_main(lane, tl.t0 + 2 * cc, T_use, out_len, write, s_win, out, w.acc[lane]);
                 }
             if (have)
-                for (int lane = 0; lane < 32; ++lane) i8_passB_tail(lane, s_win, frames, ybuf);
+                for (int lane = 0; lane < 32; ++lane) i8_passB_tail(lane, s_win, tw.data(), frames, ybuf);
             for (int lane = 0; lane < 32; ++lane)
                 i8_tail_reduce_emit(lane, tl.t0, T_use, out_len, write, have, s_win, out, ybuf, side_in, side_out);
         }
