@@ -49,7 +49,7 @@ EXPORTS = [
     "avse_snr_factor", "avse_forward", "avse_floor_inplace", "avse_floor_gather", "avse_reset_max", "avse_max_db",
     "avse_inverse", "avse_inverse_work_elems", "avse_floor_inplace3", "avse_gather_rows",
     "avse_create_ex", "avse_get_geometry", "avse_inverse_work_elems_ctx",
-    "avse_video_stats", "avse_video_normalize", "avse_mse",
+    "avse_video_stats", "avse_video_normalize", "avse_mse", "avse_magphase",
 ]
 
 
@@ -105,6 +105,8 @@ def load(build=True):
     lib.avse_video_normalize.restype = i32
     lib.avse_mse.argtypes = [vp, vp, vp, ll, vp, vp, vp]
     lib.avse_mse.restype = i32
+    lib.avse_magphase.argtypes = [vp, vp, ll, i32, i32, vp, vp, vp]
+    lib.avse_magphase.restype = i32
     lib.avse_gather_rows.argtypes = [vp, vp, vp, vp, ll, ll, vp, ll, vp, vp, vp, vp, vp]
     lib.avse_gather_rows.restype = i32
     _lib = lib

@@ -29,6 +29,9 @@
 #if !defined(AVSE_I8_POST_UNROLL)
 #define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
 #endif
+#if !defined(AVSE_I8_EDGE_OUT_OF_LINE)
+#define AVSE_I8_EDGE_OUT_OF_LINE 0   // 1: the cold reflect / zero-pad pass-1 stage as a real function call (one copy, outside the hot loop)
+#endif
 #if !defined(AVSE_I8_TW_IN_B)
 #define AVSE_I8_TW_IN_B 1        // inter-pass twiddles applied on pass B's column loads (lane-resident registers) instead of in pass A
 #endif
@@ -164,7 +167,12 @@ AVSE_HD void i8_pass1_tail(int lane, const float (&rt)[20], const float* s_win, 
 
 // pass 1, edge groups (first / last frames of an utterance, zero padding): every sample through the reflect + pad loader; frames
 // beyond the last one are clamped (their coefficients are zero).  Cold code, rolled over the five rounds.
-AVSE_HD void i8_pass1_edge(const InvTile& tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+#if AVSE_I8_EDGE_OUT_OF_LINE
+#define AVSE_I8_EDGE_Q AVSE_HD_COLD
+#else
+#define AVSE_I8_EDGE_Q AVSE_HD
+#endif
+AVSE_I8_EDGE_Q void i8_pass1_edge(const InvTile tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
 #pragma unroll 1
     for (int round = 0; round < 5; ++round) {
         const int c = round < 4 ? round : lane >> 3;

@@ -143,6 +143,23 @@ __global__ void __launch_bounds__(256) avse_mse_kernel(const float* __restrict__
 
 __global__ void avse_mse_finalize_kernel(const double* __restrict__ acc, double n, float* __restrict__ out) { *out = (float)(*acc / n); }
 
+// librosa.core.magphase (dp:80): mag = |D|, phase = D / |D| with 1 + 0j where D == 0.  Also transposes the kernel's frame-major
+// STFT [T][bins] into the reference's [bins][T] (dp:96 returns (freq, time) arrays).  One thread per output element.
+__global__ void __launch_bounds__(256) avse_magphase_kernel(const float2* __restrict__ stft, long long n_utt, int T, int bins,
+                                                            float* __restrict__ mag, float2* __restrict__ phase) {
+    const long long total = n_utt * T * bins;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const long long u = i / ((long long)T * bins);
+        const int r = (int)(i - u * (long long)T * bins);
+        const int k = r / T, t = r - k * T;                       // output index [u][k][t]
+        const float2 d = stft[(u * T + t) * bins + k];
+        const float m = hypotf(d.x, d.y);
+        if (mag) mag[i] = m;
+        if (phase) phase[i] = m > 0.0f ? make_float2(d.x / m, d.y / m) : make_float2(1.0f, 0.0f);
+    }
+}
+
 }  // namespace
 
 extern "C" int avse_video_stats(avse_ctx* ctx, const float* video, long long n_slices, int hw, int frames, double* scratch,
@@ -193,6 +210,20 @@ extern "C" int avse_mse(avse_ctx* ctx, const float* a, const float* b, long long
     avse_mse_kernel<<<(unsigned)bx, 256, 0, st>>>(a, b, n, scratch);
     CUDA_TRY(cudaGetLastError());
     avse_mse_finalize_kernel<<<1, 1, 0, st>>>(scratch, (double)n, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int avse_magphase(avse_ctx* ctx, const float* stft, long long n_utt, int n_frames, int n_bins, float* mag_out, float* phase_out,
+                             void* stream) {
+    if (!ctx || !stft || (!mag_out && !phase_out)) return avse_fail(AVSE_E_ARG, "avse_magphase: NULL argument");
+    if (n_utt <= 0 || n_frames <= 0 || n_bins <= 0) return avse_fail(AVSE_E_ARG, "avse_magphase: bad sizes");
+    const long long total = n_utt * n_frames * n_bins;
+    long long bx = (total + 255) / 256;
+    const long long cap = 16LL * ctx->num_sms;
+    if (bx > cap) bx = cap;
+    avse_magphase_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(stft), n_utt, n_frames, n_bins, mag_out,
+                                                                        reinterpret_cast<float2*>(phase_out));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

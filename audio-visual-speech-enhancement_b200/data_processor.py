@@ -77,10 +77,8 @@ def signal_to_spectrogram(audio_signal, n_fft, hop_length, mel=True, db=True):
     eng = _engine_for_fft(audio_signal.get_sample_rate(), n_fft, hop_length)
     x = _to_dev(_mono_f32(audio_signal), eng)
     db_mel, D = eng.spectrogram(x, stft=True)
-    D = D[0].transpose(0, 1)  # (321, T)
-    mag = D.abs()
-    zeros = mag == 0
-    phase = D / (mag + zeros) + zeros  # librosa.magphase: 1+0j where D == 0 (dp:80)
+    mag, phase = eng.magphase(D)          # librosa.magphase: 1+0j where D == 0 (dp:80); (321, T) orientation
+    mag, phase = mag[0], phase[0]
     if mel and db:
         magnitude = db_mel[0]
     else:

@@ -312,6 +312,18 @@ class SpectralEngine(object):
         out = res["speech"][:, :, :res["T"]]
         return (out, res["stft"]) if stft else out
 
+    @_on_device
+    def magphase(self, stft):
+        """librosa.core.magphase (dp:80) of a complex STFT [B, T, bins] (as `spectrogram(..., stft=True)` returns it):
+        (|D| float32 [B, bins, T], D/|D| complex64 [B, bins, T] with 1 + 0j where D == 0), in the reference's (freq, time) orientation."""
+        st = torch.view_as_real(stft.contiguous())
+        B, T, bins = stft.shape
+        mag = torch.empty((B, bins, T), dtype=torch.float32, device=self.device)
+        phase = torch.empty((B, bins, T), dtype=torch.complex64, device=self.device)
+        check(self._lib.avse_magphase(self._ctx, st.data_ptr(), B, T, bins, _ptr(mag), torch.view_as_real(phase).data_ptr(), self._stream()),
+              "avse_magphase")
+        return mag, phase
+
     def floor_spec_(self, spec, max_key, which, T):
         # pad columns (>= T) are untouched garbage; floor the whole padded rows (harmless)
         return self.floor_(spec, max_key, which)

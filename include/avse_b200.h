@@ -203,6 +203,12 @@ int avse_video_normalize(avse_ctx* ctx, float* video, long long n_slices, int hw
  * scratch: 1 double (device); out: 1 float (device). */
 int avse_mse(avse_ctx* ctx, const float* a, const float* b, long long n, double* scratch, float* out, void* stream);
 
+/* librosa.core.magphase (dp:80) on the complex STFT that avse_forward writes (stft_speech, frame-major [n_utt][n_frames][n_bins],
+ * re / im interleaved): mag_out [n_utt][n_bins][n_frames] = |D| and phase_out (same shape, complex64) = D / |D|, with 1 + 0j where
+ * D == 0 -- i.e. in the reference's (freq, time) orientation (dp:96).  Either output may be NULL. */
+int avse_magphase(avse_ctx* ctx, const float* stft, long long n_utt, int n_frames, int n_bins, float* mag_out, float* phase_out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,37 @@ def test_batch_driver_isolates_failures_per_sample(tmp_path):
     assert [s.video_file_path for s in samples] == ["v0", "v2"]
     for s in samples:
         assert np.isfinite(s.mixed_spectrograms).all() and s.mixed_spectrograms.shape == (5, 80, 20)
+
+
+@pytest.mark.gpu
+def test_mel_converter_facade_and_magphase():
+    """BASELINE.json's north_star names `MelConverter`; the reference snapshot has free functions instead.  The
+    façade routes to the same CUDA path; signal_to_spectrogram's phase is librosa.magphase (dp:80: 1 + 0j where D == 0), computed
+    by avse_magphase."""
+    dp = importlib.import_module(D.PKG + ".data_processor")
+    compat = importlib.import_module(D.PKG + ".mediaio_compat")
+    mc = dp.MelConverter(D.SR, D.FPS, 200)
+    s = O.synth_speech(16000, D.SR, 21).astype(np.float32)
+    s[6000:9000] = 0.0                                               # digital silence: exact zero frames -> phase 1 + 0j
+    n = O.synth_noise(16000, 21).astype(np.float32)
+    ref_db, ref_phase = O.signal_to_spectrogram(O.AudioSignal(s.astype(np.float64), D.SR), 640, 160)
+    got_db = mc.signal_to_mel_spectrogram(compat.AudioSignal(s, D.SR))
+    assert got_db.shape == ref_db.shape == (80, 101) and np.max(np.abs(got_db - ref_db)) <= TOL_DB
+    mag, phase = dp.signal_to_spectrogram(compat.AudioSignal(s, D.SR), 640, 160)
+    assert phase.shape == ref_phase.shape == (321, 101) and phase.dtype == np.complex64
+    Dref = O.stft(s.astype(np.float64), 640, 160)
+    zero = np.abs(Dref) == 0
+    assert zero.any() and np.all(phase[zero] == 1.0 + 0.0j)
+    strong = np.abs(Dref) > 1e-3 * np.abs(Dref).max()
+    assert np.max(np.abs(phase[strong] - ref_phase[strong])) <= 2e-3
+    assert np.max(np.abs(np.abs(phase[~zero]) - 1.0)) <= 1e-5
+    slices = mc.signal_to_slices(compat.AudioSignal(s, D.SR), 5)
+    want = O.preprocess_audio_signal(O.AudioSignal(s.astype(np.float64), D.SR), 200, 5, D.FPS)
+    assert slices.shape == (5, 80, 20) and np.max(np.abs(slices - want)) <= TOL_DB
+    mixed, speech, noise, sig = mc.mix_pair(compat.AudioSignal(s, D.SR), compat.AudioSignal(n, D.SR), 5, snr_db=5)
+    r = O.preprocess_audio_pair_signals(O.AudioSignal(s.astype(np.float64), D.SR), O.AudioSignal(n.astype(np.float64), D.SR), 200, 5, D.FPS, snr_db=5)
+    for a, b in zip((mixed, speech, noise), r[:3]):
+        assert np.max(np.abs(a - b)) <= TOL_DB
+    rec = mc.reconstruct_signal_from_mel_spectrogram(sig, speech)
+    want = O.reconstruct_speech_signal(O.AudioSignal(sig.get_data().astype(np.float64), D.SR), speech.astype(np.float64), D.FPS).get_data()
+    assert np.max(np.abs(rec.get_data() - want)) <= TOL_PCM * np.max(np.abs(sig.get_data()))
