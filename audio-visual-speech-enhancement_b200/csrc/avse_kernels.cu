@@ -28,7 +28,7 @@ int avse_cuda_fail(cudaError_t e, const char* where) {
 }
 
 extern "C" const char* avse_last_error(void) { return g_err.c_str(); }
-extern "C" const char* avse_version(void) { return "avse_b200 0.3 (sm_100a)"; }
+extern "C" const char* avse_version(void) { return "avse_b200 0.4 (sm_100a)"; }
 
 extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device, avse_ctx** out) {
     if (out == nullptr) return avse_fail(AVSE_E_ARG, "avse_create: out is NULL");
