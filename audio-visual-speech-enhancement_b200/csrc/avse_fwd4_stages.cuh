@@ -22,6 +22,9 @@
 #include "avse_dft.cuh"
 #include "avse_fwd_stages.cuh"
 
+#if !defined(AVSE_DB_FAST_MINMAX)
+#define AVSE_DB_FAST_MINMAX 0     // 1: min / max of a full group's four frames without the per-frame validity selects
+#endif
 #if !defined(AVSE_SCAN4_UNROLL)
 #define AVSE_SCAN4_UNROLL 8
 #endif
@@ -453,11 +456,20 @@ AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const 
         float d[F4];
         float lm = neg_inf(), ln = -neg_inf();
 #pragma unroll
-        for (int f = 0; f < F4; ++f) {
-            d[f] = amp_to_db(mel[sig][f] * scale);
-            const bool v = f < nvalid;
-            lm = v ? fmaxf(lm, d[f]) : lm;     // branch-free: selects, no divergent code in the hot dB loop
-            ln = v ? fminf(ln, d[f]) : ln;
+        for (int f = 0; f < F4; ++f) d[f] = amp_to_db(mel[sig][f] * scale);
+#if AVSE_DB_FAST_MINMAX
+        if (nvalid == F4) {                    // warp-uniform: every group but the utterance's last one
+            lm = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+            ln = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        } else
+#endif
+        {
+#pragma unroll
+            for (int f = 0; f < F4; ++f) {
+                const bool v = f < nvalid;
+                lm = v ? fmaxf(lm, d[f]) : lm;     // branch-free: selects, no divergent code in the hot dB loop
+                ln = v ? fminf(ln, d[f]) : ln;
+            }
         }
         mx[sig] = fmaxf(lm, mx[sig]);
         float* dst = out.dst[sig];

@@ -562,6 +562,7 @@ class HostPipeline(object):
                 "s": torch.empty((self.chunk, self.L), dtype=sample_dtype, device=dev),
                 "n": torch.empty((self.chunk, self.L), dtype=sample_dtype, device=dev),
                 "snr": torch.zeros((self.chunk,), dtype=torch.float32, device=dev),
+                "nlen": torch.zeros((self.chunk,), dtype=torch.int32, device=dev),
                 "out": {},
             })
         self._next = 0
@@ -581,10 +582,11 @@ class HostPipeline(object):
         for st in self.streams:
             st.synchronize()
 
-    def submit(self, h_speech, h_noise, h_mixed, h_speech_out, h_noise_out, h_pcm, snr_db=None):
-        """Queue one batch.  h_speech / h_noise: pinned [B, L] of the pipeline's sample dtype (noise fitted to the speech length, dp:125-128);
-        h_mixed / h_speech_out / h_noise_out: pinned [B, n_slices, 80, 20]; h_pcm: pinned [B, L]; snr_db: optional
-        pinned [B] float32 (None: 0 dB, dp:130).  Returns the number of chunks queued."""
+    def submit(self, h_speech, h_noise, h_mixed, h_speech_out, h_noise_out, h_pcm, snr_db=None, noise_lengths=None):
+        """Queue one batch.  h_speech / h_noise: pinned [B, L] of the pipeline's sample dtype; h_mixed / h_speech_out /
+        h_noise_out: pinned [B, n_slices, 80, 20]; h_pcm: pinned [B, L]; snr_db: optional pinned [B] float32 (None: 0 dB,
+        dp:130); noise_lengths: optional pinned [B] int32, the noise files' own lengths -- shorter noises are tiled inside the
+        kernels (dp:125-128); without it the noise rows must already cover L.  Returns the number of chunks queued."""
         B = h_speech.shape[0]
         eng = self.eng
         n_chunks = 0
@@ -602,9 +604,13 @@ class HostPipeline(object):
                 if snr_db is not None:
                     snr = slot["snr"][:m]
                     snr.copy_(snr_db[lo:hi], non_blocking=True)
+                nlen = None
+                if noise_lengths is not None:
+                    nlen = slot["nlen"][:m]
+                    nlen.copy_(noise_lengths[lo:hi], non_blocking=True)
                 out = slot["out"] if m == self.chunk else {}
-                factor, keys = eng.snr_factor(d_s, d_n, snr_db=snr, max_key=out.get("max_key"))
-                r = eng.forward_raw(d_s, d_n, L=self.L, factor=factor, n_slices=self.n_slices, max_key=keys, out=out)
+                factor, keys = eng.snr_factor(d_s, d_n, snr_db=snr, max_key=out.get("max_key"), noise_lengths=nlen)
+                r = eng.forward_raw(d_s, d_n, L=self.L, factor=factor, n_slices=self.n_slices, max_key=keys, out=out, noise_lengths=nlen)
                 eng.floor3_(r["speech"], r["noise"], r["mixed"], keys)
                 h_mixed[lo:hi].copy_(r["mixed"], non_blocking=True)
                 h_speech_out[lo:hi].copy_(r["speech"], non_blocking=True)

@@ -92,6 +92,30 @@ def test_host_pipeline_int16(eng, mod):
         assert torch.equal(a, b.cpu())
 
 
+def test_host_pipeline_tiles_short_noise_in_kernel(eng, mod):
+    """HostPipeline.submit(noise_lengths=...): noise files shorter than the utterance travel as they are (the rest of the pinned
+    row is never read) and are tiled inside the kernels (dp:125-128)."""
+    B, L = 5, 16000
+    rng = np.random.RandomState(2)
+    hs = torch.from_numpy((rng.randn(B, L) * 0.1).astype(np.float32)).pin_memory()
+    n_noise = [16000, 5000, 333, 9999, 640]
+    hn = torch.full((B, L), float("nan")).pin_memory()
+    full = torch.zeros((B, L))
+    for i, n in enumerate(n_noise):
+        z = torch.from_numpy((rng.randn(n) * 0.03).astype(np.float32))
+        hn[i, :n] = z
+        full[i] = z[torch.arange(L) % n]
+    nl = torch.tensor(n_noise, dtype=torch.int32).pin_memory()
+    pipe = mod.HostPipeline(eng, L, 5, chunk=2, n_streams=2)
+    outs = [torch.zeros((B, 5, 80, 20)).pin_memory() for _ in range(3)] + [torch.zeros((B, L)).pin_memory()]
+    pipe.begin_after(torch.cuda.current_stream())
+    pipe.submit(hs, hn, *outs, noise_lengths=nl)
+    pipe.synchronize()
+    ref = eng.preprocess_pairs(hs.cuda(), full.cuda(), 5)
+    for a, b in zip(outs, ref):
+        assert torch.isfinite(a).all() and torch.allclose(a, b.cpu(), rtol=0, atol=2e-5)
+
+
 def test_int16_single_signal_is_converted_by_the_host_layer(eng):
     x = (np.random.RandomState(1).randn(20000) * 2000).astype(np.int16)
     a = eng.preprocess_signals(torch.from_numpy(x).cuda(), 5)
