@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
 
     const float* s_win = smem + I8_SM_WIN;
     const vec2* s_tw = reinterpret_cast<const vec2*>(smem + I8_SM_TW);
+#if !AVSE_I8_TW_IN_B
     const vec2* s_twT = reinterpret_cast<const vec2*>(smem + I8_SM_TWT);
+#endif
     const ivec4* s_col = reinterpret_cast<const ivec4*>(smem + I8_SM_COL);
     const float* s_spk = smem + I8_SM_SPK;
     const avse_inverse_args& A = P.a;

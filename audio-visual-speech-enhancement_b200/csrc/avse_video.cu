@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(256) avse_video_normalize_kernel(float* __rest
             x.x = v[0]; x.y = v[1]; x.z = v[2]; x.w = v[3];
             v4[j] = x;
         }
-        return;
-    }
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-        const int p = (int)((i / frames) % hw);
-        video[i] = (video[i] - mean[p]) / stdv[p];
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+            const int p = (int)((i / frames) % hw);
+            video[i] = (video[i] - mean[p]) / stdv[p];
+        }
     }
 }
 

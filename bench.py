@@ -578,7 +578,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "forward_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "avse_forward4_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "avse_forward4_kernel<float, false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
                 "note": "fused FFT kernel bound by FP32 issue + the shared-memory data pipe, not by HBM; see DESIGN.md section 5 and profiles/"}
@@ -645,7 +645,7 @@ def main():
         inv_bytes = B * t_use * INV_BYTES_PER_FRAME
         line["inverse"] = {"workload": "BASELINE configs[3]: %d enhanced mel-spectrograms (%d,80,20) + mixture PCM -> waveforms per GPU" % (B, N_VIDEO_SLICES),
                            "value": world * B * UTT_SECONDS / (inv_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": inv_ms,
-                           "roofline": {"bound": "hbm", "kernel": "avse_inverse_kernel", "achieved": inv_bytes / (inv_ms * 1e-3) / 1e9,
+                           "roofline": {"bound": "hbm", "kernel": "avse_inverse8_kernel<false, float>", "achieved": inv_bytes / (inv_ms * 1e-3) / 1e9,
                                         "peak": peak, "unit": "GB/s", "frac": inv_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
 
     # ---------------- SURVEY 8(f) neighbours of the path: HBM-bound kernels, each against the copy roofline ----------------
