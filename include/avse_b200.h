@@ -153,7 +153,9 @@ typedef struct avse_inverse_args {
     int L;                   /* mixture length; T = 1 + L/160 frames; frames used = min(mel frames, T) (dp:68) */
     void* out_pcm;           /* [B][out_stride] reconstructed PCM, 160 * (frames_used - 1) samples each (librosa.istft, dp:114) */
     long long out_stride;
-    float* work;             /* scratch [B][work_stride], work_stride >= avse_inverse_work_elems(frames_used) */
+    float* work;             /* scratch [B][work_stride], work_stride >= avse_inverse_work_elems(frames_used).  Only the generic-geometry
+                                kernels (avse_create_ex contexts) and the 4-frame kernel kept for A/B runs (AVSE_INV4=1) use it; the
+                                specialised I8 kernel keeps the coefficients on chip and accepts NULL */
     long long work_stride;
     const float* phase;      /* optional complex64 [B][phase_frames][321] (re, im): explicit phase (dp:99 signature); when set,
                                 mixed_pcm / L are ignored and frames used = min(mel frames, phase_frames) */
@@ -165,7 +167,7 @@ typedef struct avse_inverse_args {
 
 /* reconstruct_speech_signal / reconstruct_signal_from_spectrogram (dp:60-74, dp:99-116) for a batch:
  * db_to_amplitude -> pinv(mel fb) as a tridiagonal solve + 2-tap F^T -> x phase of the mixture's STFT (recomputed
- * on the fly) -> irfft + Hann + overlap-add / window sum-square, centre trim.  Two kernels on `stream`. */
+ * on the fly) -> irfft + Hann + overlap-add / window sum-square, centre trim.  One kernel on `stream` (two for generic geometries). */
 int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* stream);
 
 /* Scratch floats per utterance needed by avse_inverse for `n_frames_use` reconstructed frames (specialised geometry). */
