@@ -8,6 +8,7 @@ device memory and the current stream.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -142,6 +143,11 @@ class SpectralEngine(object):
         if x.stride(-1) != 1:
             x = x.contiguous()
         return x
+
+    def _needs_inverse_scratch(self):
+        """The specialised I8 inverse kernel keeps the pinv coefficients on chip; only generic-geometry contexts and the
+        round-1 4-frame kernel (AVSE_INV4=1, A/B runs) need the `work` scratch of avse_inverse_work_elems."""
+        return (not self.specialised) or os.environ.get("AVSE_INV4") == "1"
 
     def n_frames(self, L):
         """librosa.stft(center=True) frame count: 1 + (L + 2 (n_fft // 2) - n_fft) // hop (== 1 + L // hop for even n_fft)."""
@@ -357,9 +363,12 @@ class SpectralEngine(object):
             out = torch.empty((B, out_len), dtype=out_dtype, device=self.device)
         assert out.dtype in (torch.float32, torch.int16)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
-        if work is None or work.numel() < B * per.value:
-            work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        if self._needs_inverse_scratch():
+            check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
+            if work is None or work.numel() < B * per.value:
+                work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        else:
+            work = None
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SLICES, n, 0, 0
         a.mel_stride = _rs(mel)
@@ -382,8 +391,10 @@ class SpectralEngine(object):
         T_use = min(T_mel, T_ph)
         out = torch.empty((B, self.hop * (T_use - 1)), dtype=torch.float32, device=self.device)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
-        work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        work = None
+        if self._needs_inverse_scratch():
+            check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
+            work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, T_mel, T_mel
         a.mel_stride = _rs(mel)
@@ -407,8 +418,10 @@ class SpectralEngine(object):
         T_use = min(mel.shape[2], self.n_frames(L))
         out = torch.empty((B, self.hop * (T_use - 1)), dtype=torch.float32, device=self.device)
         per = ctypes.c_longlong(0)
-        check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
-        work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
+        work = None
+        if self._needs_inverse_scratch():
+            check(self._lib.avse_inverse_work_elems_ctx(self._ctx, T_use, ctypes.byref(per)), "avse_inverse_work_elems_ctx")
+            work = torch.empty((B, per.value), dtype=torch.float32, device=self.device)
         a = InverseArgs()
         a.mel_db, a.layout, a.n_slices, a.n_frames, a.ld_t = _ptr(mel), LAYOUT_SPEC, 0, mel.shape[2], mel.shape[2]
         a.mel_stride = _rs(mel)
