@@ -83,3 +83,23 @@ def test_explicit_phase_and_data_processor_signatures(eng, dp):
     got = dp.reconstruct_signal_from_spectrogram(mag, phase, SR, 640, 160).get_data()
     assert got.shape == want.shape
     assert np.max(np.abs(got - want)) <= TOL_PCM * np.max(np.abs(pcm))
+
+
+def test_inverse_is_independent_of_the_work_partition(eng):
+    """The I8 kernel cuts the launch's (utterance, group) sequence into one contiguous range per warp; a range that starts inside
+    an utterance rebuilds the overlap-add carry by recomputing the previous group.  Results must therefore be bit-identical
+    whatever the batch size (i.e. wherever the range boundaries fall) -- also for int16 output and ragged mixture lengths."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, L, n = 37, 48000, 15
+    pcm = torch.randn((B, L), generator=g, device="cuda") * 0.1
+    mel = torch.rand((B, n, 80, 20), generator=g, device="cuda") * 60.0 - 70.0
+    lens = torch.randint(20000, L + 1, (B,), generator=g, device="cuda", dtype=torch.int32)
+    lens[0] = L
+    whole = eng.reconstruct(pcm, mel, lengths=lens)
+    whole16 = eng.reconstruct(pcm * 30000.0, mel + 90.0, lengths=lens, out_dtype=torch.int16)
+    for lo, hi in ((0, 1), (5, 9), (20, 37), (36, 37)):
+        part = eng.reconstruct(pcm[lo:hi].contiguous(), mel[lo:hi].contiguous(), lengths=lens[lo:hi].contiguous())
+        assert torch.equal(part, whole[lo:hi]), (lo, hi)
+        part16 = eng.reconstruct((pcm[lo:hi] * 30000.0).contiguous(), (mel[lo:hi] + 90.0).contiguous(), lengths=lens[lo:hi].contiguous(),
+                                 out_dtype=torch.int16)
+        assert torch.equal(part16, whole16[lo:hi]), (lo, hi)
