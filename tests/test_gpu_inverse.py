@@ -103,3 +103,19 @@ def test_inverse_is_independent_of_the_work_partition(eng):
         part16 = eng.reconstruct((pcm[lo:hi] * 30000.0).contiguous(), (mel[lo:hi] + 90.0).contiguous(), lengths=lens[lo:hi].contiguous(),
                                  out_dtype=torch.int16)
         assert torch.equal(part16, whole16[lo:hi]), (lo, hi)
+
+
+@pytest.mark.parametrize("jump_db,tol", [(60.0, 1e-4), (70.0, 1e-4), (80.0, 2e-4)])
+def test_inverse_level_jump_between_packed_frames(eng, jump_db, tol):
+    """The GPU counterpart of tests/test_emul_inverse.py::test_inverse_level_jump_between_packed_frames: a hard digital step of
+    60 / 70 / 80 dB on a frame boundary between two mixture frames that share one packed FFT (see there for the float32 limit)."""
+    L = 16000
+    step = 160 * 41 + 320
+    for seed in (3, 4):
+        rng = np.random.RandomState(seed)
+        pcm = (0.3 * rng.randn(L)).astype(np.float32)
+        pcm[step:] *= np.float32(10.0 ** (-jump_db / 20.0))
+        mel = (rng.rand(5, 80, 20) * 30.0 - 50.0).astype(np.float32)
+        want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+        got = eng.reconstruct(torch.from_numpy(pcm[None]).cuda(), torch.from_numpy(mel[None]).cuda())[0].cpu().numpy()
+        assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want)), (jump_db, seed)
