@@ -26,6 +26,9 @@
 #include "avse_inv_stages.cuh"
 #include "avse_tables.h"
 
+#if !defined(AVSE_I8_POST_WALK)
+#define AVSE_I8_POST_WALK 1      // post stage: the coefficient pair of a lane's current band walks in registers (mask-driven advance)
+#endif
 #if !defined(AVSE_I8_POST_UNROLL)
 #define AVSE_I8_POST_UNROLL 2    // bins per unrolled block of the post stage (independent load -> rsqrt -> store chains in flight)
 #endif
@@ -283,14 +286,10 @@ AVSE_HD void i8_coef_finish(int lane, const float* s_spk, const float (&d)[SPIKE
 // weights carry the irfft's 1/640.  s_col: [SCAN4_BINS] (b0, b1, w0, w1) bit patterns; ybuf: [80][8] coefficients of the group.
 // ---------------------------------------------------------------------------------------
 template <bool EXT>
-AVSE_HD void i8_post_bin(int i, int p, const ivec4* tab, const float* yb, float* za, float* zc, bool liveA, bool liveB, const vec2* phA,
-                         const vec2* phB) {
+AVSE_HD void i8_post_core(int i, int p, cpx lin, float* za, float* zc, bool liveA, bool liveB, const vec2* phA, const vec2* phB) {
     const int k = CHUNK4 * p + i;
     const bool tail = k > NBINS - 1;            // chunk 7 ends with slots that mirror other bins: compute harmlessly, do not store
     const bool nyq = k == NBINS - 1;            // lin = 0 at the Nyquist bin (the filterbank's last column is empty)
-    const ivec4 t = tab[i];
-    const cpx y0 = cload(yb + I8_YS * t.x), y1 = cload(yb + I8_YS * t.y);
-    const cpx lin = cfma_s(y1, bits_to_float(t.w), cmul_s(y0, bits_to_float(t.z)));   // (lin_A, lin_B) / 640
     float yar, yai, ybr, ybi;
     if (EXT) {
         const vec2 qa = (phA != nullptr && !tail) ? phA[k] : vec2{1.0f, 0.0f};
@@ -315,6 +314,50 @@ AVSE_HD void i8_post_bin(int i, int p, const ivec4* tab, const float* yb, float*
     }
 }
 
+#if AVSE_I8_POST_WALK
+// Walk form: s_col = [SCAN4_BINS] (w0, w1) / 640, followed by [8] (mask lo, mask hi, first band, -) per chunk.  Bit i of the
+// chunk's mask: the pair (y[b], y[b + 1]) moves up one band before bin i.  The pair lives in registers; an advance is one
+// predicated 8-byte load instead of two gathers and a 16-byte table entry per bin.
+template <bool EXT>
+AVSE_HD void i8_stage_post(int lane, const ivec4* s_col, const float* ybuf, float* frames, const vec2* phA, const vec2* phB) {
+    const int c = lane >> 3, p = lane & 7;
+    float* fr = frames + c * FRAME4_F;
+    float* za = fr + 2 * CHUNK4 * p;
+    float* zc = fr + 2 * (NFFT - CHUNK4 * p);
+    const vec2* tab = reinterpret_cast<const vec2*>(s_col) + CHUNK4 * p;
+    const ivec4 ch = *(reinterpret_cast<const ivec4*>(reinterpret_cast<const vec2*>(s_col) + SCAN4_BINS) + p);
+    unsigned mlo = (unsigned)ch.x, mhi = (unsigned)ch.y;
+    const float* yb = ybuf + 2 * c + I8_YS * ch.z;            // (c_A, c_B) of band b at ybuf[I8_YS b + 2 c]
+    cpx y0 = cload(yb), y1 = cload(yb + I8_YS);
+    const bool liveA = EXT || fr[I8_FLAG_F] != 0.0f;
+    const bool liveB = EXT || fr[I8_FLAG_F + 1] != 0.0f;
+    static_assert(CHUNK4 == 41 && (40 % AVSE_I8_POST_UNROLL) == 0 && AVSE_I8_POST_UNROLL <= 8, "blocks of AVSE_I8_POST_UNROLL bins + 1");
+#pragma unroll 1
+    for (int ib = 0; ib < 40; ib += AVSE_I8_POST_UNROLL) {
+#pragma unroll
+        for (int j = 0; j < AVSE_I8_POST_UNROLL; ++j) {
+            if ((mlo >> j) & 1u) { yb += I8_YS; y0 = y1; y1 = cload(yb + I8_YS); }
+            const vec2 w = tab[ib + j];
+            const cpx lin = cfma_s(y1, w.y, cmul_s(y0, w.x));         // (lin_A, lin_B) / 640
+            i8_post_core<EXT>(ib + j, p, lin, za, zc, liveA, liveB, phA, phB);
+        }
+        mlo = (mlo >> AVSE_I8_POST_UNROLL) | (mhi << (32 - AVSE_I8_POST_UNROLL));
+        mhi >>= AVSE_I8_POST_UNROLL;
+    }
+    if (mlo & 1u) { yb += I8_YS; y0 = y1; y1 = cload(yb + I8_YS); }
+    const vec2 w = tab[40];
+    i8_post_core<EXT>(40, p, cfma_s(y1, w.y, cmul_s(y0, w.x)), za, zc, liveA, liveB, phA, phB);
+}
+#else
+template <bool EXT>
+AVSE_HD void i8_post_bin(int i, int p, const ivec4* tab, const float* yb, float* za, float* zc, bool liveA, bool liveB, const vec2* phA,
+                         const vec2* phB) {
+    const ivec4 t = tab[i];
+    const cpx y0 = cload(yb + I8_YS * t.x), y1 = cload(yb + I8_YS * t.y);
+    const cpx lin = cfma_s(y1, bits_to_float(t.w), cmul_s(y0, bits_to_float(t.z)));   // (lin_A, lin_B) / 640
+    i8_post_core<EXT>(i, p, lin, za, zc, liveA, liveB, phA, phB);
+}
+
 template <bool EXT>
 AVSE_HD void i8_stage_post(int lane, const ivec4* s_col, const float* ybuf, float* frames, const vec2* phA, const vec2* phB) {
     const int c = lane >> 3, p = lane & 7;
@@ -333,6 +376,7 @@ AVSE_HD void i8_stage_post(int lane, const ivec4* s_col, const float* ybuf, floa
     }
     i8_post_bin<EXT>(40, p, tab, yb, za, zc, liveA, liveB, phA, phB);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // pass A, round r: lane = (c = 2 r + lane / 16, n1' = lane % 16): gather V[n1' + 16 n2'], (DFT-40 by the caller), twiddle

@@ -81,6 +81,8 @@ struct InvParams {
     const int* col_band;
     const float* col_w;
     const float* spike;
+    const int* post_b;        // I8 post stage, walk form (avse_tables.h)
+    const float* post_w;
     int T;            // mixture STFT frames
     int T_use;        // frames reconstructed
     int T_pad;        // coefficient row length (multiple of 4, >= 4 (G + 1))
@@ -292,6 +294,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
         smem[I8_SM_TW + 2 * i] = re; smem[I8_SM_TW + 2 * i + 1] = im;
         smem[I8_SM_TWT + 2 * (n2 * N1 + k1)] = re; smem[I8_SM_TWT + 2 * (n2 * N1 + k1) + 1] = im;   // symmetric in (n2, k1)
     }
+#if AVSE_I8_POST_WALK
+    for (int i = threadIdx.x; i < SCAN4_BINS; i += I8_THREADS) {       // (w0, w1) / 640 per bin, then per chunk (mask lo, mask hi, first band)
+        smem[I8_SM_COL + 2 * i] = P.post_w[2 * i] * INV_SCALE; smem[I8_SM_COL + 2 * i + 1] = P.post_w[2 * i + 1] * INV_SCALE;
+    }
+    if (threadIdx.x < 8) {
+        const int p = threadIdx.x;
+        unsigned lo = 0u, hi = 0u;
+        for (int i = 1; i < CHUNK4; ++i)
+            if (P.post_b[CHUNK4 * p + i] != P.post_b[CHUNK4 * p + i - 1]) { if (i < 32) lo |= 1u << i; else hi |= 1u << (i - 32); }
+        unsigned* e = reinterpret_cast<unsigned*>(smem + I8_SM_COL + 2 * SCAN4_BINS) + 4 * p;
+        e[0] = lo; e[1] = hi; e[2] = (unsigned)P.post_b[CHUNK4 * p]; e[3] = 0u;
+    }
+#else
     for (int i = threadIdx.x; i < SCAN4_BINS; i += I8_THREADS) {
         int* e = reinterpret_cast<int*>(smem + I8_SM_COL) + 4 * i;
         if (i < NBINS) {
@@ -299,6 +314,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             e[2] = __float_as_int(P.col_w[2 * i] * INV_SCALE); e[3] = __float_as_int(P.col_w[2 * i + 1] * INV_SCALE);   // irfft's 1/640 folded in
         } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
     }
+#endif
     for (int i = threadIdx.x; i < SPIKE_P * SPIKE_ROW; i += I8_THREADS) smem[I8_SM_SPK + i] = P.spike[i];
     float* frames = smem + warp * I8_WARP_SMEM_F;
     float* ybuf = frames + I8_NC * FRAME4_F;
@@ -504,6 +520,8 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     P.col_band = ctx->d_col_band;
     P.col_w = ctx->d_col_w;
     P.spike = ctx->d_spike;
+    P.post_b = ctx->d_post_b;
+    P.post_w = ctx->d_post_w;
 
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));

@@ -65,6 +65,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
         {h.scan4_w.data(), h.scan4_w.size() * 4, 0},   {h.scan4_mask.data(), h.scan4_mask.size() * 4, 0},
         {h.scan4_loc.data(), h.scan4_loc.size() * 4, 0},
         {h.spike.data(), h.spike.size() * 4, 0},
+        {h.post_b.data(), h.post_b.size() * 4, 0},     {h.post_w.data(), h.post_w.size() * 4, 0},
     };
     size_t total = 0;
     for (auto& s : secs) { s.off = total; total += (s.bytes + 255) / 256 * 256; }
@@ -93,6 +94,8 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->fwd.scan4_mask = (const unsigned*)(b + secs[15].off);
     c->fwd.scan4_loc = (const int*)(b + secs[16].off);
     c->d_spike = (const float*)(b + secs[17].off);
+    c->d_post_b = (const int*)(b + secs[18].off);
+    c->d_post_w = (const float*)(b + secs[19].off);
     c->f4_tables = h.scan4_ok;   // fast F4 kernel (4 frames per warp)
     c->std_tables = h.scan_ok;   // fused post+mel scan kernel; otherwise the generic band-gather kernel
     cudaSetDevice(prev);

@@ -105,6 +105,38 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
         }
     }
 
+    {   // walk form of the columns (see avse_tables.h)
+        constexpr int PB = 328;
+        t.post_b.assign(PB, 0);
+        t.post_w.assign((size_t)PB * 2, 0.0f);
+        t.post_ok = NMEL >= 2;
+        int prev = -1;                                     // -1: the walk has not been pinned by a tap yet
+        for (int k = 0; k < NBINS && t.post_ok; ++k) {
+            const int b0 = t.col_band[2 * k], b1 = t.col_band[2 * k + 1];
+            const float w0 = t.col_w[2 * k], w1 = t.col_w[2 * k + 1];
+            int b = prev < 0 ? 0 : prev;
+            float wa = 0.0f, wb = 0.0f;
+            if (w0 != 0.0f && w1 != 0.0f) {
+                if (b1 != b0 + 1) { t.post_ok = false; break; }
+                b = b0; wa = w0; wb = w1;
+            } else if (w0 != 0.0f) {                       // one tap (band b0): it can be the pair's first or second member
+                const bool first_ok = b0 <= NMEL - 2, second_ok = b0 >= 1;
+                if (first_ok && (prev < 0 || b0 == prev || b0 == prev + 1) && !(second_ok && b0 - 1 == prev)) { b = b0; wa = w0; }
+                else if (second_ok) { b = b0 - 1; wb = w0; }
+                else { b = b0; wa = w0; }
+            }
+            if (prev >= 0 && b != prev && b != prev + 1) { t.post_ok = false; break; }
+            t.post_b[k] = b; t.post_w[2 * k] = wa; t.post_w[2 * k + 1] = wb;
+            if (w0 != 0.0f || prev >= 0) prev = b;
+        }
+        if (prev < 0) prev = 0;
+        for (int k = NBINS; k < PB; ++k) t.post_b[k] = prev;
+        for (int k = NBINS - 1; k > 0; --k)                // bins before the first tap sit on the first tap's pair
+            if (t.post_w[2 * (k - 1)] == 0.0f && t.post_w[2 * (k - 1) + 1] == 0.0f && t.post_b[k - 1] > t.post_b[k]) t.post_b[k - 1] = t.post_b[k];
+        for (int k = 1; k < PB && t.post_ok; ++k)
+            if (t.post_b[k] < t.post_b[k - 1] || t.post_b[k] > t.post_b[k - 1] + 1 || t.post_b[k] > NMEL - 2) t.post_ok = false;
+    }
+
     // G = F F^T must be tridiagonal; Thomas factors in float64
     std::vector<double> diag(NMEL), sub(NMEL, 0.0), sup(NMEL, 0.0);
     for (int a = 0; a < NMEL; ++a)

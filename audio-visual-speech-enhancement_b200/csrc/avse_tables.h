@@ -50,6 +50,12 @@ struct HostTables {
     std::vector<float> spike;         // [4][SPIKE_ROW]: lw[20] lipiv[20] lsup[20] wv[20] vv[20] rb[8] rt[8]
     std::vector<int> col_band;        // [321][2] band index of the (<=2) non-zeros in column k (or 0)
     std::vector<float> col_w;         // [321][2] their weights (0 when absent)
+    // the same columns as a walk (I8 post stage): bin k reads the coefficient pair (y[post_b[k]], y[post_b[k] + 1]) with weights
+    // post_w[k]; post_b is non-decreasing in steps of <= 1 and stays in [0, 78], so a lane walking a chunk of bins keeps the pair
+    // in registers and advances it on the bits of a mask.  post_ok == false: the filterbank does not allow it (I4 kernel serves).
+    bool post_ok = false;
+    std::vector<int> post_b;          // [328]
+    std::vector<float> post_w;        // [328][2]
 
     std::string error;                // non-empty when the configuration is unsupported
 };

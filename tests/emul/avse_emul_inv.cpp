@@ -146,6 +146,19 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
             twT[n2 * N1 + k1] = v;
         }
     std::vector<ivec4> col(SCAN4_BINS);
+#if AVSE_I8_POST_WALK
+    {   // the kernel's shared-memory image: [SCAN4_BINS] (w0, w1) / 640, then [8] (mask lo, mask hi, first band, -)
+        float* f = reinterpret_cast<float*>(col.data());
+        for (int k = 0; k < SCAN4_BINS; ++k) { f[2 * k] = h.post_w[2 * k] * INV_SCALE; f[2 * k + 1] = h.post_w[2 * k + 1] * INV_SCALE; }
+        unsigned* e = reinterpret_cast<unsigned*>(f + 2 * SCAN4_BINS);
+        for (int p = 0; p < 8; ++p) {
+            unsigned lo = 0u, hi = 0u;
+            for (int i = 1; i < CHUNK4; ++i)
+                if (h.post_b[CHUNK4 * p + i] != h.post_b[CHUNK4 * p + i - 1]) { if (i < 32) lo |= 1u << i; else hi |= 1u << (i - 32); }
+            e[4 * p] = lo; e[4 * p + 1] = hi; e[4 * p + 2] = (unsigned)h.post_b[CHUNK4 * p]; e[4 * p + 3] = 0u;
+        }
+    }
+#else
     for (int k = 0; k < SCAN4_BINS; ++k) {
         ivec4 e; e.x = e.y = e.z = e.w = 0;
         if (k < NBINS) {
@@ -155,6 +168,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
         }
         col[k] = e;
     }
+#endif
     const float* s_win = h.window.data();
 
     static Inv8Warp w;
