@@ -26,6 +26,9 @@
 #include "avse_inv_stages.cuh"
 #include "avse_tables.h"
 
+#if !defined(AVSE_I8_SKIP_FFTS)
+#define AVSE_I8_SKIP_FFTS 1      // skip the FFTs of a group that cannot matter (warm-up groups: 0 and 1; frames beyond T_use)
+#endif
 #if !defined(AVSE_I8_POST_WALK)
 #define AVSE_I8_POST_WALK 1      // post stage: the coefficient pair of a lane's current band walks in registers (mask-driven advance)
 #endif
@@ -129,16 +132,19 @@ AVSE_HD void i8_mark_group(const float (&raw)[I8_RAW], int lane, float* frames) 
 
 // pass 1, interior groups, columns n2 = lane of the four FFTs.  FFT c packs frames (t0 + 2c, t0 + 2c + 1): strides [8c, 8c+16)
 // and [8c+4, 8c+20) of the batch.  Consumes (rotates) raw[] when rolled.
-AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames) {
+// c_lo: first FFT that is needed (2 in a warm-up group, whose FFTs 0 and 1 cannot reach the carry; see the kernel).
+AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames, int c_lo) {
     i8_mark_group(raw, lane, frames);
 #if AVSE_I8_ROLL_P1
     float* dst = frames + 2 * lane;
 #pragma unroll 1
     for (int c = 0; c < I8_NC; ++c) {
-        cpx x[16];
+        if (c >= c_lo) {
+            cpx x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j] * lc.win[j], raw[j + 4] * lc.win[j]);
-        p4_column(x, lc.tw, dst);
+            for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j] * lc.win[j], raw[j + 4] * lc.win[j]);
+            p4_column(x, lc.tw, dst);
+        }
         dst += FRAME4_F;
 #pragma unroll
         for (int j = 0; j + 8 < I8_RAW; ++j) raw[j] = raw[j + 8];
@@ -146,6 +152,7 @@ AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc,
 #else
 #pragma unroll
     for (int c = 0; c < I8_NC; ++c) {
+        if (c < c_lo) continue;
         cpx x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = cmake(raw[8 * c + j] * lc.win[j], raw[8 * c + j + 4] * lc.win[j]);
@@ -175,9 +182,10 @@ AVSE_HD void i8_pass1_tail(int lane, const float (&rt)[20], const float* s_win, 
 #else
 #define AVSE_I8_EDGE_Q AVSE_HD
 #endif
-AVSE_I8_EDGE_Q void i8_pass1_edge(const InvTile tl, int lane, const float* s_win, const vec2* s_tw, float* frames) {
+AVSE_I8_EDGE_Q void i8_pass1_edge(const InvTile tl, int lane, const float* s_win, const vec2* s_tw, float* frames, int c_lo, int c_hi) {
 #pragma unroll 1
     for (int round = 0; round < 5; ++round) {
+        if (round < 4 && (round < c_lo || round >= c_hi)) continue;     // FFTs outside [c_lo, c_hi) are not needed (see the kernel)
         const int c = round < 4 ? round : lane >> 3;
         const int n2 = round < 4 ? lane : 32 + (lane & 7);
         const int tA = tl.t0 + 2 * c;
@@ -459,8 +467,10 @@ AVSE_HD void i8_emit_main(int lane, int h0, int T_use, int out_len, bool write, 
 
 // Tail columns k2' = 32 + r: lane = (c, r) computes its column and parks the 20 row contributions in the staging buffer
 // st[c][j][r] (the dead coefficient buffer); window from the CTA's table.
-AVSE_HD void i8_passB_tail(int lane, const float* s_win, const vec2* s_tw, const float* frames, float* st) {
+// FFTs outside [c_lo, c_hi) were not computed in this group: their (stale) rows contribute exact zeros.
+AVSE_HD void i8_passB_tail(int lane, const float* s_win, const vec2* s_tw, const float* frames, float* st, int c_lo, int c_hi) {
     const int c = lane >> 3, r = lane & 7, k2 = 32 + r;
+    const bool act = c >= c_lo && c < c_hi;
     const float* col = frames + c * FRAME4_F + 2 * k2;
     cpx x[16];
 #if AVSE_I8_TW_IN_B
@@ -484,7 +494,13 @@ AVSE_HD void i8_passB_tail(int lane, const float* s_win, const vec2* s_tw, const
     }
     float* d = st + c * I8_ST_C + r;
 #pragma unroll
-    for (int j = 0; j < 20; ++j) d[8 * j] = cc[j];
+    for (int j = 0; j < 20; ++j) d[8 * j] = act ? cc[j] : 0.0f;
+}
+
+// A group that skipped some FFTs leaves their "frame is non-zero" flags set by pass 1's marks without the re-arm of pass A's
+// store: clear all eight.
+AVSE_HD void i8_rearm_flags(int lane, float* frames) {
+    if (lane < I8_FPG) frames[(lane >> 1) * FRAME4_F + I8_FLAG_F + (lane & 1)] = 0.0f;
 }
 
 // Tail columns, second half: the group's 44 tail rows x 8 columns are summed and leave.  lane = (q = lane / 8, r) owns column

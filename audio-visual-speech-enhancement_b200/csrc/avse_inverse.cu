@@ -389,6 +389,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             const bool write = g >= g0;
             const float* side_in = side + I8_SIDE_F * (g & 1);
             float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
+            // FFTs [c_lo, c_hi) of the group are needed: a warm-up group only rebuilds the carry, which FFTs 0 and 1 (rows 0..27 of the
+            // group) cannot reach; FFTs whose frames lie beyond T_use have zero coefficients.  Skipped FFTs add exact zeros.
+#if AVSE_I8_SKIP_FFTS
+            const int c_lo = write ? 0 : 2;
+            const int c_left = (P.T_use - tl.t0 + 1) >> 1;
+            const int c_hi = c_left < I8_NC ? c_left : I8_NC;
+#else
+            const int c_lo = 0, c_hi = I8_NC;
+#endif
             if (have) {
                 // coefficients of the 8 frames -> ybuf[band][I8_YS] (i8_coef_*): the 20 dB values of this lane are loaded ahead of
                 // pass 1 (AVSE_I8_PIPE_MEL: one whole group ahead, with the samples); the partitioned solve runs after pass 1
@@ -397,10 +406,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
 #endif
                 if (!EXT) {
                     if (interior) {
-                        i8_pass1_main(lane, raw, lc, frames);
+                        i8_pass1_main(lane, raw, lc, frames, c_lo);
                         i8_pass1_tail(lane, rt, s_win, s_tw, frames);
                     } else {
-                        i8_pass1_edge(tl, lane, s_win, s_tw, frames);
+                        i8_pass1_edge(tl, lane, s_win, s_tw, frames, c_lo, c_hi);
                     }
                 }
                 i8_coef_local(lane, s_spk, cd, xch);
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                         i8_stage_post<false>(lane, s_col, ybuf, frames, nullptr, nullptr);
                         __syncwarp();
                     }
+                    if (2 * r + 1 < c_lo || 2 * r >= c_hi) continue;      // neither FFT of this round is needed
                     cpx x[40];
                     if (it < 2) p4_pass2_load(lane, r, frames, x);
                     else i8_passA_load(lane, r, frames, x);
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                     else i8_passA_store(lane, r, frames, x);
                     __syncwarp();
                 }
+                if (c_lo > 0 || c_hi < I8_NC) i8_rearm_flags(lane, frames);
             }
             // ---- next computed group: issue its loads now (they land during pass B / emit) ----
             bool interior2 = false;
@@ -454,10 +465,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             // ---- pass B + emit: one FFT at a time (rolled), two finished hops leave after each ----
 #pragma unroll 1
             for (int cc = 0; cc < I8_NC; ++cc) {
-                if (have) i8_passB_add(lane, cc, lc, frames, acc);
+                if (have && cc >= c_lo && cc < c_hi) i8_passB_add(lane, cc, lc, frames, acc);
                 i8_emit_main(lane, tl.t0 + 2 * cc, P.T_use, P.out_len, write, s_win, out, acc);
             }
-            if (have) i8_passB_tail(lane, s_win, s_tw, frames, ybuf);
+            if (have) i8_passB_tail(lane, s_win, s_tw, frames, ybuf, c_lo, c_hi);
             __syncwarp();
             i8_tail_reduce_emit(lane, tl.t0, P.T_use, P.out_len, write, have, s_win, out, ybuf, side_in, side_out);
             __syncwarp();

@@ -197,14 +197,19 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
             const bool write = g >= g0;
             const float* side_in = side + I8_SIDE_F * (g & 1);
             float* side_out = side + I8_SIDE_F * ((g & 1) ^ 1);
+            // the kernel's FFT range of the group (AVSE_I8_SKIP_FFTS): warm-up groups need FFTs 2, 3 only; frames beyond T_use none
+            const bool skip_ffts = AVSE_I8_SKIP_FFTS != 0;
+            const int c_lo = skip_ffts ? (write ? 0 : 2) : 0;
+            const int c_left = (T_use - tl.t0 + 1) >> 1;
+            const int c_hi = skip_ffts ? (c_left < I8_NC ? c_left : I8_NC) : I8_NC;
             if (have) {
                 for (int lane = 0; lane < 32; ++lane) i8_coef_load(lane, mel_slices, 0, 0, tl.t0, T_use, w.cd[lane]);
                 if (i8_group_interior(tl)) {
                     for (int lane = 0; lane < 32; ++lane) { i8_load_raw(tl, lane, w.raw[lane]); i8_load_tail_raw(tl, lane, w.rt[lane]); }
-                    for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames);
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames, c_lo);
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_tail(lane, w.rt[lane], s_win, tw.data(), frames);
                 } else {
-                    for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames);
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames, c_lo, c_hi);
                 }
                 for (int lane = 0; lane < 32; ++lane) i8_coef_local(lane, h.spike.data(), w.cd[lane], xch);
                 for (int lane = 0; lane < 32; ++lane) i8_coef_finish(lane, h.spike.data(), w.cd[lane], xch, ybuf);
@@ -212,6 +217,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                     const int r = it & 1;
                     if (it == 2)
                         for (int lane = 0; lane < 32; ++lane) i8_stage_post<false>(lane, col.data(), ybuf, frames, nullptr, nullptr);
+                    if (2 * r + 1 < c_lo || 2 * r >= c_hi) continue;
                     for (int lane = 0; lane < 32; ++lane) {
                         if (it < 2) p4_pass2_load(lane, r, frames, w.x[lane]);
                         else i8_passA_load(lane, r, frames, w.x[lane]);
@@ -225,14 +231,16 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
                         else i8_passA_store(lane, r, frames, w.x[lane]);
                     }
                 }
+                if (c_lo > 0 || c_hi < I8_NC)
+                    for (int lane = 0; lane < 32; ++lane) i8_rearm_flags(lane, frames);
             }
             for (int cc = 0; cc < I8_NC; ++cc)
                 for (int lane = 0; lane < 32; ++lane) {
-                    if (have) i8_passB_add(lane, cc, w.lc[lane], frames, w.acc[lane]);
+                    if (have && cc >= c_lo && cc < c_hi) i8_passB_add(lane, cc, w.lc[lane], frames, w.acc[lane]);
                     i8_emit_main(lane, tl.t0 + 2 * cc, T_use, out_len, write, s_win, out, w.acc[lane]);
                 }
             if (have)
-                for (int lane = 0; lane < 32; ++lane) i8_passB_tail(lane, s_win, tw.data(), frames, ybuf);
+                for (int lane = 0; lane < 32; ++lane) i8_passB_tail(lane, s_win, tw.data(), frames, ybuf, c_lo, c_hi);
             for (int lane = 0; lane < 32; ++lane)
                 i8_tail_reduce_emit(lane, tl.t0, T_use, out_len, write, have, s_win, out, ybuf, side_in, side_out);
         }

@@ -134,3 +134,30 @@ def test_inverse_level_jump_between_packed_frames(emul, jump_db, tol):
         for kernel in ("i8", "i4"):
             out = _run(emul, mel, pcm, L, 1, kernel)
             assert np.max(np.abs(out - want)) <= tol * full, (kernel, jump_db, seed)
+
+
+@pytest.mark.parametrize("n_slices,L", [(5, 16000), (4, 12000), (3, 9440), (2, 5760)])
+def test_i8_skipped_ffts_change_nothing(emul, n_slices, L):
+    """A warm-up group (chunk start inside the utterance) computes FFTs 2 and 3 only, and a last group whose frames run past T_use
+    skips the FFTs without frames (AVSE_I8_SKIP_FFTS): the result is bit-identical whatever the chunking, also when the frames
+    right behind a warm-up group are digital silence (their 'frame is non-zero' flags must not be left set by the skipped FFTs)."""
+    rng = np.random.RandomState(n_slices)
+    pcm = (0.2 * rng.randn(L)).astype(np.float32)
+    T_use = min(20 * n_slices, 1 + L // 160)
+    G = -(-T_use // 8)
+    mel = (rng.rand(n_slices, 80, 20) * 40.0 - 60.0).astype(np.float32)
+    whole = _run(emul, mel, pcm, L, 1, "i8")
+    want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    assert np.max(np.abs(whole - want)) <= TOL_PCM * np.max(np.abs(want))
+    for chunks in range(2, G + 1):
+        assert np.array_equal(_run(emul, mel, pcm, L, chunks, "i8"), whole), chunks
+    # silence over whole groups in the middle: every chunking starts some chunk right at (or inside) the silent stretch
+    quiet = pcm.copy()
+    quiet[160 * 16: 160 * 41] = 0.0
+    for t in (8, 48, 57):            # ... and single silent frames (first frame of a group; an odd one) packed with a live partner
+        quiet[max(160 * t - 320, 0): 160 * t + 320] = 0.0
+    whole_q = _run(emul, mel, quiet, L, 1, "i8")
+    want_q = O.reconstruct_speech_signal(O.AudioSignal(quiet.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    assert np.max(np.abs(whole_q - want_q)) <= TOL_PCM * np.max(np.abs(want_q))
+    for chunks in range(2, G + 1):
+        assert np.array_equal(_run(emul, mel, quiet, L, chunks, "i8"), whole_q), chunks
