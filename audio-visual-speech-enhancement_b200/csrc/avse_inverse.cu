@@ -91,8 +91,7 @@ struct InvParams {
     int cg;           // groups per chunk
     int out_len;      // 160 (T_use - 1)
     long long total_groups;   // I8 kernel: B * G groups, cut into one contiguous range per warp
-    int base_groups;          // I8 kernel: groups per warp (the first rem_warps warps take one more)
-    int rem_warps;
+    WarpSplit split;          // I8 kernel: balanced contiguous ranges (avse_common.h)
 };
 
 // EXT: explicit phase array (dp:99 signature) instead of the recomputed mixture STFT; a separate instantiation keeps each
@@ -338,9 +337,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
     // (like the forward kernel's tiles).  A range that starts inside an utterance first recomputes the group before it (no
     // stores) to rebuild the overlap-add carry; a range that ends an utterance also drains the carry (group G).  Against
     // whole-utterance items this removes the idle SMs of a 1 000-utterance launch (1 000 items on 1 184 warps: 23 SMs had no work).
-    const long long gw = (long long)blockIdx.x * I8_WARPS + warp;
-    long long tile = gw * P.base_groups + (gw < P.rem_warps ? gw : P.rem_warps);
-    const long long tile_end = tile + P.base_groups + (gw < P.rem_warps ? 1 : 0);
+    long long tile, n_groups;
+    warp_split_range(P.split, (int)blockIdx.x, warp, I8_WARPS, tile, n_groups);
+    const long long tile_end = tile + n_groups;
 #pragma unroll 1
     while (tile < tile_end) {
         const int u = (int)(tile / P.G);
@@ -579,9 +578,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
         long long blocks = ctx->num_sms;
         const long long need = (P.total_groups + I8_WARPS - 1) / I8_WARPS;
         if (blocks > need) blocks = need;
-        const long long nw = blocks * I8_WARPS;
-        P.base_groups = (int)(P.total_groups / nw);
-        P.rem_warps = (int)(P.total_groups % nw);
+        P.split = make_warp_split(P.total_groups, blocks, I8_WARPS);
         if (a.phase) {
             if (o16) avse_inverse8_kernel<true, short><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);
             else avse_inverse8_kernel<true, float><<<(unsigned)blocks, I8_THREADS, I8_SMEM_BYTES, st>>>(P);

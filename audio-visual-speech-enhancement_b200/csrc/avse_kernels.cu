@@ -409,7 +409,8 @@ struct FwdParams {
     int T;            // frames per utterance
     int G;            // groups of FPG frames per utterance
     int total_tiles;  // B * G
-    int per_warp;     // tiles per warp (contiguous range)
+    int per_warp;     // tiles per warp (contiguous range): the 2-frame kernel
+    WarpSplit split;  // F4 kernel: balanced contiguous ranges (avse_common.h)
 };
 
 // SCAN = true: fused post+mel scan (tables with scan_ok); false: generic banded gather.
@@ -616,10 +617,10 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     const unsigned mask_lo = P.tb.scan4_mask[2 * (lane & 7)], mask_hi = P.tb.scan4_mask[2 * (lane & 7) + 1];
 
     const avse_forward_args& A = P.a;
-    const int gw = blockIdx.x * F4_WARPS + warp;
-    int tile = gw * P.per_warp;
-    int n_tiles = P.total_tiles - tile;
-    n_tiles = n_tiles < P.per_warp ? n_tiles : P.per_warp;
+    long long first, count;
+    warp_split_range(P.split, (int)blockIdx.x, warp, F4_WARPS, first, count);
+    int tile = (int)first;
+    const int n_tiles = (int)count;
     if (n_tiles <= 0) return;
     int u = tile / P.G;
     int g = tile - u * P.G;
@@ -834,6 +835,7 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
         const long long nwarps4 = blocks4 * F4_WARPS;
         P.total_tiles = (int)total4;
         P.per_warp = (int)((total4 + nwarps4 - 1) / nwarps4);
+        P.split = make_warp_split(total4, blocks4, F4_WARPS);
         const bool tiled = a.noise_period != nullptr;
         if (i16 && tiled) avse_forward4_kernel<short, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
         else if (i16) avse_forward4_kernel<short, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);

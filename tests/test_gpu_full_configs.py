@@ -49,12 +49,13 @@ def _check(eng, speech, noise, outs, idx, nvs, snr_db=None, inverse=None):
 
 
 def _tile_boundary_utterances(B, groups_per_utt, n_warps):
-    """Utterances in which a persistent warp's contiguous tile range ends and the next one begins (avse_forward launcher)."""
+    """Utterances in which a persistent warp's contiguous tile range ends and the next one begins (avse_common.h WarpSplit:
+    total / n_warps tiles per warp, the remainder one apiece to the first warps)."""
     total = B * groups_per_utt
-    per_warp = -(-total // n_warps)
+    base, extras = divmod(total, n_warps)
     picks = set()
-    for w in (1, n_warps // 2, n_warps - 1):
-        u = (w * per_warp) // groups_per_utt
+    for gw in (1, n_warps // 2, n_warps - 1):
+        u = (gw * base + min(gw, extras)) // groups_per_utt
         picks.update(x for x in (u - 1, u, u + 1) if 0 <= x < B)
     return picks
 
