@@ -22,7 +22,7 @@ struct avse_ctx {
     const int* d_col_band = nullptr;
     const float* d_col_w = nullptr;
     const float* d_spike = nullptr;
-    const int* d_post_b = nullptr;
+    const unsigned* d_post_mask = nullptr;
     const float* d_post_w = nullptr;
     // geometry served by this context; generic == true: the fallback kernels of avse_generic.cu (any n_fft)
     bool generic = false;

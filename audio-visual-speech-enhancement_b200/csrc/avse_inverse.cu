@@ -81,7 +81,7 @@ struct InvParams {
     const int* col_band;
     const float* col_w;
     const float* spike;
-    const int* post_b;        // I8 post stage, walk form (avse_tables.h)
+    const unsigned* post_mask;   // I8 post stage, walk form (avse_tables.h)
     const float* post_w;
     int T;            // mixture STFT frames
     int T_use;        // frames reconstructed
@@ -282,44 +282,74 @@ constexpr int I8_SMEM_BYTES = I8_SMEM_F * 4;
 static_assert((I8_SM_COL % 4) == 0 && (I8_SM_TW % 2) == 0 && (I8_WARP_SMEM_F % 4) == 0, "table alignment");
 static_assert(I8_SMEM_BYTES + 1024 <= 232448, "I8 shared memory must fit in one SM");
 
+#ifndef AVSE_I8_PROLOGUE_OUT_OF_LINE
+#define AVSE_I8_PROLOGUE_OUT_OF_LINE 1
+#endif
+#if AVSE_I8_PROLOGUE_OUT_OF_LINE
+#define AVSE_I8_PROLOGUE_Q __device__ __noinline__
+#else
+#define AVSE_I8_PROLOGUE_Q __device__ __forceinline__
+#endif
+// Kernel start: the CTA's tables, every global load in flight before the first store (table_fetch, avse_common.h), the warp's
+// buffers zeroed meanwhile.
+AVSE_I8_PROLOGUE_Q void i8_fill_tables(const InvParams& P, float* smem, float* frames) {
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    static_assert((I8_SM_WIN % 4) == 0 && (I8_SM_TW % 4) == 0 && (I8_SM_COL % 4) == 0 && (I8_SM_SPK % 4) == 0 && (I8_WARP_SMEM_F % 4) == 0 &&
+                  ((SPIKE_P * SPIKE_ROW) % 4) == 0, "16-byte table copies");
+    TableRegs<NFFT * 2 / 4, I8_THREADS> r_win;              // P.window holds (w, w) pairs
+    TableRegs<N1 * N2 * 2 / 4, I8_THREADS> r_tw;
+    TableRegs<SPIKE_P * SPIKE_ROW / 4, I8_THREADS> r_spk;
+    table_fetch(P.window, tid, r_win);
+    table_fetch(P.tw1t, tid, r_tw);
+    table_fetch(P.spike, tid, r_spk);
+#if AVSE_I8_POST_WALK
+    TableRegs<SCAN4_BINS * 2 / 4, I8_THREADS> r_pw;         // (w0, w1) per bin; then per chunk (mask lo, mask hi, first band, -)
+    TableRegs<8, I8_THREADS> r_pm;
+    table_fetch(P.post_w, tid, r_pw);
+    table_fetch(P.post_mask, tid, r_pm);
+#endif
+    for (int i = lane; i < I8_WARP_SMEM_F / 4; i += 32) reinterpret_cast<float4*>(frames)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < TableRegs<NFFT * 2 / 4, I8_THREADS>::K; ++k) {
+        const int i = tid + k * I8_THREADS;
+        if (i < NFFT * 2 / 4) { smem[I8_SM_WIN + 2 * i] = r_win.v[k].x; smem[I8_SM_WIN + 2 * i + 1] = r_win.v[k].z; }
+    }
+    table_put(smem + I8_SM_TW, tid, r_tw);
+    table_put(smem + I8_SM_SPK, tid, r_spk);
+#if !AVSE_I8_TW_IN_B
+#pragma unroll
+    for (int k = 0; k < TableRegs<N1 * N2 * 2 / 4, I8_THREADS>::K; ++k) {      // transposed copy [40][16] for pass A's own twiddles
+        const int i4 = tid + k * I8_THREADS;
+        if (i4 < N1 * N2 * 2 / 4) {
+            const int i = 2 * i4, k1 = i / N2, n2 = i - k1 * N2;             // entries i and i + 1 (same k1: N2 is even)
+            smem[I8_SM_TWT + 2 * (n2 * N1 + k1)] = r_tw.v[k].x; smem[I8_SM_TWT + 2 * (n2 * N1 + k1) + 1] = r_tw.v[k].y;
+            smem[I8_SM_TWT + 2 * ((n2 + 1) * N1 + k1)] = r_tw.v[k].z; smem[I8_SM_TWT + 2 * ((n2 + 1) * N1 + k1) + 1] = r_tw.v[k].w;
+        }
+    }
+#endif
+#if AVSE_I8_POST_WALK
+    table_put_scaled(smem + I8_SM_COL, tid, r_pw, INV_SCALE);       // irfft's 1 / 640 folded in
+    table_put(smem + I8_SM_COL + 2 * SCAN4_BINS, tid, r_pm);
+#else
+    for (int i = tid; i < SCAN4_BINS; i += I8_THREADS) {
+        int* e = reinterpret_cast<int*>(smem + I8_SM_COL) + 4 * i;
+        if (i < NBINS) {
+            e[0] = P.col_band[2 * i]; e[1] = P.col_band[2 * i + 1];
+            e[2] = __float_as_int(P.col_w[2 * i] * INV_SCALE); e[3] = __float_as_int(P.col_w[2 * i + 1] * INV_SCALE);
+        } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
+    }
+#endif
+}
+
 template <bool EXT, typename O>
 __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __grid_constant__ InvParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NFFT; i += I8_THREADS) smem[I8_SM_WIN + i] = P.window[2 * i];       // P.window holds (w, w) pairs
-    for (int i = threadIdx.x; i < N1 * N2; i += I8_THREADS) {
-        const int k1 = i / N2, n2 = i - k1 * N2;
-        const float re = P.tw1t[2 * i], im = P.tw1t[2 * i + 1];
-        smem[I8_SM_TW + 2 * i] = re; smem[I8_SM_TW + 2 * i + 1] = im;
-        smem[I8_SM_TWT + 2 * (n2 * N1 + k1)] = re; smem[I8_SM_TWT + 2 * (n2 * N1 + k1) + 1] = im;   // symmetric in (n2, k1)
-    }
-#if AVSE_I8_POST_WALK
-    for (int i = threadIdx.x; i < SCAN4_BINS; i += I8_THREADS) {       // (w0, w1) / 640 per bin, then per chunk (mask lo, mask hi, first band)
-        smem[I8_SM_COL + 2 * i] = P.post_w[2 * i] * INV_SCALE; smem[I8_SM_COL + 2 * i + 1] = P.post_w[2 * i + 1] * INV_SCALE;
-    }
-    if (threadIdx.x < 8) {
-        const int p = threadIdx.x;
-        unsigned lo = 0u, hi = 0u;
-        for (int i = 1; i < CHUNK4; ++i)
-            if (P.post_b[CHUNK4 * p + i] != P.post_b[CHUNK4 * p + i - 1]) { if (i < 32) lo |= 1u << i; else hi |= 1u << (i - 32); }
-        unsigned* e = reinterpret_cast<unsigned*>(smem + I8_SM_COL + 2 * SCAN4_BINS) + 4 * p;
-        e[0] = lo; e[1] = hi; e[2] = (unsigned)P.post_b[CHUNK4 * p]; e[3] = 0u;
-    }
-#else
-    for (int i = threadIdx.x; i < SCAN4_BINS; i += I8_THREADS) {
-        int* e = reinterpret_cast<int*>(smem + I8_SM_COL) + 4 * i;
-        if (i < NBINS) {
-            e[0] = P.col_band[2 * i]; e[1] = P.col_band[2 * i + 1];
-            e[2] = __float_as_int(P.col_w[2 * i] * INV_SCALE); e[3] = __float_as_int(P.col_w[2 * i + 1] * INV_SCALE);   // irfft's 1/640 folded in
-        } else { e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0; }
-    }
-#endif
-    for (int i = threadIdx.x; i < SPIKE_P * SPIKE_ROW; i += I8_THREADS) smem[I8_SM_SPK + i] = P.spike[i];
     float* frames = smem + warp * I8_WARP_SMEM_F;
     float* ybuf = frames + I8_NC * FRAME4_F;
     float* side = ybuf + I8_Y_F;
     float* xch = side + 2 * I8_SIDE_F;
-    for (int i = lane; i < I8_WARP_SMEM_F; i += 32) frames[i] = 0.0f;
+    i8_fill_tables(P, smem, frames);
     __syncthreads();
 
     const float* s_win = smem + I8_SM_WIN;
@@ -530,7 +560,7 @@ extern "C" int avse_inverse(avse_ctx* ctx, const avse_inverse_args* args, void* 
     P.col_band = ctx->d_col_band;
     P.col_w = ctx->d_col_w;
     P.spike = ctx->d_spike;
-    P.post_b = ctx->d_post_b;
+    P.post_mask = ctx->d_post_mask;
     P.post_w = ctx->d_post_w;
 
     int dev = 0;

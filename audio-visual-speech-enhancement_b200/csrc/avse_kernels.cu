@@ -65,7 +65,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
         {h.scan4_w.data(), h.scan4_w.size() * 4, 0},   {h.scan4_mask.data(), h.scan4_mask.size() * 4, 0},
         {h.scan4_loc.data(), h.scan4_loc.size() * 4, 0},
         {h.spike.data(), h.spike.size() * 4, 0},
-        {h.post_b.data(), h.post_b.size() * 4, 0},     {h.post_w.data(), h.post_w.size() * 4, 0},
+        {h.post_mask.data(), h.post_mask.size() * 4, 0}, {h.post_w.data(), h.post_w.size() * 4, 0},
     };
     size_t total = 0;
     for (auto& s : secs) { s.off = total; total += (s.bytes + 255) / 256 * 256; }
@@ -94,7 +94,7 @@ extern "C" int avse_create(int sample_rate, double fmin, double fmax, int device
     c->fwd.scan4_mask = (const unsigned*)(b + secs[15].off);
     c->fwd.scan4_loc = (const int*)(b + secs[16].off);
     c->d_spike = (const float*)(b + secs[17].off);
-    c->d_post_b = (const int*)(b + secs[18].off);
+    c->d_post_mask = (const unsigned*)(b + secs[18].off);
     c->d_post_w = (const float*)(b + secs[19].off);
     c->f4_tables = h.scan4_ok;   // fast F4 kernel (4 frames per warp)
     c->std_tables = h.scan_ok;   // fused post+mel scan kernel; otherwise the generic band-gather kernel
@@ -592,6 +592,31 @@ constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
 static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0 && (F4_SM_UTT % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
 
+#ifndef AVSE_F4_BATCHED_PROLOGUE
+#define AVSE_F4_BATCHED_PROLOGUE 1
+#endif
+// Kernel start: the CTA's tables, every global load in flight before the first store (table_fetch, avse_common.h), the warp's
+// frame buffers zeroed meanwhile.  Out of line on purpose: inlined, the same code changed the register allocation of the main
+// loop of this kernel (255 registers) and cost 1.3 % (profiles/README.md).
+__device__ __noinline__ void f4_fill_tables(float* smem, float* frames, const float* window, const float* tw1t, const float* scan4_w,
+                                            const int* scan4_loc) {
+    static_assert((F4_SM_WIN % 4) == 0 && (F4_SM_TW % 4) == 0 && (F4_SM_SCANW % 4) == 0 && (F4_SM_LOC % 4) == 0 && (WARP4_SMEM_F % 4) == 0, "16-byte table copies");
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    TableRegs<NFFT / 4, F4_THREADS> r_win;
+    TableRegs<N1 * N2 * 2 / 4, F4_THREADS> r_tw;
+    TableRegs<SCAN4_BINS * 2 / 4, F4_THREADS> r_sw;
+    TableRegs<NMEL, F4_THREADS> r_loc;
+    table_fetch(window, tid, r_win);
+    table_fetch(tw1t, tid, r_tw);
+    table_fetch(scan4_w, tid, r_sw);
+    table_fetch(scan4_loc, tid, r_loc);
+    for (int i = lane; i < WARP4_SMEM_F / 4; i += 32) reinterpret_cast<float4*>(frames)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // pad slots stay finite
+    table_put(smem + F4_SM_WIN, tid, r_win);
+    table_put(smem + F4_SM_TW, tid, r_tw);
+    table_put(smem + F4_SM_SCANW, tid, r_sw);
+    table_put(smem + F4_SM_LOC, tid, r_loc);
+}
+
 // TILED: the batch carries per-utterance noise periods (avse_forward_args::noise_period, dp:125-128).  A separate
 // instantiation, because this kernel sits on the 255-register / 32 KB instruction-cache cliff: with the period logic
 // compiled into the common kernel, batches that do not use it ran 4.5 % slower (profiles/README.md, round 2).
@@ -599,12 +624,16 @@ template <typename S, bool TILED>
 __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* frames = smem + warp * WARP4_SMEM_F;
+#if AVSE_F4_BATCHED_PROLOGUE
+    f4_fill_tables(smem, frames, P.tb.window, P.tb.tw1t, P.tb.scan4_w, P.tb.scan4_loc);
+#else
     for (int i = threadIdx.x; i < NFFT; i += F4_THREADS) smem[F4_SM_WIN + i] = P.tb.window[i];
     for (int i = threadIdx.x; i < N1 * N2 * 2; i += F4_THREADS) smem[F4_SM_TW + i] = P.tb.tw1t[i];
     for (int i = threadIdx.x; i < SCAN4_BINS * 2; i += F4_THREADS) smem[F4_SM_SCANW + i] = P.tb.scan4_w[i];
     for (int i = threadIdx.x; i < NMEL * 4; i += F4_THREADS) reinterpret_cast<int*>(smem + F4_SM_LOC)[i] = P.tb.scan4_loc[i];
-    float* frames = smem + warp * WARP4_SMEM_F;
     for (int i = lane; i < WARP4_SMEM_F; i += 32) frames[i] = 0.0f;   // pad slots stay finite (they meet exact-zero weights)
+#endif
     __syncthreads();
 
     const float* s_win = smem + F4_SM_WIN;

@@ -135,6 +135,13 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
             if (t.post_w[2 * (k - 1)] == 0.0f && t.post_w[2 * (k - 1) + 1] == 0.0f && t.post_b[k - 1] > t.post_b[k]) t.post_b[k - 1] = t.post_b[k];
         for (int k = 1; k < PB && t.post_ok; ++k)
             if (t.post_b[k] < t.post_b[k - 1] || t.post_b[k] > t.post_b[k - 1] + 1 || t.post_b[k] > NMEL - 2) t.post_ok = false;
+        constexpr int CH = 41;
+        t.post_mask.assign(8 * 4, 0u);
+        for (int p = 0; p < 8; ++p) {
+            for (int i = 1; i < CH; ++i)
+                if (t.post_b[CH * p + i] != t.post_b[CH * p + i - 1]) t.post_mask[4 * p + (i >> 5)] |= 1u << (i & 31);
+            t.post_mask[4 * p + 2] = (unsigned)t.post_b[CH * p];
+        }
     }
 
     // G = F F^T must be tridiagonal; Thomas factors in float64

@@ -56,6 +56,7 @@ struct HostTables {
     bool post_ok = false;
     std::vector<int> post_b;          // [328]
     std::vector<float> post_w;        // [328][2]
+    std::vector<unsigned> post_mask;  // [8][4] per chunk of 41 bins: (mask lo, mask hi, first band, 0); bit i: the pair advances before bin 41 p + i
 
     std::string error;                // non-empty when the configuration is unsupported
 };

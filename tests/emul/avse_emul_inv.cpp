@@ -151,12 +151,7 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
         float* f = reinterpret_cast<float*>(col.data());
         for (int k = 0; k < SCAN4_BINS; ++k) { f[2 * k] = h.post_w[2 * k] * INV_SCALE; f[2 * k + 1] = h.post_w[2 * k + 1] * INV_SCALE; }
         unsigned* e = reinterpret_cast<unsigned*>(f + 2 * SCAN4_BINS);
-        for (int p = 0; p < 8; ++p) {
-            unsigned lo = 0u, hi = 0u;
-            for (int i = 1; i < CHUNK4; ++i)
-                if (h.post_b[CHUNK4 * p + i] != h.post_b[CHUNK4 * p + i - 1]) { if (i < 32) lo |= 1u << i; else hi |= 1u << (i - 32); }
-            e[4 * p] = lo; e[4 * p + 1] = hi; e[4 * p + 2] = (unsigned)h.post_b[CHUNK4 * p]; e[4 * p + 3] = 0u;
-        }
+        for (int i = 0; i < 32; ++i) e[i] = h.post_mask[i];
     }
 #else
     for (int k = 0; k < SCAN4_BINS; ++k) {
