@@ -537,9 +537,14 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS) avse_forward_kernel(con
         // ---- dB + stores ----
         {
             FwdOut out;
+#if AVSE_F4_PTR_SLOT
+            float* const* ps = reinterpret_cast<float* const*>(utt_sm + F4_UTT_F * (u & 1) + 2);
+            out.dst[0] = ps[0]; out.dst[1] = ps[1]; out.dst[2] = ps[2];
+#else
             out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
             out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
             out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+#endif
             out.layout = A.layout;
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
@@ -586,8 +591,12 @@ constexpr int F4_SM_TW = F4_SM_WIN + NFFT;                     // [16][40] vec2
 constexpr int F4_SM_SCANW = F4_SM_TW + N1 * N2 * 2;            // [328] vec2 (wa, wb)
 constexpr int F4_SM_LOC = F4_SM_SCANW + SCAN4_BINS * 2;        // [80] ivec4
 constexpr int F4_SM_MIN = F4_SM_LOC + NMEL * 4;                // [warps][3][32] per-lane running minima
-constexpr int F4_SM_UTT = F4_SM_MIN + F4_WARPS * 96;           // [warps][2][2] per-utterance (gain, noise period), see the kernel
-constexpr int F4_SMEM_F = F4_SM_UTT + F4_WARPS * 4;
+#ifndef AVSE_F4_PTR_SLOT
+#define AVSE_F4_PTR_SLOT 1         // 1: the utterance's output row pointers live in the per-warp slot (written once per utterance)
+#endif
+constexpr int F4_UTT_F = AVSE_F4_PTR_SLOT ? 12 : 2;            // per parity: gain, noise period [, 4 output row pointers, 2 pad]
+constexpr int F4_SM_UTT = F4_SM_MIN + F4_WARPS * 96;           // [warps][2][F4_UTT_F] per-utterance values, see the kernel
+constexpr int F4_SMEM_F = F4_SM_UTT + F4_WARPS * 2 * F4_UTT_F;
 constexpr int F4_SMEM_BYTES = F4_SMEM_F * 4;
 static_assert((F4_SM_TW % 2) == 0 && (F4_SM_SCANW % 2) == 0 && (F4_SM_LOC % 4) == 0 && (F4_SM_UTT % 4) == 0, "table alignment");
 static_assert(F4_SMEM_BYTES + 1024 <= 232448, "F4 shared memory must fit in one SM");
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     int vs = 0, vn = 0;
     // the level-equaliser gain (and the noise period) are needed once per tile, at the top of pass 1: they live in a
     // per-warp shared-memory slot, double-buffered by the utterance's parity, instead of in loop-carried registers
-    float* utt_sm = smem + F4_SM_UTT + warp * 4;
+    float* utt_sm = smem + F4_SM_UTT + warp * (2 * F4_UTT_F);
     const S* in_speech = reinterpret_cast<const S*>(A.speech);
     const S* in_noise = reinterpret_cast<const S*>(A.noise);
     constexpr int LINE = 128 / (int)sizeof(S);        // samples per 128-byte line
@@ -710,17 +719,26 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         ovn = ovn < 0 ? 0 : (ovn < A.L ? ovn : A.L);
         const MixGain mg = mix_gain(A, uu);
         of = mg.resid;
-        utt_sm[2 * (uu & 1)] = mg.gain;                       // every lane writes the same value
+        utt_sm[F4_UTT_F * (uu & 1)] = mg.gain;                // every lane writes the same value
+#if AVSE_F4_PTR_SLOT
+        {   // this utterance's output rows (null stays null): read back once per tile instead of 64-bit multiplies + null checks
+            float** ps = reinterpret_cast<float**>(utt_sm + F4_UTT_F * (uu & 1) + 2);
+            ps[0] = A.out_speech ? A.out_speech + (size_t)uu * A.out_stride : nullptr;
+            ps[1] = A.out_noise ? A.out_noise + (size_t)uu * A.out_stride : nullptr;
+            ps[2] = A.out_mixed ? A.out_mixed + (size_t)uu * A.out_stride : nullptr;
+            ps[3] = A.mixed_pcm ? A.mixed_pcm + (size_t)uu * A.pcm_stride : nullptr;
+        }
+#endif
         if (TILED) {
             int period = A.noise_period[uu];
             if (period <= 0 || period >= ovn) period = 0;     // the stored noise already covers [0, vn)
-            reinterpret_cast<int*>(utt_sm)[2 * (uu & 1) + 1] = period;
+            reinterpret_cast<int*>(utt_sm)[F4_UTT_F * (uu & 1) + 1] = period;
         }
     };
     auto make_tile = [&](int uu, int gg, int tvs, int tvn, float tf) {
         FwdTileT<S> t;
-        t.sp = in_speech + (size_t)uu * A.in_stride;
-        t.nz = in_noise + (size_t)uu * A.in_stride;
+        t.sp = in_speech + (size_t)uu * A.in_stride;      // (the INPUT row pointers through the slot too: 3 % slower -- they feed the
+        t.nz = in_noise + (size_t)uu * A.in_stride;       //  address generation of the software-pipelined loads)
         t.L = A.L;
         t.valid_s = tvs;
         t.valid_n = tvn;
@@ -729,8 +747,12 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         t.t0 = gg * F4;
         t.factor = tf;
         t.gain = 0.0f;            // read from the slot at the top of pass 1
-        t.period_n = TILED ? reinterpret_cast<const int*>(utt_sm)[2 * (uu & 1) + 1] : 0;
+        t.period_n = TILED ? reinterpret_cast<const int*>(utt_sm)[F4_UTT_F * (uu & 1) + 1] : 0;
+#if AVSE_F4_PTR_SLOT
+        t.mixed_pcm = reinterpret_cast<float* const*>(utt_sm + F4_UTT_F * (uu & 1) + 2)[3];
+#else
         t.mixed_pcm = A.mixed_pcm ? A.mixed_pcm + (size_t)uu * A.pcm_stride : nullptr;
+#endif
         return t;
     };
     load_utt(u, vs, vn, factor);
@@ -746,7 +768,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     for (int it = 0; it < n_tiles; ++it) {
         prefetch_ahead(it, u, g);
         // ---- pass 1 ----
-        tl.gain = utt_sm[2 * (u & 1)];
+        tl.gain = utt_sm[F4_UTT_F * (u & 1)];
         if (interior) {
 #if AVSE_P1_UNIFIED
             stage4_pass1_unified(tl, lane, rs, rn, ts, tn, lc, s_win, s_tw, frames);
@@ -791,9 +813,14 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         // ---- dB + stores ----
         {
             FwdOut out;
+#if AVSE_F4_PTR_SLOT
+            float* const* ps = reinterpret_cast<float* const*>(utt_sm + F4_UTT_F * (u & 1) + 2);
+            out.dst[0] = ps[0]; out.dst[1] = ps[1]; out.dst[2] = ps[2];
+#else
             out.dst[0] = A.out_speech ? A.out_speech + (size_t)u * A.out_stride : nullptr;
             out.dst[1] = A.out_noise ? A.out_noise + (size_t)u * A.out_stride : nullptr;
             out.dst[2] = A.out_mixed ? A.out_mixed + (size_t)u * A.out_stride : nullptr;
+#endif
             out.layout = A.layout;
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
