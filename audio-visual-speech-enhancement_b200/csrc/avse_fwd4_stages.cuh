@@ -35,6 +35,10 @@ constexpr int F4 = 4;                          // frames per group
 constexpr int CHUNK4 = 41;                     // bins per scan lane (odd: bank spread); 8 x 41 = 328 >= 321
 constexpr int SCAN4_BINS = 8 * CHUNK4;         // 328
 constexpr int FRAME4_F = N1 * ROW_F + 16;      // 1360 floats per frame buffer, == 16 (mod 32)
+constexpr int ZERO4_F = N1 * ROW_F;             // floats [1344, 1360) of a frame buffer are never written: always zero
+#ifndef AVSE_DB_BRANCHFREE_EXTRA
+#define AVSE_DB_BRANCHFREE_EXTRA 1
+#endif
 constexpr int FLUSH4_F = 1284;                 // chunk-end partial sums: 8 chunks x 6 floats in [1284, 1332)
 constexpr int WARP4_SMEM_F = F4 * FRAME4_F;    // 5440 floats = 21760 B per warp
 constexpr int RAW4 = 16 + 4 * (F4 - 1);        // 28 strides of 40 samples cover the four frames of a group
@@ -424,7 +428,8 @@ AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const 
         const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.x & 0xffff));
         mel[0][f] = sn.x; mel[1][f] = sn.y; mel[2][f] = fr[loc.x >> 16];
     }
-    if (loc.y >= 0) {
+#if AVSE_DB_BRANCHFREE_EXTRA
+    {   // second partial sum: bands without one read the buffer's zero pad (ZERO4_F, avse_tables.cpp) -- no divergent branch
 #pragma unroll
         for (int f = 0; f < F4; ++f) {
             const float* fr = frames + f * FRAME4_F;
@@ -432,6 +437,16 @@ AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const 
             mel[0][f] += sn.x; mel[1][f] += sn.y; mel[2][f] += fr[loc.y >> 16];
         }
     }
+#else
+    if ((loc.y & 0xffff) != ZERO4_F) {
+#pragma unroll
+        for (int f = 0; f < F4; ++f) {
+            const float* fr = frames + f * FRAME4_F;
+            const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.y & 0xffff));
+            mel[0][f] += sn.x; mel[1][f] += sn.y; mel[2][f] += fr[loc.y >> 16];
+        }
+    }
+#endif
     if (loc.z >= 0) {
 #pragma unroll
         for (int f = 0; f < F4; ++f) {

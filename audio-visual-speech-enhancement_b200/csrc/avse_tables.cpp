@@ -287,7 +287,7 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
     // ---- F4 kernel scan tables: 8 chunks of CHUNK4 = 41 bins, emissions written densely ----
     // (constants restated from avse_fwd4_stages.cuh, which this plain-C++ file does not include)
     {
-        constexpr int CH = 41, NCH = 8, FLUSH = 1284;
+        constexpr int CH = 41, NCH = 8, FLUSH = 1284, ZERO4 = 1344;
         t.scan4_ok = t.scan_ok;
         t.scan4_w.assign((size_t)NCH * CH * 2, 0.0f);
         t.scan4_mask.assign(NCH * 2, 0u);
@@ -322,8 +322,12 @@ bool build_tables(HostTables& t, int sample_rate, double fmin, double fmax) {
             add4(seg[kl] - 1, fl + 0, fl + 4);
             add4(seg[kl], fl + 2, fl + 5);
         }
-        for (int m = 0; m < NMEL && t.scan4_ok; ++m)
+        for (int m = 0; m < NMEL && t.scan4_ok; ++m) {
             if (n4[m] == 0) t.scan4_ok = false;
+            // no second partial sum: point it at the frame buffer's always-zero pad (floats 1344..1346) so that the dB stage adds it
+            // without a divergent branch (every warp holds bands with and without one); a third one stays -1 (rare, warp-uniform skip)
+            if (n4[m] == 1) t.scan4_loc[m * 4 + 1] = ZERO4 | ((ZERO4 + 2) << 16);
+        }
     }
     return true;
 }
