@@ -36,6 +36,9 @@ constexpr int CHUNK4 = 41;                     // bins per scan lane (odd: bank 
 constexpr int SCAN4_BINS = 8 * CHUNK4;         // 328
 constexpr int FRAME4_F = N1 * ROW_F + 16;      // 1360 floats per frame buffer, == 16 (mod 32)
 constexpr int ZERO4_F = N1 * ROW_F;             // floats [1344, 1360) of a frame buffer are never written: always zero
+#ifndef AVSE_SCAN4_BLK
+#define AVSE_SCAN4_BLK 4          // bins per unrolled block of the scan: 1 / 2 / 4 / 5 / 8 / 10 / 20 -> 0.567 / 0.548 / 0.532 / 0.537 / 0.533 / 0.542 / 0.553 ms
+#endif
 #ifndef AVSE_DB_BRANCHFREE_EXTRA
 #define AVSE_DB_BRANCHFREE_EXTRA 1
 #endif
@@ -392,14 +395,14 @@ AVSE_HD void stage4_scan(int lane, float factor, const vec2* s_w, unsigned mask_
     float Am = 0.0f, Bm = 0.0f;
     const float nfactor = -factor;
     unsigned mlo = mask_lo, mhi = mask_hi;
-    static_assert(CHUNK4 == 41, "5 blocks of 8 bins + 1");
+    static_assert(CHUNK4 == 41 && (40 % AVSE_SCAN4_BLK) == 0 && AVSE_SCAN4_BLK < 32, "blocks of AVSE_SCAN4_BLK bins + 1");
 #pragma unroll 1
-    for (int ib = 0; ib < 40; ib += 8) {
+    for (int ib = 0; ib < 40; ib += AVSE_SCAN4_BLK) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) scan4_bin(za, zc, tab, j, ((mlo >> j) & 1u) != 0u, factor, nfactor, esn, em, Asn, Bsn, Am, Bm);
-        za += 16; zc -= 16; tab += 8;
-        mlo = (mlo >> 8) | (mhi << 24);
-        mhi >>= 8;
+        for (int j = 0; j < AVSE_SCAN4_BLK; ++j) scan4_bin(za, zc, tab, j, ((mlo >> j) & 1u) != 0u, factor, nfactor, esn, em, Asn, Bsn, Am, Bm);
+        za += 2 * AVSE_SCAN4_BLK; zc -= 2 * AVSE_SCAN4_BLK; tab += AVSE_SCAN4_BLK;
+        mlo = (mlo >> AVSE_SCAN4_BLK) | (mhi << (32 - AVSE_SCAN4_BLK));
+        mhi >>= AVSE_SCAN4_BLK;
     }
     scan4_bin(za, zc, tab, 0, (mlo & 1u) != 0u, factor, nfactor, esn, em, Asn, Bsn, Am, Bm);
     float* fl = fr + FLUSH4_F + 6 * p;
