@@ -94,6 +94,63 @@ AVSE_HD void p4_load_raw(const FwdTileT<S>& tl, int nz_shift, int lane, float (&
     for (int j = 0; j < RAW4; ++j) { rs[j] = (float)ps[N2 * j]; rn[j] = (float)pn[N2 * j]; }
 }
 
+// ---------------------------------------------------------------------------------------
+// Reflect-only edge groups (AVSE_F4_REFLECT_FAST): the first group of an utterance and the last ones differ from an interior
+// group only in WHERE their samples come from when both signals are full length (no zero padding) and the noise is not tiled:
+// librosa's centre padding mirrors the index (pad_mode='reflect', dp:79).  Such a group takes the interior pass 1 with mirrored
+// load indices instead of the per-sample edge loader (3 of the 76 groups of a 3 s utterance, each 3.4 x the interior cost).
+// Frames past the last one read mirrored samples too (finite, never stored: the edge stage duplicates the last frame instead).
+// The mixture PCM of the group's own hops is stored by stage4_store_pcm_guarded (the interior stores are unguarded).
+// ---------------------------------------------------------------------------------------
+#if !defined(AVSE_F4_REFLECT_FAST)
+#define AVSE_F4_REFLECT_FAST 1
+#endif
+AVSE_HD int reflect_index(int i, int L) {
+    i = i < 0 ? -i : i;
+    const int m = 2 * (L - 1) - i;
+    return i < m ? i : m;
+}
+
+template <typename S>
+AVSE_HD bool group4_reflect_only(const FwdTileT<S>& tl) {
+    // L >= 4 n_fft keeps every mirrored index inside [0, L), the phantom frames of the last group included
+    return tl.nz != nullptr && tl.vmin >= tl.L && tl.period_n == 0 && tl.L >= 4 * NFFT;
+}
+
+template <typename S>
+AVSE_HD void p4_load_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
+    const int o = tl.t0 * HOP - HALF + lane;
+#pragma unroll
+    for (int j = 0; j < RAW4; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+}
+
+template <typename S>
+AVSE_HD void p4_load_tail_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[16], float (&rn)[16]) {
+    const int o = (tl.t0 + (lane >> 3)) * HOP - HALF + 32 + (lane & 7);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+}
+
+// s + factor * (gain * n) of the group's own hops, samples < L only: the same arithmetic as the interior stores of
+// stage4_pass1_main / stage4_pass1_tail_compute (rn, tn still unscaled here).
+template <typename S>
+AVSE_HD void stage4_store_pcm_guarded(const FwdTileT<S>& tl, int lane, const float (&rs)[RAW4], const float (&rn)[RAW4], const float (&ts)[16],
+                                      const float (&tn)[16]) {
+    if (tl.mixed_pcm == nullptr) return;
+    const int i0 = tl.t0 * HOP + lane;
+#pragma unroll
+    for (int j = 8; j < 24; ++j) {
+        const int i = i0 + N2 * (j - 8);
+        if (i < tl.L) tl.mixed_pcm[i] = rs[j] + tl.factor * (rn[j] * tl.gain);
+    }
+    const int i1 = (tl.t0 + (lane >> 3)) * HOP + 32 + (lane & 7);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i1 + N2 * j;
+        if (i < tl.L) tl.mixed_pcm[i] = ts[8 + j] + tl.factor * (tn[8 + j] * tl.gain);
+    }
+}
+
 // Rounds 0..3 of an interior group: frame f, column n2 = lane.  Also stores the mixture PCM (dp:133) of the
 // group's own four hops (strides 8..23 of the batch) for the residues n2 < 32.
 // The raw noise samples are scaled by the level equaliser tl.gain here (see FwdTileT).

@@ -759,17 +759,25 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     FwdTileT<S> tl = make_tile(u, g, vs, vn, factor);
     int nz_shift = 0;
     bool interior = group4_interior<S, TILED>(tl, nz_shift);
+    bool reflect = AVSE_F4_REFLECT_FAST && !TILED && !interior && group4_reflect_only(tl);   // see avse_fwd4_stages.cuh
     float rs[RAW4], rn[RAW4], ts[16], tn[16];
     if (interior) {
         p4_load_raw(tl, nz_shift, lane, rs, rn);
         p4_load_tail_raw(tl, nz_shift, lane, ts, tn);
+    } else if (reflect) {
+        p4_load_raw_reflect(tl, lane, rs, rn);
+        p4_load_tail_raw_reflect(tl, lane, ts, tn);
     }
 #pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
         prefetch_ahead(it, u, g);
         // ---- pass 1 ----
         tl.gain = utt_sm[F4_UTT_F * (u & 1)];
-        if (interior) {
+        if (reflect) {                       // mirrored loads, interior arithmetic; this group's PCM stores need their bounds check
+            stage4_store_pcm_guarded(tl, lane, rs, rn, ts, tn);
+            tl.mixed_pcm = nullptr;
+        }
+        if (interior || reflect) {
 #if AVSE_P1_UNIFIED
             stage4_pass1_unified(tl, lane, rs, rn, ts, tn, lc, s_win, s_tw, frames);
 #else
@@ -805,9 +813,13 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
         int nz_shift2 = 0;
         const bool interior2 = have_next && group4_interior<S, TILED>(tnx, nz_shift2);
+        const bool reflect2 = AVSE_F4_REFLECT_FAST && !TILED && have_next && !interior2 && group4_reflect_only(tnx);
         if (interior2) {
             p4_load_raw(tnx, nz_shift2, lane, rs, rn);
             p4_load_tail_raw(tnx, nz_shift2, lane, ts, tn);
+        } else if (reflect2) {
+            p4_load_raw_reflect(tnx, lane, rs, rn);
+            p4_load_tail_raw_reflect(tnx, lane, ts, tn);
         }
 
         // ---- dB + stores ----
@@ -833,6 +845,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         u = u2; g = g2; vs = vs2; vn = vn2;
         tl = tnx;
         interior = interior2;
+        reflect = reflect2;
     }
 }
 
