@@ -99,6 +99,35 @@ AVSE_HD void i8_load_tail_raw(const InvTile& tl, int lane, float (&rt)[20]) {
     for (int j = 0; j < 20; ++j) rt[j] = p[N2 * j];
 }
 
+// Reflect-only edge groups (AVSE_I8_REFLECT_FAST, like the forward kernel's AVSE_F4_REFLECT_FAST): with a full-length mixture
+// (no zero padding) the first and the last group of an utterance differ from an interior one only in the mirrored sample index of
+// librosa's centre padding (dp:79), so they take the interior pass 1 on mirrored loads instead of the per-sample edge loader.
+// Frames past the last mixture frame read mirrored samples too: their coefficients are zero (or their FFT is skipped).
+#if !defined(AVSE_I8_REFLECT_FAST)
+#define AVSE_I8_REFLECT_FAST 1
+#endif
+AVSE_HD bool i8_group_reflect_only(const InvTile& tl) {
+    return tl.valid >= tl.L && tl.L >= 4 * NFFT;      // every mirrored index of the group (phantom frames included) stays inside [0, L)
+}
+
+AVSE_HD int i8_reflect_index(int i, int L) {
+    i = i < 0 ? -i : i;
+    const int m = 2 * (L - 1) - i;
+    return i < m ? i : m;
+}
+
+AVSE_HD void i8_load_raw_reflect(const InvTile& tl, int lane, float (&raw)[I8_RAW]) {
+    const int o = tl.t0 * HOP - HALF + lane;
+#pragma unroll
+    for (int j = 0; j < I8_RAW; ++j) raw[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+}
+
+AVSE_HD void i8_load_tail_raw_reflect(const InvTile& tl, int lane, float (&rt)[20]) {
+    const int o = (tl.t0 + 2 * (lane >> 3)) * HOP - HALF + 32 + (lane & 7);
+#pragma unroll
+    for (int j = 0; j < 20; ++j) rt[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+}
+
 // Non-zero flags of the two real frames packed in one FFT, from the raw sample bits (see inv_mark_nonzero_raw): frame A uses
 // strides 0..15, frame B strides 4..19 of r[]; w[n] != 0 except n = 0, which only column n2 = 0 holds (stride 0 of its frame).
 AVSE_HD void i8_mark(const float* r, int n2, float* frame_base) {
@@ -132,14 +161,15 @@ AVSE_HD void i8_mark_group(const float (&raw)[I8_RAW], int lane, float* frames) 
 
 // pass 1, interior groups, columns n2 = lane of the four FFTs.  FFT c packs frames (t0 + 2c, t0 + 2c + 1): strides [8c, 8c+16)
 // and [8c+4, 8c+20) of the batch.  Consumes (rotates) raw[] when rolled.
-// c_lo: first FFT that is needed (2 in a warm-up group, whose FFTs 0 and 1 cannot reach the carry; see the kernel).
-AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames, int c_lo) {
+// [c_lo, c_hi): the FFTs that are needed (a warm-up group: 2, 3 -- FFTs 0 and 1 cannot reach the carry; a last group: those with
+// frames below T_use; see the kernel).
+AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames, int c_lo, int c_hi) {
     i8_mark_group(raw, lane, frames);
 #if AVSE_I8_ROLL_P1
     float* dst = frames + 2 * lane;
 #pragma unroll 1
     for (int c = 0; c < I8_NC; ++c) {
-        if (c >= c_lo) {
+        if (c >= c_lo && c < c_hi) {
             cpx x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = cmake(raw[j] * lc.win[j], raw[j + 4] * lc.win[j]);
@@ -152,7 +182,7 @@ AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc,
 #else
 #pragma unroll
     for (int c = 0; c < I8_NC; ++c) {
-        if (c < c_lo) continue;
+        if (c < c_lo || c >= c_hi) continue;
         cpx x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = cmake(raw[8 * c + j] * lc.win[j], raw[8 * c + j + 4] * lc.win[j]);

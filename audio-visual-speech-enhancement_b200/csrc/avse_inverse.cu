@@ -408,6 +408,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
             if (!EXT) {
                 interior = i8_group_interior(tl);
                 if (interior) { i8_load_raw(tl, lane, raw); i8_load_tail_raw(tl, lane, rt); }
+                else if (AVSE_I8_REFLECT_FAST && i8_group_reflect_only(tl)) {      // mirrored loads, interior pass 1 (avse_inv8_stages.cuh)
+                    i8_load_raw_reflect(tl, lane, raw); i8_load_tail_raw_reflect(tl, lane, rt);
+                    interior = true;
+                }
             }
         }
 
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
 #endif
                 if (!EXT) {
                     if (interior) {
-                        i8_pass1_main(lane, raw, lc, frames, c_lo);
+                        i8_pass1_main(lane, raw, lc, frames, c_lo, c_hi);
                         i8_pass1_tail(lane, rt, s_win, s_tw, frames);
                     } else {
                         i8_pass1_edge(tl, lane, s_win, s_tw, frames, c_lo, c_hi);
@@ -488,6 +492,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
                     if (!EXT) {
                         interior2 = i8_group_interior(tn);
                         if (interior2) { i8_load_raw(tn, lane, raw); i8_load_tail_raw(tn, lane, rt); }
+                        else if (AVSE_I8_REFLECT_FAST && i8_group_reflect_only(tn)) {
+                            i8_load_raw_reflect(tn, lane, raw); i8_load_tail_raw_reflect(tn, lane, rt);
+                            interior2 = true;
+                        }
                     }
                 }
             }

@@ -199,9 +199,14 @@ extern "C" int emul_inverse8(const float* mel_slices, int n_slices, const float*
             const int c_hi = skip_ffts ? (c_left < I8_NC ? c_left : I8_NC) : I8_NC;
             if (have) {
                 for (int lane = 0; lane < 32; ++lane) i8_coef_load(lane, mel_slices, 0, 0, tl.t0, T_use, w.cd[lane]);
-                if (i8_group_interior(tl)) {
-                    for (int lane = 0; lane < 32; ++lane) { i8_load_raw(tl, lane, w.raw[lane]); i8_load_tail_raw(tl, lane, w.rt[lane]); }
-                    for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames, c_lo);
+                const bool interior = i8_group_interior(tl);
+                const bool mirrored = AVSE_I8_REFLECT_FAST && !interior && i8_group_reflect_only(tl);
+                if (interior || mirrored) {
+                    for (int lane = 0; lane < 32; ++lane) {
+                        if (interior) { i8_load_raw(tl, lane, w.raw[lane]); i8_load_tail_raw(tl, lane, w.rt[lane]); }
+                        else { i8_load_raw_reflect(tl, lane, w.raw[lane]); i8_load_tail_raw_reflect(tl, lane, w.rt[lane]); }
+                    }
+                    for (int lane = 0; lane < 32; ++lane) i8_pass1_main(lane, w.raw[lane], w.lc[lane], frames, c_lo, c_hi);
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_tail(lane, w.rt[lane], s_win, tw.data(), frames);
                 } else {
                     for (int lane = 0; lane < 32; ++lane) i8_pass1_edge(tl, lane, s_win, tw.data(), frames, c_lo, c_hi);
