@@ -291,7 +291,7 @@ AVSE_HD void i8_coef_local(int lane, const float* s_spk, float (&d)[SPIKE_Q], fl
     const int f = lane >> 2, p = lane & 3;
     const float* tb = s_spk + p * SPIKE_ROW;
 #pragma unroll
-    for (int i = 0; i < SPIKE_Q; ++i) d[i] = exp2f(K * d[i]);
+    for (int i = 0; i < SPIKE_Q; ++i) d[i] = inv_exp2(K * d[i]);
 #pragma unroll
     for (int i = 1; i < SPIKE_Q; ++i) d[i] = fmaf(-tb[i], d[i - 1], d[i]);
     d[SPIKE_Q - 1] *= tb[SPIKE_Q + SPIKE_Q - 1];

@@ -141,6 +141,18 @@ AVSE_HD float inv_rsqrt(float x) {
 #endif
 }
 
+// 2^x for the dB -> amplitude conversion (x = dB log2(10) / 20, a few tens in magnitude; the -1e30 dB sentinel of absent frames
+// gives exactly 0).  exp2f() wraps the same MUFU.EX2 in a range test and two scalings for results below 2^-126 that cannot occur.
+AVSE_HD float inv_exp2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+
 AVSE_HD float bits_to_float(int b) {
 #if defined(__CUDA_ARCH__)
     return __int_as_float(b);
