@@ -165,7 +165,24 @@ AVSE_HD void i8_mark_group(const float (&raw)[I8_RAW], int lane, float* frames) 
 // frames below T_use; see the kernel).
 AVSE_HD void i8_pass1_main(int lane, float (&raw)[I8_RAW], const Lane4Const& lc, float* frames, int c_lo, int c_hi) {
     i8_mark_group(raw, lane, frames);
-#if AVSE_I8_ROLL_P1
+#if AVSE_I8_ROLL_P1 == 2      // two FFTs per iteration: half the register rotation (28 instead of 2 x 36 moves per pair)
+    float* dst = frames + 2 * lane;
+#pragma unroll 1
+    for (int c = 0; c < I8_NC; c += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (c + h >= c_lo && c + h < c_hi) {
+                cpx x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = cmake(raw[8 * h + j] * lc.win[j], raw[8 * h + j + 4] * lc.win[j]);
+                p4_column(x, lc.tw, dst + h * FRAME4_F);
+            }
+        }
+        dst += 2 * FRAME4_F;
+#pragma unroll
+        for (int j = 0; j + 16 < I8_RAW; ++j) raw[j] = raw[j + 16];
+    }
+#elif AVSE_I8_ROLL_P1
     float* dst = frames + 2 * lane;
 #pragma unroll 1
     for (int c = 0; c < I8_NC; ++c) {
