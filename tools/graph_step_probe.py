@@ -1,5 +1,5 @@
-"""Scratch probe (not product): does capturing the three launches of a forward step in a CUDA graph shrink the ~25 us of
-launch gaps per step?  Usage on the GPU box: python variants/graph_step_probe.py"""
+"""Probe (not product): does capturing the three launches of a forward step in a CUDA graph shrink the ~25 us of
+launch gaps per step?  Usage on the GPU box: python tools/graph_step_probe.py"""
 import importlib, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
