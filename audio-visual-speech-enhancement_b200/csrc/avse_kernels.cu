@@ -940,6 +940,9 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
 // blockIdx.z selects the signal (data0/1/2 with key column which0 + z).  Only 16-byte groups that actually hold a value
 // below the floor are written back, and an utterance whose stored minimum (min_key, tracked by avse_forward) is already
 // >= max - 80 is skipped without being read: the pass then costs one key load per CTA.
+#ifndef AVSE_FLOOR_ZLOOP
+#define AVSE_FLOOR_ZLOOP 1
+#endif
 static __device__ __forceinline__ void floor_store(float4* q, float4 v, float thr) {
     if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < thr) {
         v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
@@ -950,12 +953,23 @@ static __device__ __forceinline__ void floor_store(float4* q, float4 v, float th
 __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restrict__ data0, float* __restrict__ data1,
                                                                  float* __restrict__ data2, long long stride, long long n_per_utt,
                                                                  const int* __restrict__ max_key, const int* __restrict__ min_key,
-                                                                 int which0) {
+                                                                 int which0, int n_sig) {
     const int u = blockIdx.x;                 // utterance on grid.x: B is not capped at 65 535
+#if AVSE_FLOOR_ZLOOP
+    // gridDim.z == 1 with n_sig signals looped here: at 1 000 utterances two thirds of the (utterance, signal) pairs need no
+    // clipping, and 6 000 CTAs that only read a key and exit still cost their launch slots
+    for (int z = 0; z < n_sig; ++z) {
+#else
     const int z = blockIdx.z;
+    {
+#endif
     float* data = z == 0 ? data0 : (z == 1 ? data1 : data2);
     const float thr = key_to_float(max_key[3 * u + which0 + z]) - TOP_DB;
+#if AVSE_FLOOR_ZLOOP
+    if (min_key != nullptr && key_to_float(min_key[3 * u + which0 + z]) >= thr) continue;
+#else
     if (min_key != nullptr && key_to_float(min_key[3 * u + which0 + z]) >= thr) return;
+#endif
     float* p = data + (size_t)u * stride;
     const long long n4 = n_per_utt >> 2;
     const long long step = (long long)gridDim.y * blockDim.x;
@@ -977,6 +991,7 @@ __global__ void __launch_bounds__(256) avse_floor_inplace_kernel(float* __restri
     }
     for (long long j = 4 * n4 + (long long)blockIdx.y * blockDim.x + threadIdx.x; j < n_per_utt; j += step)
         p[j] = fmaxf(p[j], thr);
+    }
 }
 
 static unsigned floor_grid_x(long long n_per_utt) {
@@ -992,8 +1007,8 @@ extern "C" int avse_floor_inplace3(avse_ctx* ctx, float* speech, float* noise, f
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt) return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: bad sizes");
     if ((((size_t)speech | (size_t)noise | (size_t)mixed) & 15) || (stride & 3))
         return avse_fail(AVSE_E_ARG, "avse_floor_inplace3: data must be 16-byte aligned with stride % 4 == 0");
-    dim3 grid((unsigned)B, floor_grid_x(n_per_utt), 3);
-    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, min_key, 0);
+    dim3 grid((unsigned)B, floor_grid_x(n_per_utt), AVSE_FLOOR_ZLOOP ? 1 : 3);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(speech, noise, mixed, stride, n_per_utt, max_key, min_key, 0, 3);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1004,7 +1019,7 @@ extern "C" int avse_floor_inplace(avse_ctx* ctx, float* data, long long stride, 
     if (B <= 0 || n_per_utt <= 0 || stride < n_per_utt || which < 0 || which > 2) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: bad sizes");
     if (((size_t)data & 15) || (stride & 3)) return avse_fail(AVSE_E_ARG, "avse_floor_inplace: data must be 16-byte aligned with stride % 4 == 0");
     dim3 grid((unsigned)B, floor_grid_x(n_per_utt));
-    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, min_key, which);
+    avse_floor_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, data, data, stride, n_per_utt, max_key, min_key, which, 1);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
