@@ -562,4 +562,69 @@ AVSE_HD void stage4_db(int lane, int q, float factor, const ivec4* s_loc, const 
     }
 }
 
+// The last 16 bands (64..79) with all 32 lanes: lane = (half = lane / 16, band 64 + lane % 16) converts frames 2 half, 2 half + 1.
+// As round q = 2 of stage4_db these bands keep 16 lanes idle for a whole round (80 bands on 32 lanes), a sixth of the dB stage;
+// this form costs a second, smaller copy of the stage's code (AVSE_DB_SPLIT_LAST).  Same arithmetic per value, 8-byte stores.
+#if !defined(AVSE_DB_SPLIT_LAST)
+#define AVSE_DB_SPLIT_LAST 1
+#endif
+AVSE_HD void stage4_db_last(int lane, float factor, const ivec4* s_loc, const float* frames, const FwdOut& out, int t0, int T,
+                            float (&mx)[3], float* mn) {
+    const int half = lane >> 4, m = 64 + (lane & 15), f0 = 2 * half;
+    const ivec4 loc = s_loc[m];
+    float mel[3][2];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const float* fr = frames + (f0 + f) * FRAME4_F;
+        const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.x & 0xffff));
+        mel[0][f] = sn.x; mel[1][f] = sn.y; mel[2][f] = fr[loc.x >> 16];
+        const vec2 s2 = *reinterpret_cast<const vec2*>(fr + (loc.y & 0xffff));      // zero pad when absent (AVSE_DB_BRANCHFREE_EXTRA)
+        mel[0][f] += s2.x; mel[1][f] += s2.y; mel[2][f] += fr[loc.y >> 16];
+    }
+    if (loc.z >= 0) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const float* fr = frames + (f0 + f) * FRAME4_F;
+            const vec2 sn = *reinterpret_cast<const vec2*>(fr + (loc.z & 0xffff));
+            mel[0][f] += sn.x; mel[1][f] += sn.y; mel[2][f] += fr[loc.z >> 16];
+        }
+    }
+    const int nvalid = T - t0 < F4 ? T - t0 : F4;   // >= 1
+    int off;
+    bool store = true;
+    if (out.layout == 0) {
+        const int sl = t0 / SPSS, tt = t0 - sl * SPSS;
+        off = (sl * NMEL + m) * SPSS + tt + f0;
+        store = sl < out.n_slices;
+    } else {
+        off = m * out.ld_t + t0 + f0;
+    }
+#pragma unroll
+    for (int sig = 0; sig < 3; ++sig) {
+        const float scale = sig == 1 ? factor : 1.0f;
+        float d[2];
+        float lm = neg_inf(), ln = -neg_inf();
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            d[f] = amp_to_db(mel[sig][f] * scale);
+            const bool v = f0 + f < nvalid;
+            lm = v ? fmaxf(lm, d[f]) : lm;
+            ln = v ? fminf(ln, d[f]) : ln;
+        }
+        mx[sig] = fmaxf(lm, mx[sig]);
+        float* dst = out.dst[sig];
+        mn[32 * sig + lane] = fminf(mn[32 * sig + lane], (dst != nullptr && store) ? ln : -neg_inf());
+        if (dst != nullptr && store) {
+            if (out.layout == 0) {
+                vec2 o; o.x = d[0]; o.y = d[1];
+                *reinterpret_cast<vec2*>(dst + off) = o;     // 8-byte aligned: off % 2 == 0
+            } else {
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+                    if (f0 + f < nvalid) dst[off + f] = d[f];
+            }
+        }
+    }
+}
+
 }  // namespace avse

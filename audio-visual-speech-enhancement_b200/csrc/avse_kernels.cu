@@ -837,7 +837,12 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
             out.n_slices = A.n_slices;
             out.ld_t = A.ld_t;
 #pragma unroll 1
+#if AVSE_DB_SPLIT_LAST && AVSE_DB_BRANCHFREE_EXTRA
+            for (int q = 0; q < 2; ++q) stage4_db(lane, q, tl.factor, s_loc, frames, out, g * F4, P.T, mx, mn);
+            stage4_db_last(lane, tl.factor, s_loc, frames, out, g * F4, P.T, mx, mn);
+#else
             for (int q = 0; q < 3; ++q) stage4_db(lane, q, tl.factor, s_loc, frames, out, g * F4, P.T, mx, mn);
+#endif
         }
         __syncwarp();
 

@@ -213,6 +213,10 @@ extern "C" int emul_forward4_ex(const float* speech, const float* noise, int L, 
             for (int lane = 0; lane < 32; ++lane) {
                 float lm[3] = {-INFINITY, -INFINITY, -INFINITY};
                 float ln[96]; for (int i = 0; i < 96; ++i) ln[i] = INFINITY;
+#if AVSE_DB_SPLIT_LAST && AVSE_DB_BRANCHFREE_EXTRA
+                if (q == 2) stage4_db_last(lane, tl.factor, loc.data(), w.frames, out, tl.t0, T, lm, ln);     // the kernel's form of the last 16 bands
+                else
+#endif
                 stage4_db(lane, q, tl.factor, loc.data(), w.frames, out, tl.t0, T, lm, ln);
                 for (int s = 0; s < 3; ++s) if (lm[s] > mx[s]) mx[s] = lm[s];
             }
