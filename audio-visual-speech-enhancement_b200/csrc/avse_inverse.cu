@@ -292,7 +292,11 @@ static_assert(I8_SMEM_BYTES + 1024 <= 232448, "I8 shared memory must fit in one 
 #endif
 // Kernel start: the CTA's tables, every global load in flight before the first store (table_fetch, avse_common.h), the warp's
 // buffers zeroed meanwhile.
-AVSE_I8_PROLOGUE_Q void i8_fill_tables(const InvParams& P, float* smem, float* frames) {
+struct I8TablePtrs {      // by value: taking the address of the kernel's parameter block would make every later access of it a load
+    const float* window; const float* tw1t; const float* spike; const float* post_w; const unsigned* post_mask;
+    const int* col_band; const float* col_w;
+};
+AVSE_I8_PROLOGUE_Q void i8_fill_tables(const I8TablePtrs P, float* smem, float* frames) {
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
     static_assert((I8_SM_WIN % 4) == 0 && (I8_SM_TW % 4) == 0 && (I8_SM_COL % 4) == 0 && (I8_SM_SPK % 4) == 0 && (I8_WARP_SMEM_F % 4) == 0 &&
                   ((SPIKE_P * SPIKE_ROW) % 4) == 0, "16-byte table copies");
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) avse_inverse8_kernel(const __gr
     float* ybuf = frames + I8_NC * FRAME4_F;
     float* side = ybuf + I8_Y_F;
     float* xch = side + 2 * I8_SIDE_F;
-    i8_fill_tables(P, smem, frames);
+    i8_fill_tables(I8TablePtrs{P.window, P.tw1t, P.spike, P.post_w, P.post_mask, P.col_band, P.col_w}, smem, frames);
     __syncthreads();
 
     const float* s_win = smem + I8_SM_WIN;
