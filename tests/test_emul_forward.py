@@ -343,3 +343,26 @@ def test_in_kernel_noise_tiling(emul, n_noise, f2):
     for k, ref in (("speech", speech), ("noise", noise), ("mixed", mixed)):
         assert np.max(np.abs(got[k] - ref)) <= TOL_DB, k
     assert np.max(np.abs(got["mixed_pcm"] - msig.get_data())) <= TOL_PCM * np.max(np.abs(msig.get_data()))
+
+
+@pytest.mark.parametrize("L", [2560, 2561, 2719, 3333, 4001, 6400, 16000, 16100])
+def test_f4_reflect_only_edge_groups_at_awkward_lengths(emul, L):
+    """Full-length utterances (no zero padding) take the interior pass 1 with mirrored load indices in their first and last groups
+    (AVSE_F4_REFLECT_FAST; L >= 4 n_fft): lengths that are not multiples of the hop, last groups holding 1, 2, 3 or 4 frames, and
+    the shortest length the path accepts -- log-mel, running max and mixture PCM against the oracle."""
+    rng = np.random.RandomState(L)
+    s = O.synth_speech(L, SR, L % 7).astype(np.float32)
+    nf = (0.05 * rng.randn(L)).astype(np.float32)
+    fac = 0.9
+    T = 1 + L // 160
+    ns = max(1, T // 20)
+    got = _run_emul4(emul, s, nf, L, fac, ns)
+    for k, x in (("speech", s.astype(np.float64)), ("noise", fac * nf.astype(np.float64)), ("mixed", s.astype(np.float64) + fac * nf.astype(np.float64))):
+        ref, _ = O.signal_to_spectrogram(O.AudioSignal(x, SR), 640, 160)
+        assert ref.shape[1] == T
+        if T >= 20:
+            want = np.stack([ref[:, 20 * i:20 * i + 20] for i in range(ns)])
+            assert np.max(np.abs(got[k] - want)) <= TOL_DB, k
+        assert abs(got["max"][("speech", "noise", "mixed").index(k)] - ref.max()) <= TOL_DB, k
+    want_pcm = s.astype(np.float64) + fac * nf.astype(np.float64)
+    assert np.max(np.abs(got["mixed_pcm"] - want_pcm)) <= TOL_PCM * np.max(np.abs(want_pcm))

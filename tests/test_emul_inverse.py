@@ -161,3 +161,18 @@ def test_i8_skipped_ffts_change_nothing(emul, n_slices, L):
     assert np.max(np.abs(whole_q - want_q)) <= TOL_PCM * np.max(np.abs(want_q))
     for chunks in range(2, G + 1):
         assert np.array_equal(_run(emul, mel, quiet, L, chunks, "i8"), whole_q), chunks
+
+
+@pytest.mark.parametrize("L", [3200, 3333, 4001, 6400, 9440, 16100])
+def test_i8_reflect_only_edge_groups_at_awkward_lengths(emul, L):
+    """Full-length mixtures take the interior pass 1 with mirrored load indices in their first and last groups
+    (AVSE_I8_REFLECT_FAST): lengths that are not multiples of the hop and last groups of 1 ... 8 frames, every chunking."""
+    rng = np.random.RandomState(L)
+    pcm = (0.2 * rng.randn(L)).astype(np.float32)
+    n_slices = max(1, (1 + L // 160) // 20)
+    mel = (rng.rand(n_slices, 80, 20) * 40.0 - 60.0).astype(np.float32)
+    want = O.reconstruct_speech_signal(O.AudioSignal(pcm.astype(np.float64), SR), mel.astype(np.float64), 25.0).get_data()
+    whole = _run(emul, mel, pcm, L, 1, "i8")
+    assert whole.shape == want.shape
+    assert np.max(np.abs(whole - want)) <= TOL_PCM * np.max(np.abs(want))
+    assert np.array_equal(_run(emul, mel, pcm, L, 3, "i8"), whole)

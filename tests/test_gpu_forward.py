@@ -437,3 +437,37 @@ def test_noise_tiling_on_the_two_frame_kernel(eng):
     D = r2["stft"][0].cpu().numpy().T
     want = O.stft(S[0].astype(np.float64), 640, 160)
     assert np.max(np.abs(D - want)) <= 2e-5 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("L", [3200, 3333, 4001, 6400, 16100])
+def test_reflect_only_edge_groups_at_awkward_lengths(eng, L):
+    """Full-length utterances (no `lengths`): the first and last groups take the interior pass 1 on mirrored load indices
+    (AVSE_F4_REFLECT_FAST / AVSE_I8_REFLECT_FAST).  Lengths that are not multiples of the hop, last groups of 1 ... 4 (forward)
+    and 1 ... 8 (inverse) frames: forward and inverse against the oracle, float and int16 input, and the same rows bit-identical
+    when the utterances carry explicit lengths == L."""
+    B = 3
+    rng = np.random.RandomState(L)
+    S = np.stack([O.synth_speech(L, SR, 10 + i) for i in range(B)]).astype(np.float32)
+    N = (0.05 * rng.randn(B, L)).astype(np.float32)
+    nvs = max(1, (1 + L // 160) // 20)
+    mixed, speech, noise, pcm = eng.preprocess_pairs(_dev(S), _dev(N), nvs)
+    again = eng.preprocess_pairs(_dev(S), _dev(N), nvs, lengths=_dev(np.full(B, L, np.int32)))
+    for a, b in zip((mixed, speech, noise, pcm), again):
+        assert torch.equal(a, b)
+    rec = eng.reconstruct(pcm, speech)
+    for i in range(B):
+        r_mixed, r_speech, r_noise, r_sig = O.preprocess_audio_pair_signals(O.AudioSignal(S[i].astype(np.float64), SR),
+                                                                            O.AudioSignal(N[i].astype(np.float64), SR), 200, nvs, FPS)
+        for name, got, ref in (("mixed", mixed, r_mixed), ("speech", speech, r_speech), ("noise", noise, r_noise)):
+            assert np.max(np.abs(got[i].cpu().numpy() - ref)) <= TOL_DB, (i, name)
+        full = np.max(np.abs(r_sig.get_data()))
+        assert np.max(np.abs(pcm[i].cpu().numpy() - r_sig.get_data())) <= TOL_PCM * full
+        want = O.reconstruct_speech_signal(O.AudioSignal(pcm[i].double().cpu().numpy(), SR), speech[i].double().cpu().numpy(), FPS).get_data()
+        assert np.max(np.abs(rec[i].cpu().numpy()[:len(want)] - want)) <= TOL_PCM * full, (i, "inverse")
+    # int16 input through the same groups
+    S16 = np.round(S * 20000.0).astype(np.int16)
+    N16 = np.round(N * 20000.0).astype(np.int16)
+    m16, s16, n16, p16 = eng.preprocess_pairs(_dev(S16), _dev(N16), nvs)
+    mf, sf, nf_, pf = eng.preprocess_pairs(_dev(S16.astype(np.float32)), _dev(N16.astype(np.float32)), nvs)
+    for a, b in zip((m16, s16, n16, p16), (mf, sf, nf_, pf)):
+        assert torch.equal(a, b)
