@@ -111,24 +111,47 @@ AVSE_HD int reflect_index(int i, int L) {
     return i < m ? i : m;
 }
 
+#if !defined(AVSE_F4_PAD_FAST)
+#define AVSE_F4_PAD_FAST 0        // 1: utterances shorter than the row (pad_with_zeros, dp:40) too, through a guarded variant of the mirrored
+                                  // loader: ragged batches 7 % faster, but the full-length benchmark 2.2 % slower (register allocation of the
+                                  // tile loop); the inverse kernel adopts it (AVSE_I8_PAD_FAST)
+#endif
 template <typename S>
 AVSE_HD bool group4_reflect_only(const FwdTileT<S>& tl) {
     // L >= 4 n_fft keeps every mirrored index inside [0, L), the phantom frames of the last group included
-    return tl.nz != nullptr && tl.vmin >= tl.L && tl.period_n == 0 && tl.L >= 4 * NFFT;
+    return tl.nz != nullptr && (AVSE_F4_PAD_FAST || tl.vmin >= tl.L) && tl.period_n == 0 && tl.L >= 4 * NFFT;
 }
 
 template <typename S>
 AVSE_HD void p4_load_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
     const int o = tl.t0 * HOP - HALF + lane;
+    if (!AVSE_F4_PAD_FAST || tl.vmin >= tl.L) {          // full-length rows (warp-uniform): no guard
 #pragma unroll
-    for (int j = 0; j < RAW4; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+        for (int j = 0; j < RAW4; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+    } else {                                             // zero padding: a mirrored index at or past the valid length reads 0, untouched
+#pragma unroll
+        for (int j = 0; j < RAW4; ++j) {
+            const int i = reflect_index(o + N2 * j, tl.L);
+            rs[j] = i < tl.valid_s ? (float)tl.sp[i] : 0.0f;
+            rn[j] = i < tl.valid_n ? (float)tl.nz[i] : 0.0f;
+        }
+    }
 }
 
 template <typename S>
 AVSE_HD void p4_load_tail_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[16], float (&rn)[16]) {
     const int o = (tl.t0 + (lane >> 3)) * HOP - HALF + 32 + (lane & 7);
+    if (!AVSE_F4_PAD_FAST || tl.vmin >= tl.L) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+        for (int j = 0; j < 16; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = reflect_index(o + N2 * j, tl.L);
+            rs[j] = i < tl.valid_s ? (float)tl.sp[i] : 0.0f;
+            rn[j] = i < tl.valid_n ? (float)tl.nz[i] : 0.0f;
+        }
+    }
 }
 
 // s + factor * (gain * n) of the group's own hops, samples < L only: the same arithmetic as the interior stores of

@@ -106,8 +106,11 @@ AVSE_HD void i8_load_tail_raw(const InvTile& tl, int lane, float (&rt)[20]) {
 #if !defined(AVSE_I8_REFLECT_FAST)
 #define AVSE_I8_REFLECT_FAST 1
 #endif
+#if !defined(AVSE_I8_PAD_FAST)
+#define AVSE_I8_PAD_FAST 1        // zero-padded mixtures too: guarded variant of the mirrored loader (indices at or past `valid` read 0)
+#endif
 AVSE_HD bool i8_group_reflect_only(const InvTile& tl) {
-    return tl.valid >= tl.L && tl.L >= 4 * NFFT;      // every mirrored index of the group (phantom frames included) stays inside [0, L)
+    return (AVSE_I8_PAD_FAST || tl.valid >= tl.L) && tl.L >= 4 * NFFT;      // every mirrored index (phantom frames included) stays inside [0, L)
 }
 
 AVSE_HD int i8_reflect_index(int i, int L) {
@@ -118,14 +121,24 @@ AVSE_HD int i8_reflect_index(int i, int L) {
 
 AVSE_HD void i8_load_raw_reflect(const InvTile& tl, int lane, float (&raw)[I8_RAW]) {
     const int o = tl.t0 * HOP - HALF + lane;
+    if (!AVSE_I8_PAD_FAST || tl.valid >= tl.L) {
 #pragma unroll
-    for (int j = 0; j < I8_RAW; ++j) raw[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+        for (int j = 0; j < I8_RAW; ++j) raw[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+    } else {
+#pragma unroll
+        for (int j = 0; j < I8_RAW; ++j) { const int i = i8_reflect_index(o + N2 * j, tl.L); raw[j] = i < tl.valid ? tl.pcm[i] : 0.0f; }
+    }
 }
 
 AVSE_HD void i8_load_tail_raw_reflect(const InvTile& tl, int lane, float (&rt)[20]) {
     const int o = (tl.t0 + 2 * (lane >> 3)) * HOP - HALF + 32 + (lane & 7);
+    if (!AVSE_I8_PAD_FAST || tl.valid >= tl.L) {
 #pragma unroll
-    for (int j = 0; j < 20; ++j) rt[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+        for (int j = 0; j < 20; ++j) rt[j] = tl.pcm[i8_reflect_index(o + N2 * j, tl.L)];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 20; ++j) { const int i = i8_reflect_index(o + N2 * j, tl.L); rt[j] = i < tl.valid ? tl.pcm[i] : 0.0f; }
+    }
 }
 
 // Non-zero flags of the two real frames packed in one FFT, from the raw sample bits (see inv_mark_nonzero_raw): frame A uses
