@@ -111,21 +111,20 @@ AVSE_HD int reflect_index(int i, int L) {
     return i < m ? i : m;
 }
 
-#if !defined(AVSE_F4_PAD_FAST)
-#define AVSE_F4_PAD_FAST 0        // 1: utterances shorter than the row (pad_with_zeros, dp:40) too, through a guarded variant of the mirrored
-                                  // loader: ragged batches 7 % faster, but the full-length benchmark 2.2 % slower (register allocation of the
-                                  // tile loop); the inverse kernel adopts it (AVSE_I8_PAD_FAST)
-#endif
-template <typename S>
+// PAD (template parameter of the kernel, set by the launcher when the batch carries per-utterance lengths): utterances shorter than
+// the row (pad_with_zeros, dp:40) take the fast path too, through a guarded variant of the mirrored loader -- a mirrored index at or
+// past the valid length reads 0 without touching memory.  A separate instantiation like TILED: compiled into the common kernel the
+// extra loader cost the full-length benchmark 2.2 % (register allocation of the tile loop) for 7 % on a ragged batch.
+template <typename S, bool PAD>
 AVSE_HD bool group4_reflect_only(const FwdTileT<S>& tl) {
     // L >= 4 n_fft keeps every mirrored index inside [0, L), the phantom frames of the last group included
-    return tl.nz != nullptr && (AVSE_F4_PAD_FAST || tl.vmin >= tl.L) && tl.period_n == 0 && tl.L >= 4 * NFFT;
+    return tl.nz != nullptr && (PAD || tl.vmin >= tl.L) && tl.period_n == 0 && tl.L >= 4 * NFFT;
 }
 
-template <typename S>
+template <typename S, bool PAD>
 AVSE_HD void p4_load_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[RAW4], float (&rn)[RAW4]) {
     const int o = tl.t0 * HOP - HALF + lane;
-    if (!AVSE_F4_PAD_FAST || tl.vmin >= tl.L) {          // full-length rows (warp-uniform): no guard
+    if (!PAD || tl.vmin >= tl.L) {          // full-length rows (warp-uniform): no guard
 #pragma unroll
         for (int j = 0; j < RAW4; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
     } else {                                             // zero padding: a mirrored index at or past the valid length reads 0, untouched
@@ -138,10 +137,10 @@ AVSE_HD void p4_load_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[RA
     }
 }
 
-template <typename S>
+template <typename S, bool PAD>
 AVSE_HD void p4_load_tail_raw_reflect(const FwdTileT<S>& tl, int lane, float (&rs)[16], float (&rn)[16]) {
     const int o = (tl.t0 + (lane >> 3)) * HOP - HALF + 32 + (lane & 7);
-    if (!AVSE_F4_PAD_FAST || tl.vmin >= tl.L) {
+    if (!PAD || tl.vmin >= tl.L) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const int i = reflect_index(o + N2 * j, tl.L); rs[j] = (float)tl.sp[i]; rn[j] = (float)tl.nz[i]; }
     } else {

@@ -629,7 +629,7 @@ __device__ __noinline__ void f4_fill_tables(float* smem, float* frames, const fl
 // TILED: the batch carries per-utterance noise periods (avse_forward_args::noise_period, dp:125-128).  A separate
 // instantiation, because this kernel sits on the 255-register / 32 KB instruction-cache cliff: with the period logic
 // compiled into the common kernel, batches that do not use it ran 4.5 % slower (profiles/README.md, round 2).
-template <typename S, bool TILED>
+template <typename S, bool TILED, bool PAD>
 __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -759,14 +759,14 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
     FwdTileT<S> tl = make_tile(u, g, vs, vn, factor);
     int nz_shift = 0;
     bool interior = group4_interior<S, TILED>(tl, nz_shift);
-    bool reflect = AVSE_F4_REFLECT_FAST && !TILED && !interior && group4_reflect_only(tl);   // see avse_fwd4_stages.cuh
+    bool reflect = AVSE_F4_REFLECT_FAST && !TILED && !interior && group4_reflect_only<S, PAD>(tl);   // see avse_fwd4_stages.cuh
     float rs[RAW4], rn[RAW4], ts[16], tn[16];
     if (interior) {
         p4_load_raw(tl, nz_shift, lane, rs, rn);
         p4_load_tail_raw(tl, nz_shift, lane, ts, tn);
     } else if (reflect) {
-        p4_load_raw_reflect(tl, lane, rs, rn);
-        p4_load_tail_raw_reflect(tl, lane, ts, tn);
+        p4_load_raw_reflect<S, PAD>(tl, lane, rs, rn);
+        p4_load_tail_raw_reflect<S, PAD>(tl, lane, ts, tn);
     }
 #pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
@@ -813,13 +813,13 @@ __global__ void __launch_bounds__(F4_THREADS, 1) avse_forward4_kernel(const __gr
         FwdTileT<S> tnx = make_tile(have_next ? u2 : u, have_next ? g2 : g, vs2, vn2, factor2);
         int nz_shift2 = 0;
         const bool interior2 = have_next && group4_interior<S, TILED>(tnx, nz_shift2);
-        const bool reflect2 = AVSE_F4_REFLECT_FAST && !TILED && have_next && !interior2 && group4_reflect_only(tnx);
+        const bool reflect2 = AVSE_F4_REFLECT_FAST && !TILED && have_next && !interior2 && group4_reflect_only<S, PAD>(tnx);
         if (interior2) {
             p4_load_raw(tnx, nz_shift2, lane, rs, rn);
             p4_load_tail_raw(tnx, nz_shift2, lane, ts, tn);
         } else if (reflect2) {
-            p4_load_raw_reflect(tnx, lane, rs, rn);
-            p4_load_tail_raw_reflect(tnx, lane, ts, tn);
+            p4_load_raw_reflect<S, PAD>(tnx, lane, rs, rn);
+            p4_load_tail_raw_reflect<S, PAD>(tnx, lane, ts, tn);
         }
 
         // ---- dB + stores ----
@@ -895,10 +895,12 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
     if (use_f4) {
         static thread_local int configured4_dev = -1;
         if (configured4_dev != dev) {
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(avse_forward4_kernel<short, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
             configured4_dev = dev;
         }
         P.G = (P.T + F4 - 1) / F4;
@@ -911,10 +913,15 @@ extern "C" int avse_forward(avse_ctx* ctx, const avse_forward_args* args, void* 
         P.per_warp = (int)((total4 + nwarps4 - 1) / nwarps4);
         P.split = make_warp_split(total4, blocks4, F4_WARPS);
         const bool tiled = a.noise_period != nullptr;
-        if (i16 && tiled) avse_forward4_kernel<short, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        else if (i16) avse_forward4_kernel<short, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        else if (tiled) avse_forward4_kernel<float, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        else avse_forward4_kernel<float, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        // PAD: the batch carries per-utterance lengths, so rows may be zero-padded (see avse_fwd4_stages.cuh); never together with TILED
+        const bool pad = !tiled && (a.len_speech != nullptr || a.len_noise != nullptr);
+        const cudaStream_t st4 = (cudaStream_t)stream;
+        if (i16 && tiled) avse_forward4_kernel<short, true, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
+        else if (tiled) avse_forward4_kernel<float, true, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
+        else if (i16 && pad) avse_forward4_kernel<short, false, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
+        else if (pad) avse_forward4_kernel<float, false, true><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
+        else if (i16) avse_forward4_kernel<short, false, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
+        else avse_forward4_kernel<float, false, false><<<(unsigned)blocks4, F4_THREADS, F4_SMEM_BYTES, st4>>>(P);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

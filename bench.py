@@ -578,7 +578,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "forward_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "avse_forward4_kernel<float, false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "avse_forward4_kernel<float, false, false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
                 "note": "fused FFT kernel bound by FP32 issue + the shared-memory data pipe, not by HBM; see DESIGN.md section 5 and profiles/"}

@@ -189,12 +189,12 @@ extern "C" int emul_forward4_ex(const float* speech, const float* noise, int L, 
             }
             for (int lane = 0; lane < 32; ++lane) stage4_pass1_tail(tl, nz_shift, lane, h.window.data(), s_tw, w.frames);
 #endif
-        } else if (AVSE_F4_REFLECT_FAST && tl.period_n == 0 && group4_reflect_only(tl)) {
+        } else if (AVSE_F4_REFLECT_FAST && tl.period_n == 0 && group4_reflect_only<float, true>(tl)) {
             // the kernel's reflect-only edge groups (non-tiled instantiation): mirrored loads, guarded PCM stores, interior pass 1
             FwdTileT<float> tr = tl;
             for (int lane = 0; lane < 32; ++lane) {
-                p4_load_raw_reflect(tl, lane, w.rs[lane], w.rn[lane]);
-                p4_load_tail_raw_reflect(tl, lane, w.ts[lane], w.tn[lane]);
+                p4_load_raw_reflect<float, true>(tl, lane, w.rs[lane], w.rn[lane]);
+                p4_load_tail_raw_reflect<float, true>(tl, lane, w.ts[lane], w.tn[lane]);
                 stage4_store_pcm_guarded(tl, lane, w.rs[lane], w.rn[lane], w.ts[lane], w.tn[lane]);
             }
             tr.mixed_pcm = nullptr;
